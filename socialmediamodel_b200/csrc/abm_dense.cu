@@ -1,0 +1,323 @@
+// abm_dense.cu -- K1: the ABM time-stepper for ensembles of small all-to-all populations
+// (configs C1/C2: n = 250, L = 4, M = 2).  One CTA owns one realization for the whole run:
+// positions, follower ids and media states live in shared memory, the NT-step loop runs
+// inside the kernel, and only the requested snapshots / histories go to HBM.
+//
+// Replaces the loop body abm.jl:166-213 (attraction :47-67, influence :69-88, Euler-Maruyama
+// :173, influencer/media update :175-198, reflection :139-150, changeinfluencer :90-137).
+// Bound: MUFU (2 per ordered pair: sqrt.approx + ex2.approx), not HBM -- see DESIGN.md.
+#include "abm_device.cuh"
+#include "smm_internal.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename real>
+__global__ void __launch_bounds__(kThreads) abm_dense_kernel(AbmDenseArgs A) {
+  using real2 = typename vec2<real>::type;
+  const AbmConst& K = A.k;
+  const int n = K.n, L = K.L, M = K.M, NT = A.NT;
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kThreads / 32;
+  const uint32_t rglob = (uint32_t)(A.first_realization + r);
+
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int npad = (n + 3) & ~3;
+  real2* xbuf0 = reinterpret_cast<real2*>(smem);
+  real2* xbuf1 = xbuf0 + npad;
+  double* infx = reinterpret_cast<double*>(xbuf1 + npad);  // [2][L]  (cur, nxt)
+  double* infy = infx + 2 * L;
+  double* medx = infy + 2 * L;                             // [2][M]
+  double* medy = medx + 2 * M;
+  double* frac = medy + 2 * M;                             // [L]
+  double* bsx = frac + L;                                  // [L+M] bin sums of old positions
+  double* bsy = bsx + (L + M);
+  int* bcnt = reinterpret_cast<int*>(bsy + (L + M));       // [L+M]
+  int* bss = bcnt + (L + M);                               // [L+M] sum of states per bin
+  int* fol = bss + (L + M);                                // [npad]
+  signed char* st = reinterpret_cast<signed char*>(fol + npad);  // [npad]
+
+  // ---- load the initial condition --------------------------------------------------------
+  const real* x0 = static_cast<const real*>(A.x0) + (size_t)r * 2 * n;
+  for (int j = tid; j < n; j += kThreads) {
+    xbuf0[j] = mk2(x0[j], x0[n + j]);
+    fol[j] = A.follow0[(size_t)r * n + j];
+    st[j] = A.state[(size_t)r * n + j];
+  }
+  if (tid < L) { infx[tid] = A.inf0[(size_t)r * 2 * L + tid]; infy[tid] = A.inf0[(size_t)r * 2 * L + L + tid]; }
+  if (tid < M) { medx[tid] = A.media0[(size_t)r * 2 * M + tid]; medy[tid] = A.media0[(size_t)r * 2 * M + M + tid]; }
+  __syncthreads();
+
+  int cur = 0;        // which x buffer / inf slot holds the current state
+  int next_save = 0;  // index into savesteps
+  const double sdt = sqrt(K.dt);
+  const double noise_x = sdt * K.sigma;
+
+  auto snapshot = [&](int hist_index, const real2* xc, int slot) {
+    // history entry `hist_index` (0 = initial state): abm.jl:161-164, 209-212
+    if (A.infs) {
+      double* o = A.infs + ((size_t)r * (NT + 1) + hist_index) * 2 * L;
+      if (tid < L) { o[tid] = infx[slot * L + tid]; o[L + tid] = infy[slot * L + tid]; }
+    }
+    if (A.meds) {
+      double* o = A.meds + ((size_t)r * (NT + 1) + hist_index) * 2 * M;
+      if (tid < M) { o[tid] = medx[slot * M + tid]; o[M + tid] = medy[slot * M + tid]; }
+    }
+    if (next_save < A.nsave && A.savesteps[next_save] == hist_index) {
+      size_t s = (size_t)r * A.nsave + next_save;
+      if (A.xs) {
+        real* o = static_cast<real*>(A.xs) + s * 2 * n;
+        for (int j = tid; j < n; j += kThreads) { real2 p = xc[j]; o[j] = p.x; o[n + j] = p.y; }
+      }
+      if (A.follows)
+        for (int j = tid; j < n; j += kThreads) A.follows[s * n + j] = fol[j];
+      if (A.ys && tid < L) {  // Julia ys[2,L,sp,R] (ensemble.jl:39)
+        A.ys[(s * L + tid) * 2 + 0] = infx[slot * L + tid];
+        A.ys[(s * L + tid) * 2 + 1] = infy[slot * L + tid];
+      }
+      if (A.zs && tid < M) {  // Julia zs[2,2,sp,R] (ensemble.jl:41)
+        A.zs[(s * M + tid) * 2 + 0] = medx[slot * M + tid];
+        A.zs[(s * M + tid) * 2 + 1] = medy[slot * M + tid];
+      }
+      next_save++;
+    }
+  };
+
+  // bin sums over the current followers: bins 0..L-1 by influencer, L..L+M-1 by medium
+  auto bin_sums = [&](const real2* xc) {
+    for (int bin = warp; bin < L + M; bin += nwarps) {
+      double sx = 0.0, sy = 0.0;
+      int c = 0, ss = 0;
+      for (int a = lane; a < n; a += 32) {
+        int s = st[a];
+        bool in = bin < L ? (fol[a] == bin) : (s == (bin == L ? -1 : 1));
+        if (in) { real2 p = xc[a]; sx += (double)p.x; sy += (double)p.y; c++; ss += s; }
+      }
+      sx = warp_sum(sx); sy = warp_sum(sy); c = warp_sum(c); ss = warp_sum(ss);
+      if (lane == 0) { bsx[bin] = sx; bsy[bin] = sy; bcnt[bin] = c; bss[bin] = ss; }
+    }
+  };
+  auto add_numbers = [&](int hist_index) {
+    // plotting.jl:284-307: numbers[t,i,j] = #agents with medium i following influencer j
+    if (A.numbers && tid < L * M) {
+      int j = tid / M, i = tid % M;
+      int c = bcnt[j], ss = bss[j];
+      int v = i == 1 ? (c + ss) / 2 : (c - ss) / 2;
+      atomicAdd(reinterpret_cast<unsigned long long*>(A.numbers) + ((size_t)hist_index * L + j) * M + i,
+                (unsigned long long)v);
+    }
+  };
+
+  snapshot(0, xbuf0, 0);
+
+  for (int k = 0; k < NT; k++) {
+    const real2* xc = cur ? xbuf1 : xbuf0;
+    real2* xn = cur ? xbuf0 : xbuf1;
+    const int nxt = cur ^ 1;
+
+    // ---- P1: S_i, cnt_i, state sums of the OLD positions / followers (abm.jl:96-100,179-180,188-191)
+    bin_sums(xc);
+    __syncthreads();
+    add_numbers(k);
+
+    // ---- P2: influencer / media update from OLD x, OLD followers (abm.jl:175-198), reflect (:202-203)
+    if (tid < L + M) {
+      const bool is_inf = tid < L;
+      const int e = is_inf ? tid : tid - L;
+      double px = is_inf ? infx[cur * L + e] : medx[cur * M + e];
+      double py = is_inf ? infy[cur * L + e] : medy[cur * M + e];
+      const double fr = is_inf ? K.frictionI : K.frictionM;
+      const double sg = is_inf ? K.sigmahat : K.sigmatilde;
+      double z0 = 0.0, z1 = 0.0;
+      if (sg != 0.0) {
+        if (A.noise_mode == SMM_NOISE_INJECTED) {
+          const double* zp = is_inf ? A.xi_inf : A.xi_med;
+          if (zp) {
+            size_t o = (((size_t)r * NT + k) * (is_inf ? L : M) + e) * 2;
+            z0 = zp[o]; z1 = zp[o + 1];
+          }
+        } else {
+          float f0, f1;
+          entity_draws(A.seed, (uint32_t)tid, (uint32_t)k, rglob, f0, f1);
+          z0 = f0; z1 = f1;
+        }
+      }
+      const double nz = 1.0 / fr * sdt * sg;
+      const int cnt = bcnt[tid];
+      if (cnt > 0) {
+        double mcx = bsx[tid] / (double)cnt, mcy = bsy[tid] / (double)cnt;
+        px = px + K.dt / fr * (mcx - px) + nz * z0;
+        py = py + K.dt / fr * (mcy - py) + nz * z1;
+      } else {
+        px = px + nz * z0;
+        py = py + nz * z1;
+      }
+      px = reflect1(px, K.lo0, K.hi0);
+      py = reflect1(py, K.lo1, K.hi1);
+      if (is_inf) {
+        infx[nxt * L + e] = px; infy[nxt * L + e] = py;
+        frac[e] = (double)bss[e] / (double)cnt;  // abm.jl:99; 0/0 = NaN (Q5)
+      } else {
+        medx[nxt * M + e] = px; medy[nxt * M + e] = py;
+      }
+    }
+    __syncthreads();
+
+    // ---- P3: per agent: attraction over all agents, influence, Euler-Maruyama, switch
+    for (int j = tid; j < n; j += kThreads) {
+      const real2 xj = xc[j];
+      real ax = 0, ay = 0, ws = 0;
+      if (A.rowptr == nullptr) {
+#pragma unroll 8
+        for (int i = 0; i < n; i++) {  // abm.jl:57-62; every lane reads the same address: smem broadcast
+          real2 p = xc[i];
+          real dx = p.x - xj.x, dy = p.y - xj.y;
+          real w = w_of_r2(dx * dx + dy * dy);
+          ws += w;
+          ax += w * dx;
+          ay += w * dy;
+        }
+      } else {  // sparse follower network shared by the realizations (row j of IndNet, abm.jl:51)
+        for (int e = A.rowptr[j]; e < A.rowptr[j + 1]; e++) {
+          real2 p = xc[A.colidx[e]];
+          real dx = p.x - xj.x, dy = p.y - xj.y;
+          real w = w_of_r2(dx * dx + dy * dy);
+          ws += w;
+          ax += w * dx;
+          ay += w * dy;
+        }
+        if (ws == (real)0) ws = (real)1;  // no neighbours: zero force (abm.jl:52-53)
+      }
+      const int sj = st[j], fj = fol[j];
+      const double x = (double)xj.x, y = (double)xj.y;
+      const int mrow = sj == 1 ? 1 : 0;  // abm.jl:74-78
+      double fx = K.a * (double)(ax / ws) + K.c * (medx[cur * M + mrow] - x) + K.b * (infx[cur * L + fj] - x);
+      double fy = K.a * (double)(ay / ws) + K.c * (medy[cur * M + mrow] - y) + K.b * (infy[cur * L + fj] - y);
+      double xi0, xi1, u1, u2;
+      if (A.noise_mode == SMM_NOISE_INJECTED) {
+        size_t o = ((size_t)r * NT + k);
+        const real* xp = static_cast<const real*>(A.xi) + o * 2 * n;
+        xi0 = (double)xp[j]; xi1 = (double)xp[n + j];
+        u1 = A.u1[o * n + j]; u2 = A.u2[o * n + j];
+      } else {
+        float f0, f1, g1, g2;
+        agent_draws(A.seed, (uint32_t)j, (uint32_t)k, rglob, f0, f1, g1, g2);
+        xi0 = f0; xi1 = f1; u1 = g1; u2 = g2;
+      }
+      double xn0 = x + K.dt * fx + noise_x * xi0;  // abm.jl:173
+      double xn1 = y + K.dt * fy + noise_x * xi1;
+      xn0 = reflect1(xn0, K.lo0, K.hi0);           // abm.jl:201
+      xn1 = reflect1(xn1, K.lo1, K.hi1);
+      // abm.jl:207: OLD x, OLD follower fractions, UPDATED influencers (Q1)
+      int fnew = switch_decision_f64(x, y, sj, fj, infx + nxt * L, infy + nxt * L, frac, L, K.eta, K.dt, u1, u2);
+      xn[j] = mk2((real)xn0, (real)xn1);
+      fol[j] = fnew;  // only this thread reads fol[j] during P3
+    }
+    __syncthreads();
+    cur = nxt;
+    snapshot(k + 1, xn, cur);
+  }
+  if (A.numbers) {
+    bin_sums(cur ? xbuf1 : xbuf0);
+    __syncthreads();
+    add_numbers(NT);
+  }
+}
+
+// ABMinit on the device (abm.jl:8-45).  One CTA per realization.
+template <typename real>
+__global__ void __launch_bounds__(kThreads) abm_init_kernel(AbmInitArgs A) {
+  const int n = A.k.n, L = A.k.L, M = A.k.M;
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kThreads / 32;
+  const uint32_t rglob = (uint32_t)(A.first_realization + r);
+  real* x0 = static_cast<real*>(A.x0) + (size_t)r * 2 * n;
+  const int g = A.cells;  // L = g*g
+  for (int j = tid; j < n; j += kThreads) {
+    uint4 b = philox4x32_10(make_uint4((uint32_t)j, 0u, SMM_STREAM_INIT, rglob),
+                            make_uint2((uint32_t)A.seed, (uint32_t)(A.seed >> 32)));
+    // abm.jl:16: rand(n,2).*(domain[1,2]-domain[1,1]) .+ domain[1,1]  (row 1 of the domain for both coordinates)
+    double w = A.k.hi0 - A.k.lo0;
+    real x = (real)((double)u24(b.x) * w + A.k.lo0);
+    real y = (real)((double)u24(b.y) * w + A.k.lo0);
+    x0[j] = x; x0[n + j] = y;
+    A.state[(size_t)r * n + j] = (u24(b.z) > 0.5f) ? 1 : -1;  // abm.jl:39
+    int f;
+    if (g == 2) {  // abm.jl:21-24: 1:(+,+) 2:(<=0,+) 3:(+,<=0) 4:(<=0,<=0)
+      f = (y > 0) ? ((x > 0) ? 0 : 1) : ((x > 0) ? 2 : 3);
+    } else {       // g x g partition of the domain (C5: L = 64), row-major in (y cell, x cell)
+      int cx = min(g - 1, max(0, (int)floor(((double)x - A.k.lo0) / w * g)));
+      int cy = min(g - 1, max(0, (int)floor(((double)y - A.k.lo0) / w * g)));
+      f = cy * g + cx;
+    }
+    A.follow0[(size_t)r * n + j] = f;
+  }
+  __syncthreads();
+  // abm.jl:33-36: influencer = mean of its followers (NaN if none)
+  for (int i = warp; i < L; i += nwarps) {
+    double sx = 0, sy = 0; int c = 0;
+    for (int a = lane; a < n; a += 32)
+      if (A.follow0[(size_t)r * n + a] == i) { sx += (double)x0[a]; sy += (double)x0[n + a]; c++; }
+    sx = warp_sum(sx); sy = warp_sum(sy); c = warp_sum(c);
+    if (lane == 0) {
+      A.inf0[(size_t)r * 2 * L + i] = sx / (double)c;
+      A.inf0[(size_t)r * 2 * L + L + i] = sy / (double)c;
+    }
+  }
+  if (tid < M) {  // abm.jl:18: media = [-1 -1; 1 1]
+    A.media0[(size_t)r * 2 * M + tid] = tid == 0 ? -1.0 : 1.0;
+    A.media0[(size_t)r * 2 * M + M + tid] = tid == 0 ? -1.0 : 1.0;
+  }
+}
+
+__global__ void abm_draws_kernel(int n, uint64_t seed, uint32_t realization, int NT, double* xi, double* u1, double* u2) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n * NT) return;
+  int k = (int)(t / n), j = (int)(t % n);
+  float a, b, c, d;
+  agent_draws(seed, (uint32_t)j, (uint32_t)k, realization, a, b, c, d);
+  xi[((size_t)k * 2 + 0) * n + j] = a;
+  xi[((size_t)k * 2 + 1) * n + j] = b;
+  u1[t] = c;
+  u2[t] = d;
+}
+
+size_t dense_smem_bytes(int n, int L, int M, size_t real_size) {
+  int npad = (n + 3) & ~3;
+  return 2 * (size_t)npad * 2 * real_size + sizeof(double) * (4 * L + 4 * M + L + 2 * (L + M)) +
+         sizeof(int) * (2 * (L + M) + npad) + npad + 16;
+}
+
+}  // namespace
+
+int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
+  size_t sm = dense_smem_bytes(A.k.n, A.k.L, A.k.M, precision == SMM_PREC_F64 ? 8 : 4);
+  SMM_REQUIRE(ctx, sm <= 227 * 1024, "dense ABM kernel: n=%d does not fit shared memory (%zu B); pass a CSR network", A.k.n, sm);
+  SMM_REQUIRE(ctx, A.k.L + A.k.M <= kThreads && A.k.L * A.k.M <= kThreads, "dense ABM kernel: L+M and L*M must be <= %d", kThreads);
+  if (precision == SMM_PREC_F64) {
+    SMM_CUDA(ctx, cudaFuncSetAttribute(abm_dense_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    abm_dense_kernel<double><<<A.R, kThreads, sm, ctx->stream>>>(A);
+  } else {
+    SMM_CUDA(ctx, cudaFuncSetAttribute(abm_dense_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    abm_dense_kernel<float><<<A.R, kThreads, sm, ctx->stream>>>(A);
+  }
+  ctx->launches++;
+  SMM_CUDA(ctx, cudaGetLastError());
+  return SMM_OK;
+}
+
+int smm_launch_abm_init(smm_ctx* ctx, const AbmInitArgs& A, int R, int precision) {
+  if (precision == SMM_PREC_F64) abm_init_kernel<double><<<R, kThreads, 0, ctx->stream>>>(A);
+  else abm_init_kernel<float><<<R, kThreads, 0, ctx->stream>>>(A);
+  ctx->launches++;
+  SMM_CUDA(ctx, cudaGetLastError());
+  return SMM_OK;
+}
+
+int smm_launch_abm_draws(smm_ctx* ctx, int n, uint64_t seed, uint32_t realization, int NT, double* xi, double* u1, double* u2) {
+  size_t tot = (size_t)n * NT;
+  abm_draws_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(n, seed, realization, NT, xi, u1, u2);
+  ctx->launches++;
+  SMM_CUDA(ctx, cudaGetLastError());
+  return SMM_OK;
+}

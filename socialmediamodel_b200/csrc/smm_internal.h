@@ -1,0 +1,95 @@
+// smm_internal.h -- argument blocks and launchers shared between the .cu files of libsmm_b200.so
+#pragma once
+#include "smm_common.cuh"
+
+// K1 dense ensemble kernel (abm_dense.cu). All pointers are DEVICE pointers; layouts are the
+// Julia layouts documented in include/smm_b200.h with `real` = float|double for x0/xi/xs.
+struct AbmDenseArgs {
+  AbmConst k;
+  int NT, R;
+  int64_t first_realization;
+  const void* x0;           // real  [R][2][n]
+  const signed char* state; // int8  [R][n]
+  const int32_t* follow0;   // int32 [R][n]
+  const double* inf0;       // f64   [R][2][L]
+  const double* media0;     // f64   [R][2][M]
+  const int32_t* rowptr;    // CSR network shared by all realizations, or null = all-to-all
+  const int32_t* colidx;
+  int noise_mode;
+  uint64_t seed;
+  const void* xi;           // real  [R][NT][2][n]
+  const double* u1;         // f64   [R][NT][n]
+  const double* u2;
+  const double* xi_inf;     // f64   [R][NT][L][2] or null
+  const double* xi_med;     // f64   [R][NT][M][2] or null
+  int nsave;
+  const int32_t* savesteps; // device int32 [nsave]
+  void* xs;                 // real  [R][nsave][2][n]
+  int32_t* follows;         // int32 [R][nsave][n]
+  double* infs;             // f64   [R][NT+1][2][L]
+  double* meds;             // f64   [R][NT+1][2][M]
+  double* ys;               // f64   [R][nsave][L][2]
+  double* zs;               // f64   [R][nsave][M][2]
+  int64_t* numbers;         // int64 [NT+1][L][M] (atomically accumulated)
+};
+
+struct AbmInitArgs {
+  AbmConst k;
+  int cells;  // L = cells*cells
+  uint64_t seed;
+  int64_t first_realization;
+  void* x0;
+  signed char* state;
+  int32_t* follow0;
+  double* inf0;
+  double* media0;
+};
+
+int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision);
+int smm_launch_abm_init(smm_ctx* ctx, const AbmInitArgs& A, int R, int precision);
+int smm_launch_abm_draws(smm_ctx* ctx, int n, uint64_t seed, uint32_t realization, int NT, double* xi, double* u1, double* u2);
+
+// K4 KDE of snapshots (kde.cu): us[s][j][i][iy][ix] for S = R*nsave snapshots
+struct KdeArgs {
+  int n, L, S;
+  int Nx, Ny;
+  double gx0, gy0, dx, dy, sigma;
+  const void* xs;               // real [S][2][n]
+  const int32_t* follows;       // [S][n]
+  const signed char* state;     // [R][n], snapshot s belongs to realization s / nsave
+  int nsave;
+  void* us;                     // real [S][L][2][Ny][Nx]
+};
+int smm_launch_kde(smm_ctx* ctx, const KdeArgs& A, int precision);
+// K4b ensemble reduction: sum over realizations (plotting.jl:361-363 numerator), f64 output
+int smm_launch_ensemble_sum(smm_ctx* ctx, const void* us, int precision, int R, size_t per_real, double* sum_us);
+int smm_launch_small_sum(smm_ctx* ctx, const double* v, int R, int per_real, double* out);
+// element conversions
+int smm_launch_convert_f64_to_real(smm_ctx* ctx, const double* in, void* out, size_t count, int precision);
+int smm_launch_convert_real_to_f64(smm_ctx* ctx, const void* in, double* out, size_t count, int precision);
+int smm_launch_convert_i32_to_i8(smm_ctx* ctx, const int32_t* in, signed char* out, size_t count);
+
+// CSR population kernels (abm_csr.cu)
+struct smm_abm_pop {
+  AbmConst k;
+  int precision;
+  uint64_t seed;
+  int64_t step;      // number of steps taken so far
+  int has_net;       // 0 = all-to-all
+  size_t nnz;
+  double fx_scale;   // fixed-point scale of the position accumulators (power of two)
+  void* x[2];        // real2 [n], double-buffered (step parity)
+  unsigned char* follow;  // [n]
+  signed char* state;     // [n]
+  int32_t* rowptr;
+  int32_t* colidx;
+  double* ent[2];    // [2][L+M] influencer then media positions (x block, y block), double-buffered
+  long long* acc[3]; // fixed-point class sums [2L][3] = (sum x, sum y, count), 3-way rotation
+  unsigned long long* fallback_count;  // FP64 re-evaluations of the switch decision so far
+};
+int smm_launch_pop_accumulate(smm_ctx* ctx, smm_abm_pop* p, int buf, int accslot);
+int smm_launch_pop_step(smm_ctx* ctx, smm_abm_pop* p, const void* xi, const double* u1, const double* u2);
+int smm_launch_pack_xy(smm_ctx* ctx, const double* xy, void* x2, size_t n, int precision);    // [2][n] f64 -> real2[n]
+int smm_launch_unpack_xy(smm_ctx* ctx, const void* x2, double* xy, size_t n, int precision);  // real2[n] -> [2][n] f64
+int smm_launch_convert_i32_to_u8(smm_ctx* ctx, const int32_t* in, unsigned char* out, size_t count);
+int smm_launch_convert_u8_to_i32(smm_ctx* ctx, const unsigned char* in, int32_t* out, size_t count);

@@ -1,0 +1,85 @@
+"""ABMsolveensemble / PDEsolveensemble of the reference (src/ensemble.jl) on the B200 path,
+plus the ensemble statistics of plotting.jl:361-363 (means) and :284-307 (follower numbers).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from .abm import _network, _noise_struct
+from .setting import ABMconstruct, parameters
+
+
+def savetimes_abm(NT, savepoints):
+    """ensemble.jl:21 (1-based indices into xs) converted to 0-based history indices."""
+    return (np.round(np.linspace(1, NT, savepoints)).astype(np.int32) - 1).astype(np.int32)
+
+
+def abm_ensemble_raw(NT, R, *, p, q, savesteps, sigma=0.1, first_realization=0, seed=0, precision="f32",
+                     init_state=None, injected=None, network=None, want=("us", "zs", "ys", "sums", "numbers"),
+                     pinned=False, ctx=None):
+    """smm_abm_ensemble for the local shard of R realizations; Julia-shaped outputs."""
+    ctx = _lib.Context.default() if ctx is None else ctx
+    n, L, M = q.n, q.L, q.M
+    Nx, Ny = p.X.shape
+    savesteps = np.ascontiguousarray(savesteps, np.int32)
+    sp_ = len(savesteps)
+    alloc = (lambda shape, dt=np.float64: ctx.pinned_empty(shape, dt)) if pinned else \
+            (lambda shape, dt=np.float64: np.empty(shape, dt, order="F"))
+    out = {}
+    if "us" in want: out["us"] = alloc((Nx, Ny, 2, L, sp_, R))
+    if "zs" in want: out["zs"] = np.empty((2, 2, sp_, R), order="F")
+    if "ys" in want: out["ys"] = np.empty((2, L, sp_, R), order="F")
+    if "sums" in want:
+        out["sum_us"] = np.empty((Nx, Ny, 2, L, sp_), order="F")
+        out["sum_zs"] = np.empty((2, 2, sp_), order="F")
+        out["sum_ys"] = np.empty((2, L, sp_), order="F")
+    if "numbers" in want: out["numbers"] = np.empty((M, L, NT + 1), np.int64, order="F")
+    keep = []
+    if init_state is not None:
+        x0 = _lib.f_array(np.asarray(init_state["x0"], float).reshape((n, 2, R), order="F"), np.float64)
+        st = _lib.f_array(np.asarray(init_state["state"]).reshape((n, R), order="F"), np.int32)
+        f0 = _lib.f_array(np.asarray(init_state["follow0"]).reshape((n, R), order="F"), np.int32)
+        i0 = _lib.f_array(np.asarray(init_state["inf0"], float).reshape((L, 2, R), order="F"), np.float64)
+        m0 = _lib.f_array(np.asarray(init_state["media0"], float).reshape((M, 2, R), order="F"), np.float64)
+    else:
+        x0 = st = f0 = i0 = m0 = None
+    rowptr, colidx = _network(network, n)
+    ns, keep = _noise_struct(seed, injected, n, L, M, NT, R)
+    spar = _lib.make_params(q, p)
+    g = _lib.make_grid(p)
+    rc = ctx.lib.smm_abm_ensemble(ctx.h, C.byref(spar), _lib.PREC[precision], int(NT), int(R), int(first_realization),
+                                  _lib.ptr(x0), _lib.ptr(st), _lib.ptr(f0), _lib.ptr(i0), _lib.ptr(m0),
+                                  _lib.ptr(rowptr), _lib.ptr(colidx), C.byref(ns), sp_, _lib.ptr(savesteps),
+                                  float(sigma), C.byref(g), _lib.ptr(out.get("us")), _lib.ptr(out.get("zs")),
+                                  _lib.ptr(out.get("ys")), _lib.ptr(out.get("sum_us")), _lib.ptr(out.get("sum_zs")),
+                                  _lib.ptr(out.get("sum_ys")), _lib.ptr(out.get("numbers")))
+    ctx.check(rc, "smm_abm_ensemble")
+    return out
+
+
+def ABMsolveensemble(NT=200, N=10, *, savepoints=4, init="4inf", p=None, q=None, sigma=0.1, save=True,
+                     precision="f32", ctx=None):
+    """ensemble.jl:11-55: N realizations with seeds k = 1..N (ensemble.jl:25), KDE of the agents per
+    (medium, influencer) at the save points.  Returns (us, zs, ys, (p, q)) with the reference's shapes
+    us[N_x,N_y,2,L,savepoints,N], zs[2,2,savepoints,N], ys[2,L,savepoints,N].
+
+    The reference seeds realization k with Random.seed!(k); here realization k uses the Philox
+    stream (key = 0, realization = k), k = 1..N.  With save=True the arrays are written to
+    data/abm_ensemble_<init>.npz under the reference's variable names (us2, zs2, ys2; ensemble.jl:46-53)."""
+    p = ABMconstruct() if p is None else p
+    q = parameters() if q is None else q
+    out = abm_ensemble_raw(NT, N, p=p, q=q, savesteps=savetimes_abm(NT, savepoints), sigma=sigma,
+                           first_realization=1, seed=0, precision=precision, want=("us", "zs", "ys"), ctx=ctx)
+    us, zs, ys = out["us"], out["zs"], out["ys"]
+    if save:
+        os.makedirs("data", exist_ok=True)
+        np.savez(os.path.join("data", f"abm_ensemble_{init}.npz"), us2=us, zs2=zs, ys2=ys)
+    return us, zs, ys, (p, q)
+
+
+def ensemble_means(us, zs, ys):
+    """plotting.jl:361-363."""
+    N = us.shape[-1]
+    return us.sum(axis=-1) / N, zs.sum(axis=-1) / N, ys.sum(axis=-1) / N

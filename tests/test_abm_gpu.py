@@ -1,0 +1,289 @@
+"""GPU parity of the ABM kernels against the Float64 oracle, through the C ABI (ctypes).
+
+Bar (BASELINE.json north_star): discrete state (follower histories) bit-exact under identical
+injected draws; positions / influencers / media <= 1e-5 relative, per step and at final time."""
+import numpy as np
+import pytest
+
+import socialmediamodel_b200 as smm
+from oracle import abm_oracle as A
+from oracle import ensemble_oracle as E
+from oracle import philox
+
+pytestmark = pytest.mark.gpu
+
+RTOL_F32 = 1e-5     # north_star tolerance, FP32 state vs the Float64 reference
+RTOL_F64 = 1e-11
+
+
+def make_run(seed, n=250, NT=40, L=4, R=1):
+    rng = np.random.default_rng(seed)
+    runs = []
+    for _ in range(R):
+        x0 = rng.uniform(-2.2, 2.2, (n, 2))
+        state = np.where(rng.random(n) > 0.5, 1, -1)
+        follow0, inf0, media0 = A.abm_init(x0)
+        runs.append(dict(x0=x0, state=state, follow0=follow0, inf0=inf0, media0=media0,
+                         xi=rng.standard_normal((NT, n, 2)), u1=rng.random((NT, n)), u2=rng.random((NT, n))))
+    return runs
+
+
+def stack_inputs(runs):
+    init = dict(x0=np.stack([r["x0"] for r in runs], axis=-1),                       # [n,2,R]
+                state=np.stack([r["state"] for r in runs], axis=-1),
+                follow0=np.stack([r["follow0"] for r in runs], axis=-1),
+                inf0=np.stack([r["inf0"] for r in runs], axis=-1),                   # [L,2,R]
+                media0=np.stack([r["media0"] for r in runs], axis=-1))
+    inj = dict(xi=np.stack([np.transpose(r["xi"], (1, 2, 0)) for r in runs], axis=-1),   # [n,2,NT,R]
+               u1=np.stack([r["u1"].T for r in runs], axis=-1),                          # [n,NT,R]
+               u2=np.stack([r["u2"].T for r in runs], axis=-1))
+    return init, inj
+
+
+def oracle_solve(r, NT, p, q, net=None):
+    return A.abm_solve(NT, r["x0"], r["state"], r["follow0"], r["inf0"], r["media0"], r["xi"], r["u1"], r["u2"],
+                       dict(dt=p.dt, domain=p.domain), dict(q), net)
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("precision,rtol", [("f64", RTOL_F64), ("f32", RTOL_F32)])
+def test_abm_solve_injected_parity(precision, rtol):
+    NT, R = 200, 3
+    p, q = smm.ABMconstruct(), smm.parameters()
+    runs = make_run(11, NT=NT, R=R)
+    init, inj = stack_inputs(runs)
+    out = smm.abm_solve_raw(NT, p=p, q=q, R=R, precision=precision, init_state=init, injected=inj)
+    nswitch = 0
+    for k, r in enumerate(runs):
+        o = oracle_solve(r, NT, p, q)
+        xs = np.transpose(out["xs"][:, :, :, k], (2, 0, 1))
+        fol = out["follows"][:, :, k].T
+        mism = np.nonzero((fol != o["follows"]).any(axis=1))[0]
+        if precision == "f64":
+            assert mism.size == 0, f"follower history differs first at step {mism[:1]}"
+        else:
+            # FP32 positions can only flip a decision whose Float64 margin is below FP32 resolution
+            assert mism.size == 0 or o["min_margin"] < 1e-5, (mism[:3], o["min_margin"])
+        if mism.size == 0:
+            per_step = np.abs(xs - o["xs"]).max(axis=(1, 2)) / np.abs(o["xs"]).max()
+            assert per_step.max() < rtol, per_step.max()
+            assert relerr(np.transpose(out["infs"][:, :, :, k], (2, 0, 1)), o["infs"]) < rtol
+            assert relerr(np.transpose(out["meds"][:, :, :, k], (2, 0, 1)), o["meds"]) < rtol
+        nswitch += (np.diff(o["follows"], axis=0) != 0).sum()
+    assert nswitch > 100                                            # the test exercises switching
+    # follower numbers (plotting.jl:284-307), summed over realizations
+    ref = sum(A.follower_numbers(oracle_solve(r, NT, p, q)["follows"], r["state"], 4) for r in runs)
+    if precision == "f64":
+        np.testing.assert_array_equal(np.transpose(out["numbers"], (2, 0, 1)), ref)
+
+
+def test_abm_solve_reference_api_shapes_and_philox_replay():
+    """ABMsolve() with the reference signature; the Philox run is replayed in the oracle by
+    injecting the draws dumped by smm_abm_draws and the initial condition from smm_abm_init."""
+    NT = 100
+    xs, stateinfs, infs, meds, state, (p, q) = smm.ABMsolve(NT, chosenseed=7, precision="f64")
+    assert len(xs) == NT + 1 and xs[0].shape == (250, 2) and infs[0].shape == (4, 2) and meds[0].shape == (2, 2)
+    assert stateinfs[0].dtype == np.float64 and set(np.unique(stateinfs[0])) <= {1.0, 2.0, 3.0, 4.0}
+    assert set(np.unique(state)) == {-1, 1}
+    x0, st, f0, i0, m0 = smm.abm_init(q, p, seed=7, R=1)
+    np.testing.assert_array_equal(xs[0], x0[:, :, 0])
+    # integer part of the generator agrees with the CPU restatement of Philox4x32-10
+    bits = philox.raw_draws(7, 0, 0, np.arange(250), philox.STREAM_INIT)
+    np.testing.assert_allclose(x0[:, 0, 0], philox.uniform24(bits[:, 0]) * 4.4 - 2.2, rtol=0, atol=1e-15)
+    np.testing.assert_array_equal(st[:, 0], np.where(philox.uniform24(bits[:, 2]) > 0.5, 1, -1))
+    f_ref, inf_ref, med_ref = A.abm_init(x0[:, :, 0])
+    np.testing.assert_array_equal(f0[:, 0], f_ref)
+    np.testing.assert_allclose(i0[:, :, 0], inf_ref, rtol=1e-13)
+    xi, u1, u2 = smm.abm_draws(250, NT, seed=7, realization=0)
+    b = philox.raw_draws(7, 0, 3, np.arange(250))
+    np.testing.assert_array_equal(u1[:, 3], philox.uniform24(b[:, 2]))
+    np.testing.assert_array_equal(u2[:, 3], philox.uniform24(b[:, 3]))
+    assert abs(xi.mean()) < 0.02 and abs(xi.std() - 1) < 0.02
+    r = dict(x0=x0[:, :, 0], state=st[:, 0], follow0=f0[:, 0], inf0=i0[:, :, 0], media0=m0[:, :, 0],
+             xi=np.transpose(xi, (2, 0, 1)), u1=u1.T, u2=u2.T)
+    o = oracle_solve(r, NT, p, q)
+    np.testing.assert_array_equal(np.array(stateinfs) - 1, o["follows"])
+    assert relerr(np.array(xs), o["xs"]) < RTOL_F64
+    # FP32 run of the same seed stays within the north-star tolerance
+    xs32, si32, *_ = smm.ABMsolve(NT, chosenseed=7, precision="f32")
+    if np.array_equal(np.array(si32) - 1, o["follows"]):
+        assert relerr(np.array(xs32), o["xs"]) < RTOL_F32
+
+
+def test_abm_edge_cases():
+    p = smm.ABMconstruct()
+    # NaN lock (Q5): an influencer without followers freezes all switching
+    q = smm.parameters(n=64)
+    r = make_run(5, n=64, NT=10)[0]
+    r["follow0"] = np.where(r["follow0"] == 2, 0, r["follow0"])
+    init, inj = stack_inputs([r])
+    out = smm.abm_solve_raw(10, p=p, q=q, precision="f64", init_state=init, injected=inj)
+    assert (out["follows"][:, :, 0] == r["follow0"][:, None]).all()
+    o = oracle_solve(r, 10, p, q)
+    np.testing.assert_array_equal(out["follows"][:, :, 0].T, o["follows"])
+    assert relerr(np.transpose(out["xs"][:, :, :, 0], (2, 0, 1)), o["xs"]) < RTOL_F64
+    # frozen dynamics (invariant 5)
+    q0 = smm.parameters(n=64, a=0.0, b=0.0, c=0.0, sigma=0.0, eta=0.0)
+    out = smm.abm_solve_raw(10, p=p, q=q0, precision="f32", init_state=init, injected=inj)
+    assert np.abs(out["xs"][:, :, -1, 0] - out["xs"][:, :, 0, 0]).max() == 0
+    # n = 1 (only the self-neighbour) and NT = 0
+    q1 = smm.parameters(n=1)
+    r1 = dict(x0=np.array([[0.5, -0.25]]), state=np.array([1]), follow0=np.array([0]),
+              inf0=np.array([[0.5, -0.25], [np.nan] * 2, [np.nan] * 2, [np.nan] * 2]), media0=np.array([[-1.0, -1], [1, 1]]),
+              xi=np.zeros((3, 1, 2)), u1=np.full((3, 1), 0.9), u2=np.full((3, 1), 0.5))
+    init1, inj1 = stack_inputs([r1])
+    out = smm.abm_solve_raw(3, p=p, q=q1, precision="f64", init_state=init1, injected=inj1)
+    o = oracle_solve(r1, 3, p, q1)
+    np.testing.assert_allclose(np.transpose(out["xs"][:, :, :, 0], (2, 0, 1)), o["xs"], rtol=1e-13)
+    out0 = smm.abm_solve_raw(0, p=p, q=q, precision="f32", init_state=init, injected=None)
+    assert out0["xs"].shape == (64, 2, 1, 1)
+    # bad arguments are reported, not crashed on
+    with pytest.raises(smm.SmmError, match="follow0"):
+        bad = dict(init); bad["follow0"] = init["follow0"] + 4
+        smm.abm_solve_raw(2, p=p, q=q, init_state=bad)
+
+
+def csr_random(n, k, rng, self_loop=True):
+    cols = np.empty((n, k + (1 if self_loop else 0)), np.int32)
+    for j in range(n):
+        c = rng.choice(n - 1, size=k, replace=False)
+        c[c >= j] += 1
+        cols[j, :k] = c
+        if self_loop:
+            cols[j, k] = j
+    deg = cols.shape[1]
+    return np.arange(0, n * deg + 1, deg, dtype=np.int32), cols.reshape(-1)
+
+
+@pytest.mark.parametrize("precision,rtol", [("f64", RTOL_F64), ("f32", RTOL_F32)])
+def test_abm_sparse_network_dense_kernel(precision, rtol):
+    NT, n = 30, 200
+    p, q = smm.ABMconstruct(), smm.parameters(n=n)
+    rng = np.random.default_rng(3)
+    net = csr_random(n, 8, rng)
+    r = make_run(21, n=n, NT=NT)[0]
+    init, inj = stack_inputs([r])
+    out = smm.abm_solve_raw(NT, p=p, q=q, precision=precision, init_state=init, injected=inj, network=net)
+    o = oracle_solve(r, NT, p, q, net)
+    if precision == "f64" or o["min_margin"] > 1e-5:
+        np.testing.assert_array_equal(out["follows"][:, :, 0].T, o["follows"])
+        assert relerr(np.transpose(out["xs"][:, :, :, 0], (2, 0, 1)), o["xs"]) < rtol
+
+
+@pytest.mark.parametrize("precision,rtol", [("f64", RTOL_F64), ("f32", RTOL_F32)])
+@pytest.mark.parametrize("L", [4, 16])
+def test_population_kernel_parity(precision, rtol, L):
+    """The HBM-resident population kernels (C5 path) at a size the oracle finishes in seconds."""
+    NT, n = 12, 3000
+    p = smm.ABMconstruct()
+    q = smm.parameters(n=n, L=L)
+    rng = np.random.default_rng(9)
+    net = csr_random(n, 16, rng)
+    x0 = rng.uniform(-2.2, 2.2, (n, 2))
+    state = np.where(rng.random(n) > 0.5, 1, -1)
+    g = int(np.sqrt(L))
+    cx = np.minimum(g - 1, np.floor((x0[:, 0] + 2.2) / 4.4 * g).astype(int))
+    cy = np.minimum(g - 1, np.floor((x0[:, 1] + 2.2) / 4.4 * g).astype(int))
+    follow0 = cy * g + cx
+    inf0 = np.stack([x0[follow0 == i].mean(axis=0) for i in range(L)])
+    media0 = np.array([[-1.0, -1.0], [1.0, 1.0]])
+    pop = smm.ABMPopulation(q, p, x0, state, follow0, inf0, media0, net, precision=precision)
+    x, inf, media, follow = x0.copy(), inf0.copy(), media0.copy(), follow0.copy()
+    pp, qq = dict(dt=p.dt, domain=p.domain), dict(q)
+    ok = True
+    for k in range(NT):
+        xi = rng.standard_normal((n, 2)); u1 = rng.random(n); u2 = rng.random(n)
+        pop.step_injected(xi, u1, u2)
+        x, inf, media, follow, margin = A.abm_step(x, inf, media, follow, state, xi, u1, u2, pp, qq, net)
+        got = pop.read()
+        if precision == "f32" and not np.array_equal(got["follow"], follow):
+            assert np.nanmin(margin) < 1e-5
+            ok = False
+            break
+        np.testing.assert_array_equal(got["follow"], follow)
+        assert relerr(got["x"], x) < rtol
+        assert relerr(got["inf"], inf) < max(rtol, 1e-9)
+        assert relerr(got["media"], media) < max(rtol, 1e-9)
+        ref_numbers = np.array([[np.sum((follow == j) & (state == s)) for j in range(L)] for s in (-1, 1)])
+        np.testing.assert_array_equal(got["numbers"], ref_numbers)
+    pop.close()
+
+
+def test_population_philox_guard_band_matches_f64_decisions():
+    """Philox mode: the FP32 guarded decision must give the follower history of a Float64
+    evaluation from the same FP32 positions.  Checked against the oracle step by step by feeding
+    it the device's own positions (so only the decision logic is compared)."""
+    n, L, NT = 20000, 64, 5
+    p = smm.ABMconstruct()
+    q = smm.parameters(n=n, L=L)
+    rng = np.random.default_rng(2)
+    net = csr_random(n, 16, rng)
+    x0 = rng.uniform(-2.2, 2.2, (n, 2)).astype(np.float32).astype(np.float64)
+    state = np.where(rng.random(n) > 0.5, 1, -1)
+    cx = np.minimum(7, np.floor((x0[:, 0] + 2.2) / 4.4 * 8).astype(int))
+    cy = np.minimum(7, np.floor((x0[:, 1] + 2.2) / 4.4 * 8).astype(int))
+    follow0 = cy * 8 + cx
+    inf0 = np.stack([x0[follow0 == i].mean(axis=0) for i in range(L)])
+    media0 = np.array([[-1.0, -1.0], [1.0, 1.0]])
+    pop = smm.ABMPopulation(q, p, x0, state, follow0, inf0, media0, net, seed=5, precision="f32")
+    prev = dict(x=x0, follow=follow0, inf=inf0, media=media0)
+    pp, qq = dict(dt=p.dt, domain=p.domain), dict(q)
+    for k in range(NT):
+        pop.step(1)
+        got = pop.read()
+        b = philox.raw_draws(5, 0, k, np.arange(n))
+        u1, u2 = philox.uniform24(b[:, 2]), philox.uniform24(b[:, 3])
+        # oracle decision from the device's previous state (noise irrelevant for the switch)
+        _, inf_n, _, follow_n, margin = A.abm_step(prev["x"], prev["inf"], prev["media"], prev["follow"], state,
+                                                   np.zeros((n, 2)), u1, u2, pp, qq, net)
+        bad = np.nonzero(got["follow"] != follow_n)[0]
+        # influencer positions carry ~1e-12 fixed-point error, so only margins < 1e-9 may differ
+        assert bad.size == 0 or np.all(margin[bad] < 1e-9), (bad[:5], margin[bad][:5])
+        assert relerr(got["inf"], inf_n) < 1e-9
+        prev = got
+    st = pop.stats()
+    assert st["steps"] == NT and 0 < st["fp64_reevaluations"] < 0.02 * n * NT
+    pop.close()
+
+
+def test_abm_ensemble_kde_and_means():
+    NT, R, sp = 30, 6, 3
+    p, q = smm.ABMconstruct(), smm.parameters(n=120)
+    runs = make_run(31, n=120, NT=NT, R=R)
+    init, inj = stack_inputs(runs)
+    st = smm.savetimes_abm(NT, sp)
+    for precision, tol in (("f64", 1e-10), ("f32", 1e-5)):
+        out = smm.abm_ensemble_raw(NT, R, p=p, q=q, savesteps=st, precision=precision, init_state=init, injected=inj)
+        us, zs, ys, means = E.abm_ensemble(NT, runs, dict(dt=p.dt, domain=p.domain, X=p.X, Y=p.Y), dict(q), sp)
+        follow_ok = True
+        assert np.abs(out["us"] - us).max() / us.max() < tol, precision   # KDE <= 1e-5 of max
+        assert relerr(out["zs"], zs) < max(tol, 1e-9) and relerr(out["ys"], ys) < max(tol, 1e-9)
+        np.testing.assert_allclose(out["sum_us"] / R, means["av_u"], atol=tol * us.max())
+        np.testing.assert_allclose(out["sum_ys"] / R, means["av_y"], rtol=max(tol, 1e-9))
+        np.testing.assert_allclose(out["sum_zs"] / R, means["av_z"], rtol=max(tol, 1e-9))
+        assert out["numbers"].sum(axis=(0, 1)).tolist() == [R * 120] * (NT + 1)
+
+
+def test_abm_ensemble_reference_api_and_monte_carlo():
+    """ABMsolveensemble with the reference signature; ensemble statistics of the Philox run agree
+    with an oracle ensemble (independent NumPy noise) within Monte-Carlo error."""
+    NT, N = 60, 64
+    us, zs, ys, (p, q) = smm.ABMsolveensemble(NT, N, savepoints=3, save=False)
+    assert us.shape == (89, 89, 2, 4, 3, N) and zs.shape == (2, 2, 3, N) and ys.shape == (2, 4, 3, N)
+    assert np.allclose(us.sum(axis=(0, 1, 2, 3)) * p.dV, 1.0, atol=0.08)        # each snapshot integrates to ~1
+    rng = np.random.default_rng(0)
+    ys_o = []
+    pp, qq = dict(dt=p.dt, domain=p.domain), dict(q)
+    for k in range(N):
+        x0 = rng.uniform(-2.2, 2.2, (250, 2)); state = np.where(rng.random(250) > 0.5, 1, -1)
+        f0, i0, m0 = A.abm_init(x0)
+        o = A.abm_solve(NT, x0, state, f0, i0, m0, rng.standard_normal((NT, 250, 2)), rng.random((NT, 250)),
+                        rng.random((NT, 250)), pp, qq)
+        ys_o.append(o["infs"][smm.savetimes_abm(NT, 3)[-1]].T)
+    ys_o = np.array(ys_o)                                                        # [N,2,L]
+    mean_gpu, mean_o = ys[:, :, -1, :].mean(axis=-1), ys_o.mean(axis=0)
+    se = np.sqrt(ys[:, :, -1, :].var(axis=-1) / N + ys_o.var(axis=0) / N)
+    assert np.all(np.abs(mean_gpu - mean_o) < 5 * se + 1e-3), (mean_gpu, mean_o, se)
