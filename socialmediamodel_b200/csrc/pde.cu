@@ -1,0 +1,756 @@
+// pde.cu -- K5..K9: the mean-field PDE right-hand side f (pde.jl:183-268) and its fixed-step RK
+// integration for batches of independent instances.
+//
+// Per RK stage two kernels run (captured, for a whole step, in one CUDA graph):
+//   pde_conv_kernel   K6  F = (w*(x'-x)rho) / (w*rho), w(d) = exp(-|d|), as a zero-extended Toeplitz
+//                         correlation generated from the table w(|dix|,|diy|) -- K_matrix/W_matrix
+//                         (setting.jl:59, pde.jl:8-23; 1.5 GB at 89x89) are never materialised.
+//   pde_stage_kernel  K7+K5+K8+K9  per grid point, for all 2L densities: advection (pde.jl:214-217),
+//                         reaction (:220-225), diffusion + boundary flux rows (:228-234), the RK
+//                         stage/accumulator update, the density sum of the NEXT stage state, its
+//                         partial moments; the last CTA of an instance turns the moments into the
+//                         influencer/media ODE right-hand sides (:239-265), the rate factors
+//                         (pde.jl:35-47) and advances the ODE unknowns (Float64).
+// Layout in HBM: u[b][j][i][iy][ix] (= Julia u[Nx,Ny,2,L,B], x fastest), rhosum/Fx/Fy[b][iy][ix].
+#include <map>
+
+#include "smm_internal.h"
+
+namespace {
+
+constexpr int LMAX = 16;
+constexpr int BX = 32, BY = 8;  // stage-kernel CTA = 32 x 8 grid points, one warp per grid row
+
+struct PdeInst {  // per-instance constants
+  double a, b, c, eta, D, frictionI, frictionM, speed1, speed2, tgt1[2], tgt2[2];
+  int cinf[LMAX];
+  int cmed[2];
+};
+
+struct PdeCoef {  // per-instance stage data: written by the finalising CTA, read by the next stage
+  double y[LMAX][2], z[2][2];    // stage values of the ODE unknowns
+  double dy[LMAX][2], dz[2][2];  // their right-hand sides at this stage (pde.jl:239-265)
+  double R[2][LMAX];             // eta * r((m_ij - m_i'j)/(m_ij + m_i'j))  (pde.jl:43)
+};
+
+struct PdeOde {  // RK bookkeeping of the ODE unknowns
+  double yn[LMAX][2], zn[2][2], yacc[LMAX][2], zacc[2][2];
+};
+
+enum { ACC_NONE = 0, ACC_INIT = 1, ACC_ADD = 2, ACC_FINAL = 3 };
+enum { FIN_INIT = 0, FIN_STAGE = 1 };
+
+struct StageArgs {
+  int B, L, Nx, Ny;
+  double gx0, gy0, dx, dy;
+  const void* U;      // stage state being differentiated
+  const void* un;     // state at the start of the step
+  void* Uout;         // next stage state (or u_{n+1})
+  void* acc;          // RK accumulator
+  const void* Fx;
+  const void* Fy;
+  void* rhosum_out;
+  double* partials;   // [B][nblk][2L][3]
+  unsigned* counters; // [B]
+  PdeCoef* coef;
+  PdeOde* ode;
+  const PdeInst* inst;
+  double dt, A, Bc, C, bw;
+  int acc_mode, last_stage, do_moments;
+};
+
+__device__ __forceinline__ float fast_exp_neg_dist(float dx, float dy) { return w_of_r2(fmaf(dx, dx, dy * dy)); }
+__device__ __forceinline__ double fast_exp_neg_dist(double dx, double dy) { return exp(-sqrt(dx * dx + dy * dy)); }
+
+__device__ __forceinline__ double r_fun(double x) { return x > 0.1 ? x : 0.1; }  // pde.jl:26-32: r(NaN) = 0.1
+
+// Reduce the per-CTA partial moments of an instance (fixed order: deterministic), advance the ODE
+// unknowns by the stage formula, and produce the coefficients of the next right-hand side.
+__device__ void finalize_instance(const StageArgs& A, int b, int nblk, int mode, double* sm /* [2L][3] */) {
+  const int L = A.L, tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const double dV = A.dx * A.dy;
+  PdeCoef& cf = A.coef[b];
+  PdeOde& od = A.ode[b];
+  const PdeInst& in = A.inst[b];
+  if (tid < 2 * L * 3) {
+    double s = 0.0;
+    const double* p = A.partials + ((size_t)b * nblk) * (2 * L * 3) + tid;
+    for (int k = 0; k < nblk; k++) s += p[(size_t)k * (2 * L * 3)];
+    sm[tid] = s * dV;  // plane index = j*2+i; entries (mass, x-moment, y-moment)
+  }
+  __syncthreads();
+  if (tid < L + 2) {
+    const bool is_inf = tid < L;
+    const int e = is_inf ? tid : tid - L;
+    double* ys = is_inf ? cf.y[e] : cf.z[e];
+    double* dys = is_inf ? cf.dy[e] : cf.dz[e];
+    double* yn = is_inf ? od.yn[e] : od.zn[e];
+    double* ya = is_inf ? od.yacc[e] : od.zacc[e];
+    double ynew[2];
+    for (int d = 0; d < 2; d++) {
+      if (mode == FIN_INIT) {
+        ynew[d] = ys[d];
+        yn[d] = ys[d];
+      } else {
+        double out = A.A * yn[d] + A.Bc * ys[d] + A.C * A.dt * dys[d];
+        if (A.acc_mode == ACC_INIT) ya[d] = yn[d] + A.dt * A.bw * dys[d];
+        else if (A.acc_mode == ACC_ADD) ya[d] += A.dt * A.bw * dys[d];
+        else if (A.acc_mode == ACC_FINAL) out = ya[d] + A.dt * A.bw * dys[d];
+        ynew[d] = out;
+        if (A.last_stage) yn[d] = out;
+      }
+    }
+    // right-hand side of the ODE at the new stage state
+    double m = 0.0, mx = 0.0, my = 0.0;
+    if (is_inf) {  // sums over the media i of plane (e, i)
+      for (int i = 0; i < 2; i++) { m += sm[(e * 2 + i) * 3]; mx += sm[(e * 2 + i) * 3 + 1]; my += sm[(e * 2 + i) * 3 + 2]; }
+    } else {       // sums over the influencers j of plane (j, e)
+      for (int j = 0; j < L; j++) { m += sm[(j * 2 + e) * 3]; mx += sm[(j * 2 + e) * 3 + 1]; my += sm[(j * 2 + e) * 3 + 2]; }
+    }
+    const int ctrl = is_inf ? in.cinf[e] : in.cmed[e];
+    double r0, r1;
+    if (ctrl == 0 || (!is_inf && ctrl != 1)) {  // free: pde.jl:239-241, :262-264
+      const double fr = is_inf ? in.frictionI : in.frictionM;
+      r0 = 1.0 / fr * (1.0 / m * mx - ynew[0]);
+      r1 = 1.0 / fr * (1.0 / m * my - ynew[1]);
+    } else if (ctrl == 1 || (is_inf && ctrl == 3)) {  // controlled: pde.jl:243-261
+      const double* tg = ctrl == 1 ? in.tgt1 : in.tgt2;
+      const double sp = ctrl == 1 ? in.speed1 : in.speed2;
+      double d0 = tg[0] - ynew[0], d1 = tg[1] - ynew[1];
+      double nr = sqrt(d0 * d0 + d1 * d1);
+      r0 = nr > 0 ? sp * d0 / nr : 0.0;
+      r1 = nr > 0 ? sp * d1 / nr : 0.0;
+    } else {  // any other flag: the reference leaves dy unwritten; zero here
+      r0 = r1 = 0.0;
+    }
+    ys[0] = ynew[0]; ys[1] = ynew[1];
+    dys[0] = r0; dys[1] = r1;
+    if (is_inf) {  // rate factor into influencer e for each medium (pde.jl:43)
+      double m0 = sm[(e * 2 + 0) * 3], m1 = sm[(e * 2 + 1) * 3];
+      cf.R[0][e] = in.eta * r_fun((m0 - m1) / (m0 + m1));
+      cf.R[1][e] = in.eta * r_fun((m1 - m0) / (m1 + m0));
+    }
+  }
+}
+
+// CTA-level: write this CTA's partial moments, detect the last CTA of the instance, finalise.
+// part_w: per-warp partials [nwarps][2L][3] already filled (by lane 0 of each warp).
+__device__ void moments_epilogue(const StageArgs& A, int b, double* part_w, double* sm, int mode) {
+  const int L = A.L, tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nwarps = (blockDim.x * blockDim.y) / 32;
+  const int nblk = gridDim.x * gridDim.y;
+  const int blk = blockIdx.y * gridDim.x + blockIdx.x;
+  __shared__ bool is_last;
+  __syncthreads();
+  if (tid < 2 * L * 3) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; w++) s += part_w[w * (2 * L * 3) + tid];
+    A.partials[((size_t)b * nblk + blk) * (2 * L * 3) + tid] = s;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned prev = atomicAdd(&A.counters[b], 1u);
+    is_last = (prev == (unsigned)(nblk - 1));
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    finalize_instance(A, b, nblk, mode, sm);
+    if (tid == 0) A.counters[b] = 0;
+  }
+}
+
+// K5 stand-alone: density sum + moments of a state (initial state / smm_pde_rhs)
+template <typename real>
+__global__ void __launch_bounds__(BX* BY) pde_moments_kernel(StageArgs A) {
+  const int L = A.L, Nx = A.Nx, Ny = A.Ny, b = blockIdx.z;
+  const int ix = blockIdx.x * BX + threadIdx.x, iy = blockIdx.y * BY + threadIdx.y;
+  const bool in = ix < Nx && iy < Ny;
+  const int lane = threadIdx.x, warp = threadIdx.y;
+  __shared__ double part_w[BY * 2 * LMAX * 3];
+  __shared__ double sm[2 * LMAX * 3];
+  const size_t plane = (size_t)Nx * Ny;
+  const real* U = static_cast<const real*>(A.U) + (size_t)b * 2 * L * plane;
+  const real X = (real)(A.gx0 + ix * A.dx), Y = (real)(A.gy0 + iy * A.dy);
+  real rs = 0;
+  for (int pl = 0; pl < 2 * L; pl++) {
+    real v = in ? U[(size_t)pl * plane + (size_t)iy * Nx + ix] : (real)0;
+    rs += v;
+    real s0 = warp_sum(v), s1 = warp_sum(v * X);
+    if (lane == 0) {
+      double* o = part_w + (warp * 2 * L + pl) * 3;
+      o[0] = (double)s0; o[1] = (double)s1; o[2] = (double)s0 * (double)Y;
+    }
+  }
+  if (in) static_cast<real*>(A.rhosum_out)[(size_t)b * plane + (size_t)iy * Nx + ix] = rs;
+  moments_epilogue(A, b, part_w, sm, FIN_INIT);
+}
+
+// K7 fused stage kernel
+template <typename real>
+__global__ void __launch_bounds__(BX* BY) pde_stage_kernel(StageArgs A) {
+  const int L = A.L, Nx = A.Nx, Ny = A.Ny, b = blockIdx.z;
+  const int ix = blockIdx.x * BX + threadIdx.x, iy = blockIdx.y * BY + threadIdx.y;
+  const int tid = threadIdx.y * BX + threadIdx.x;
+  const bool in = ix < Nx && iy < Ny;
+  const int lane = threadIdx.x, warp = threadIdx.y;
+  __shared__ double part_w[BY * 2 * LMAX * 3];
+  __shared__ double sm[2 * LMAX * 3];
+  __shared__ real s_yx[LMAX], s_yy[LMAX], s_R[2][LMAX], s_zx[2], s_zy[2];
+  __shared__ real s_par[5];  // a, b, c, D, (unused)
+  if (tid < L) {
+    s_yx[tid] = (real)A.coef[b].y[tid][0]; s_yy[tid] = (real)A.coef[b].y[tid][1];
+    s_R[0][tid] = (real)A.coef[b].R[0][tid]; s_R[1][tid] = (real)A.coef[b].R[1][tid];
+  }
+  if (tid < 2) { s_zx[tid] = (real)A.coef[b].z[tid][0]; s_zy[tid] = (real)A.coef[b].z[tid][1]; }
+  if (tid == 0) { s_par[0] = (real)A.inst[b].a; s_par[1] = (real)A.inst[b].b; s_par[2] = (real)A.inst[b].c; s_par[3] = (real)A.inst[b].D; }
+  __syncthreads();
+  const real pa = s_par[0], pb = s_par[1], pc = s_par[2], D = s_par[3];
+  const real h = (real)A.dx, ih = (real)(1.0 / A.dx), ih2 = (real)(1.0 / (A.dx * A.dx));
+  const real Ddx = (real)((double)D / A.dx), Ddy = (real)((double)D / A.dy);  // pde.jl:231-234 (Q12)
+  const size_t plane = (size_t)Nx * Ny;
+  const int cx = min(ix, Nx - 1), cy = min(iy, Ny - 1);  // clamped so that out-of-grid lanes stay in bounds
+  const int xm_i = max(cx - 1, 0), xp_i = min(cx + 1, Nx - 1), ym_i = max(cy - 1, 0), yp_i = min(cy + 1, Ny - 1);
+  const size_t o_c = (size_t)cy * Nx + cx, o_xm = (size_t)cy * Nx + xm_i, o_xp = (size_t)cy * Nx + xp_i;
+  const size_t o_ym = (size_t)ym_i * Nx + cx, o_yp = (size_t)yp_i * Nx + cx;
+  const real X = (real)(A.gx0 + cx * A.dx), Y = (real)(A.gy0 + cy * A.dy);
+  const real* Fx = static_cast<const real*>(A.Fx) + (size_t)b * plane;
+  const real* Fy = static_cast<const real*>(A.Fy) + (size_t)b * plane;
+  const real aFx_c = pa * Fx[o_c], aFx_m = pa * Fx[o_xm], aFx_p = pa * Fx[o_xp];
+  const real aFy_c = pa * Fy[o_c], aFy_m = pa * Fy[o_ym], aFy_p = pa * Fy[o_yp];
+  const real* U = static_cast<const real*>(A.U) + (size_t)b * 2 * L * plane;
+  const real* un = static_cast<const real*>(A.un) + (size_t)b * 2 * L * plane;
+  real* Uout = static_cast<real*>(A.Uout) + (size_t)b * 2 * L * plane;
+  real* acc = A.acc ? static_cast<real*>(A.acc) + (size_t)b * 2 * L * plane : nullptr;
+
+  // pass 1: per medium, sum of densities and of rates at this grid point (pde.jl:220-225)
+  real rsum[2] = {0, 0}, gsum[2] = {0, 0};
+  for (int j = 0; j < L; j++) {
+    real E = fast_exp_neg_dist(X - s_yx[j], Y - s_yy[j]);
+    for (int i = 0; i < 2; i++) {
+      rsum[i] += U[(size_t)(j * 2 + i) * plane + o_c];
+      gsum[i] += E * s_R[i][j];
+    }
+  }
+  const real bc = pb + pc;
+  const real dtA = (real)A.A, dtB = (real)A.Bc, dtC = (real)(A.C * A.dt), dtw = (real)(A.bw * A.dt);
+  real rs_out = 0;
+  for (int j = 0; j < L; j++) {
+    const real E = fast_exp_neg_dist(X - s_yx[j], Y - s_yy[j]);
+    for (int i = 0; i < 2; i++) {
+      const size_t po = (size_t)(j * 2 + i) * plane;
+      const real c = U[po + o_c], vxm = U[po + o_xm], vxp = U[po + o_xp], vym = U[po + o_ym], vyp = U[po + o_yp];
+      // velocity = a F + b (y_j - x) + c (z_i - x)   (pde.jl:214)
+      const real bx = pb * s_yx[j] + pc * s_zx[i], by = pb * s_yy[j] + pc * s_zy[i];
+      const real fxc = c * (aFx_c + bx - bc * X), fxm = vxm * (aFx_m + bx - bc * (X - h)), fxp = vxp * (aFx_p + bx - bc * (X + h));
+      const real fyc = c * (aFy_c + by - bc * Y), fym = vym * (aFy_m + by - bc * (Y - h)), fyp = vyp * (aFy_p + by - bc * (Y + h));
+      // divergence with C (pde.jl:79-87,216-217) and diffusion with MassM (pde.jl:68-77,228); the
+      // reference builds both operators from dx and applies them in x AND y
+      real ddx, lapx, ddy, lapy, bnd = 0;
+      if (cx == 0) { ddx = (fxp - fxc) * ih; lapx = (vxp - c) * ih2; bnd -= Ddx * fxc; }
+      else if (cx == Nx - 1) { ddx = (fxc - fxm) * ih; lapx = (vxm - c) * ih2; bnd += Ddx * fxc; }
+      else { ddx = (fxp - fxm) * ((real)0.5 * ih); lapx = (vxm - (real)2 * c + vxp) * ih2; }
+      if (cy == 0) { ddy = (fyp - fyc) * ih; lapy = (vyp - c) * ih2; bnd -= Ddy * fyc; }
+      else if (cy == Ny - 1) { ddy = (fyc - fym) * ih; lapy = (vym - c) * ih2; bnd += Ddy * fyc; }
+      else { ddy = (fyp - fym) * ((real)0.5 * ih); lapy = (vym - (real)2 * c + vyp) * ih2; }
+      const real G = E * s_R[i][j];
+      const real reac = -c * (gsum[i] - G) + G * (rsum[i] - c);
+      const real k = D * (lapx + lapy) + bnd - (ddx + ddy) + reac;  // pde.jl:236
+      // RK stage update
+      real out = dtC * k;
+      if (dtA != (real)0) out += dtA * un[po + o_c];
+      if (dtB != (real)0) out += dtB * c;
+      if (A.acc_mode == ACC_INIT) { if (in) acc[po + o_c] = un[po + o_c] + dtw * k; }
+      else if (A.acc_mode == ACC_ADD) { if (in) acc[po + o_c] += dtw * k; }
+      else if (A.acc_mode == ACC_FINAL) out = acc[po + o_c] + dtw * k;
+      if (in) Uout[po + o_c] = out;
+      if (A.do_moments) {
+        const real v = in ? out : (real)0;
+        rs_out += v;
+        real s0 = warp_sum(v), s1 = warp_sum(v * X);
+        if (lane == 0) {
+          double* o = part_w + (warp * 2 * L + (j * 2 + i)) * 3;
+          o[0] = (double)s0; o[1] = (double)s1; o[2] = (double)s0 * (double)Y;
+        }
+      }
+    }
+  }
+  if (A.do_moments) {
+    if (in) static_cast<real*>(A.rhosum_out)[(size_t)b * plane + o_c] = rs_out;
+    moments_epilogue(A, b, part_w, sm, FIN_STAGE);
+  }
+}
+
+// K6 direct Toeplitz correlation.  CTA = 8x8 output points x NS input slices; wext[ady][d + Nx-1]
+// = exp(-h sqrt(d^2 + ady^2)) for d in -(Nx-1)..Nx-1 (row-extended so the index is monotone in jx).
+constexpr int CT = 8, NS = 16;
+template <typename real, bool TABLE_IN_SMEM>
+__global__ void __launch_bounds__(CT* CT* NS) pde_conv_kernel(int Nx, int Ny, double h, const real* __restrict__ wext,
+                                                               const real* __restrict__ rhosum, real* __restrict__ Fx,
+                                                               real* __restrict__ Fy) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* red = reinterpret_cast<real*>(smem_raw);      // [NS][64][3]
+  real* wsm = red + NS * CT * CT * 3;                  // [Ny][2Nx-1] when TABLE_IN_SMEM
+  const int b = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int o = tid & (CT * CT - 1), slice = tid / (CT * CT);
+  const int ix = blockIdx.x * CT + (o & (CT - 1)), iy = blockIdx.y * CT + (o / CT);
+  const int W = 2 * Nx - 1;
+  if (TABLE_IN_SMEM) {
+    for (int e = tid; e < Ny * W; e += CT * CT * NS) wsm[e] = wext[e];
+    __syncthreads();
+  }
+  const real* wt = TABLE_IN_SMEM ? wsm : wext;
+  const real* rho = rhosum + (size_t)b * Nx * Ny;
+  const int cx = min(ix, Nx - 1), cy = min(iy, Ny - 1);
+  real a0 = 0, a1 = 0, a2 = 0;
+  for (int jy = slice; jy < Ny; jy += NS) {
+    const int dyi = jy - cy;
+    const real* wrow = wt + (size_t)(dyi < 0 ? -dyi : dyi) * W + (Nx - 1 - cx);
+    const real* rrow = rho + (size_t)jy * Nx;
+    real rowsum = 0, rowx = 0;
+    real d = (real)(-cx);
+#pragma unroll 4
+    for (int jx = 0; jx < Nx; jx++) {
+      real t = wrow[jx] * rrow[jx];
+      rowsum += t;
+      rowx += t * d;
+      d += (real)1;
+    }
+    a0 += rowsum;
+    a1 += rowx;
+    a2 += rowsum * (real)dyi;
+  }
+  red[(slice * CT * CT + o) * 3 + 0] = a0;
+  red[(slice * CT * CT + o) * 3 + 1] = a1;
+  red[(slice * CT * CT + o) * 3 + 2] = a2;
+  __syncthreads();
+  if (slice == 0 && ix < Nx && iy < Ny) {
+    real s0 = 0, s1 = 0, s2 = 0;
+    for (int s = 0; s < NS; s++) {  // fixed order: deterministic
+      s0 += red[(s * CT * CT + o) * 3 + 0];
+      s1 += red[(s * CT * CT + o) * 3 + 1];
+      s2 += red[(s * CT * CT + o) * 3 + 2];
+    }
+    // pde.jl:58: force ./ norms (the dV factors cancel); K = w * (x' - x) with x' - x = h * d
+    Fx[(size_t)b * Nx * Ny + (size_t)iy * Nx + ix] = (real)h * s1 / s0;
+    Fy[(size_t)b * Nx * Ny + (size_t)iy * Nx + ix] = (real)h * s2 / s0;
+  }
+}
+
+template <typename real>
+__global__ void wext_kernel(int Nx, int Ny, double hx, double hy, real* wext) {
+  const int W = 2 * Nx - 1;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= Ny * W) return;
+  int ady = e / W, d = e - ady * W - (Nx - 1);
+  double ddx = hx * d, ddy = hy * ady;
+  wext[e] = (real)exp(-sqrt(ddx * ddx + ddy * ddy));  // pde.jl:17
+}
+
+template <typename real>
+__global__ void broadcast_kernel(real* dst, size_t per_inst, int B) {  // copy instance 0 to 1..B-1
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < per_inst; e += stride) {
+    real v = dst[e];
+    for (int b = 1; b < B; b++) dst[(size_t)b * per_inst + e] = v;
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// batch object
+// ---------------------------------------------------------------------------------------------
+struct smm_pde_batch {
+  int B, L, Nx, Ny, precision;
+  smm_grid grid;
+  size_t plane, per_inst, rs;
+  void *u, *Ua, *Ub, *acc, *rhosum, *Fx, *Fy, *wext;
+  double* partials;
+  unsigned* counters;
+  PdeCoef* coef;
+  PdeOde* ode;
+  PdeInst* inst;
+  int nbx, nby;
+  bool table_in_smem;
+  size_t conv_smem;
+  std::map<std::pair<int, double>, cudaGraphExec_t> graphs;
+  int64_t steps_taken;
+};
+
+static void pde_free(smm_pde_batch* pb) {
+  if (!pb) return;
+  void* ptrs[] = {pb->u, pb->Ua, pb->Ub, pb->acc, pb->rhosum, pb->Fx, pb->Fy, pb->wext, pb->partials, pb->counters, pb->coef, pb->ode, pb->inst};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& g : pb->graphs) cudaGraphExecDestroy(g.second);
+  delete pb;
+}
+
+static StageArgs base_args(const smm_pde_batch* pb) {
+  StageArgs A;
+  memset(&A, 0, sizeof A);
+  A.B = pb->B; A.L = pb->L; A.Nx = pb->Nx; A.Ny = pb->Ny;
+  A.gx0 = pb->grid.x0; A.gy0 = pb->grid.y0; A.dx = pb->grid.dx; A.dy = pb->grid.dy;
+  A.Fx = pb->Fx; A.Fy = pb->Fy; A.rhosum_out = pb->rhosum;
+  A.partials = pb->partials; A.counters = pb->counters; A.coef = pb->coef; A.ode = pb->ode; A.inst = pb->inst;
+  return A;
+}
+
+static int launch_moments(smm_ctx* ctx, smm_pde_batch* pb, const void* U) {
+  StageArgs A = base_args(pb);
+  A.U = U;
+  dim3 grid(pb->nbx, pb->nby, pb->B), block(BX, BY);
+  if (pb->precision == SMM_PREC_F64) pde_moments_kernel<double><<<grid, block, 0, ctx->stream>>>(A);
+  else pde_moments_kernel<float><<<grid, block, 0, ctx->stream>>>(A);
+  ctx->launches++;
+  SMM_CUDA(ctx, cudaGetLastError());
+  return SMM_OK;
+}
+
+static int launch_conv(smm_ctx* ctx, smm_pde_batch* pb) {
+  dim3 grid((pb->Nx + CT - 1) / CT, (pb->Ny + CT - 1) / CT, pb->B);
+  const int threads = CT * CT * NS;
+  const double h = pb->grid.dx;
+#define CONV(real, SM)                                                                                      \
+  pde_conv_kernel<real, SM><<<grid, threads, pb->conv_smem, ctx->stream>>>(pb->Nx, pb->Ny, h, (const real*)pb->wext, \
+                                                                          (const real*)pb->rhosum, (real*)pb->Fx, (real*)pb->Fy)
+  if (pb->precision == SMM_PREC_F64) { if (pb->table_in_smem) CONV(double, true); else CONV(double, false); }
+  else { if (pb->table_in_smem) CONV(float, true); else CONV(float, false); }
+#undef CONV
+  ctx->launches++;
+  SMM_CUDA(ctx, cudaGetLastError());
+  return SMM_OK;
+}
+
+static int launch_stage(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
+  dim3 grid(pb->nbx, pb->nby, pb->B), block(BX, BY);
+  if (pb->precision == SMM_PREC_F64) pde_stage_kernel<double><<<grid, block, 0, ctx->stream>>>(A);
+  else pde_stage_kernel<float><<<grid, block, 0, ctx->stream>>>(A);
+  ctx->launches++;
+  SMM_CUDA(ctx, cudaGetLastError());
+  return SMM_OK;
+}
+
+// one RK step = nstages x (conv, stage).  Buffer roles: u = step start / result, Ua/Ub stage states.
+static int enqueue_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, int scheme) {
+  struct St { const void* U; void* out; double A, B, C, bw; int acc; };
+  St st[4];
+  int ns = 0;
+  void *u = pb->u, *a = pb->Ua, *b = pb->Ub;
+  switch (scheme) {
+    case SMM_RK_EULER:  // one stage into Ua, then copied back (the stage reads neighbours of u)
+      st[ns++] = {u, a, 1, 0, 1, 0, ACC_NONE};
+      break;
+    case SMM_RK_HEUN:
+      st[ns++] = {u, a, 1, 0, 1, 0.5, ACC_INIT};
+      st[ns++] = {a, u, 0, 0, 0, 0.5, ACC_FINAL};
+      break;
+    case SMM_RK_SSPRK3:  // Shu-Osher form
+      st[ns++] = {u, a, 1, 0, 1, 0, ACC_NONE};
+      st[ns++] = {a, b, 0.75, 0.25, 0.25, 0, ACC_NONE};
+      st[ns++] = {b, u, 1.0 / 3, 2.0 / 3, 2.0 / 3, 0, ACC_NONE};
+      break;
+    case SMM_RK_RK4:
+      st[ns++] = {u, a, 1, 0, 0.5, 1.0 / 6, ACC_INIT};
+      st[ns++] = {a, b, 1, 0, 0.5, 1.0 / 3, ACC_ADD};
+      st[ns++] = {b, a, 1, 0, 1.0, 1.0 / 3, ACC_ADD};
+      st[ns++] = {a, u, 0, 0, 0, 1.0 / 6, ACC_FINAL};
+      break;
+    default:
+      return smm_fail(ctx, SMM_ERR_INVALID, "unknown RK scheme %d", scheme);
+  }
+  for (int s = 0; s < ns; s++) {
+    SMM_TRY(launch_conv(ctx, pb));
+    StageArgs A = base_args(pb);
+    A.U = st[s].U; A.un = pb->u; A.Uout = st[s].out; A.acc = pb->acc;
+    A.dt = dt; A.A = st[s].A; A.Bc = st[s].B; A.C = st[s].C; A.bw = st[s].bw; A.acc_mode = st[s].acc;
+    A.last_stage = s == ns - 1; A.do_moments = 1;
+    SMM_TRY(launch_stage(ctx, pb, A));
+  }
+  if (scheme == SMM_RK_EULER)
+    SMM_CUDA(ctx, cudaMemcpyAsync(pb->u, pb->Ua, (size_t)pb->B * pb->per_inst * pb->rs, cudaMemcpyDeviceToDevice, ctx->stream));
+  return SMM_OK;
+}
+
+static int fill_inst(smm_ctx* ctx, const smm_params* q, int B, int L, const double* cinf, const double* cmed, std::vector<PdeInst>& v) {
+  v.resize(B);
+  for (int b = 0; b < B; b++) {
+    PdeInst& I = v[b];
+    memset(&I, 0, sizeof I);
+    const smm_params& p = q[b];
+    SMM_REQUIRE(ctx, p.M == 2, "PDE: M=%d, the reference hard-wires M = 2 (pde.jl:204)", p.M);
+    I.a = p.a; I.b = p.b; I.c = p.c; I.eta = p.eta; I.D = p.sigma * p.sigma * 0.5;  // pde.jl:188
+    I.frictionI = p.frictionI; I.frictionM = p.frictionM;
+    I.speed1 = p.controlspeed1; I.speed2 = p.controlspeed2;
+    I.tgt1[0] = p.controltarget1[0]; I.tgt1[1] = p.controltarget1[1];
+    I.tgt2[0] = p.controltarget2[0]; I.tgt2[1] = p.controltarget2[1];
+    for (int j = 0; j < L; j++) I.cinf[j] = cinf ? (int)cinf[(size_t)b * L + j] : 0;
+    for (int i = 0; i < 2; i++) I.cmed[i] = cmed ? (int)cmed[(size_t)b * 2 + i] : 0;
+  }
+  return SMM_OK;
+}
+
+#define PB_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess) {                                                                           \
+      pde_free(pb);                                                                                     \
+      cudaGetLastError();                                                                               \
+      return smm_fail(ctx, e__ == cudaErrorMemoryAllocation ? SMM_ERR_NOMEM : SMM_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(e__)); \
+    }                                                                                                   \
+  } while (0)
+#define PB_TRY(expr)                                   \
+  do {                                                 \
+    int rc__ = (expr);                                 \
+    if (rc__ != SMM_OK) { pde_free(pb); return rc__; } \
+  } while (0)
+
+extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const smm_params* q, int32_t B, int32_t L,
+                                    int32_t precision, const double* controlled_inf, const double* controlled_med,
+                                    const double* u0, const double* z0, const double* y0, int32_t shared_init,
+                                    smm_pde_batch** out) {
+  SMM_REQUIRE(ctx, ctx && out, "smm_pde_batch_create: NULL argument");
+  *out = nullptr;
+  SMM_REQUIRE(ctx, grid && q && u0 && z0 && y0, "smm_pde_batch_create: NULL input");
+  SMM_REQUIRE(ctx, grid->Nx >= 2 && grid->Ny >= 2 && grid->dx > 0 && grid->dy > 0, "smm_pde_batch_create: bad grid");
+  SMM_REQUIRE(ctx, B >= 1 && L >= 1 && L <= LMAX, "smm_pde_batch_create: need B >= 1 and 1 <= L <= %d", LMAX);
+  SMM_REQUIRE(ctx, precision == SMM_PREC_F32 || precision == SMM_PREC_F64, "smm_pde_batch_create: unknown precision");
+  SMM_CUDA(ctx, cudaSetDevice(ctx->device));
+  smm_pde_batch* pb = new smm_pde_batch();
+  pb->B = B; pb->L = L; pb->Nx = grid->Nx; pb->Ny = grid->Ny; pb->precision = precision; pb->grid = *grid;
+  pb->u = pb->Ua = pb->Ub = pb->acc = pb->rhosum = pb->Fx = pb->Fy = pb->wext = nullptr;
+  pb->partials = nullptr; pb->counters = nullptr; pb->coef = nullptr; pb->ode = nullptr; pb->inst = nullptr;
+  pb->steps_taken = 0;
+  pb->rs = precision == SMM_PREC_F64 ? 8 : 4;
+  pb->plane = (size_t)grid->Nx * grid->Ny;
+  pb->per_inst = pb->plane * 2 * L;
+  pb->nbx = (grid->Nx + BX - 1) / BX; pb->nby = (grid->Ny + BY - 1) / BY;
+  const size_t state_bytes = (size_t)B * pb->per_inst * pb->rs, field_bytes = (size_t)B * pb->plane * pb->rs;
+  const size_t wcount = (size_t)grid->Ny * (2 * grid->Nx - 1);
+  std::vector<PdeInst> inst;
+  PB_TRY(fill_inst(ctx, q, B, L, controlled_inf, controlled_med, inst));
+  PB_CUDA(cudaMalloc(&pb->u, state_bytes)); PB_CUDA(cudaMalloc(&pb->Ua, state_bytes));
+  PB_CUDA(cudaMalloc(&pb->Ub, state_bytes)); PB_CUDA(cudaMalloc(&pb->acc, state_bytes));
+  PB_CUDA(cudaMalloc(&pb->rhosum, field_bytes)); PB_CUDA(cudaMalloc(&pb->Fx, field_bytes)); PB_CUDA(cudaMalloc(&pb->Fy, field_bytes));
+  PB_CUDA(cudaMalloc(&pb->wext, wcount * pb->rs));
+  PB_CUDA(cudaMalloc((void**)&pb->partials, (size_t)B * pb->nbx * pb->nby * 2 * L * 3 * 8));
+  PB_CUDA(cudaMalloc((void**)&pb->counters, (size_t)B * 4));
+  PB_CUDA(cudaMalloc((void**)&pb->coef, (size_t)B * sizeof(PdeCoef)));
+  PB_CUDA(cudaMalloc((void**)&pb->ode, (size_t)B * sizeof(PdeOde)));
+  PB_CUDA(cudaMalloc((void**)&pb->inst, (size_t)B * sizeof(PdeInst)));
+  PB_CUDA(cudaMemsetAsync(pb->counters, 0, (size_t)B * 4, ctx->stream));
+  PB_CUDA(cudaMemsetAsync(pb->ode, 0, (size_t)B * sizeof(PdeOde), ctx->stream));
+  PB_CUDA(cudaMemcpyAsync(pb->inst, inst.data(), (size_t)B * sizeof(PdeInst), cudaMemcpyHostToDevice, ctx->stream));
+  // interaction table
+  {
+    unsigned g = (unsigned)((wcount + 255) / 256);
+    if (precision == SMM_PREC_F64) wext_kernel<double><<<g, 256, 0, ctx->stream>>>(grid->Nx, grid->Ny, grid->dx, grid->dy, (double*)pb->wext);
+    else wext_kernel<float><<<g, 256, 0, ctx->stream>>>(grid->Nx, grid->Ny, grid->dx, grid->dy, (float*)pb->wext);
+    ctx->launches++;
+    PB_CUDA(cudaGetLastError());
+  }
+  const size_t red_bytes = (size_t)NS * CT * CT * 3 * pb->rs;
+  pb->table_in_smem = red_bytes + wcount * pb->rs <= 200 * 1024;
+  pb->conv_smem = red_bytes + (pb->table_in_smem ? wcount * pb->rs : 0);
+  if (pb->conv_smem > 48 * 1024) {
+    if (precision == SMM_PREC_F64) PB_CUDA(cudaFuncSetAttribute(pde_conv_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb->conv_smem));
+    else PB_CUDA(cudaFuncSetAttribute(pde_conv_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb->conv_smem));
+  }
+  // initial state: u (converted to `real`), coef.y/z
+  const int ninit = shared_init ? 1 : B;
+  {
+    void* tmp;
+    PB_TRY(smm_scratch(ctx, S_STAGE, (size_t)ninit * pb->per_inst * 8, &tmp));
+    PB_CUDA(cudaMemcpyAsync(tmp, u0, (size_t)ninit * pb->per_inst * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PB_TRY(smm_launch_convert_f64_to_real(ctx, (const double*)tmp, pb->u, (size_t)ninit * pb->per_inst, precision));
+    if (shared_init && B > 1) {
+      if (precision == SMM_PREC_F64) broadcast_kernel<double><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>((double*)pb->u, pb->per_inst, B);
+      else broadcast_kernel<float><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>((float*)pb->u, pb->per_inst, B);
+      ctx->launches++;
+      PB_CUDA(cudaGetLastError());
+    }
+  }
+  std::vector<PdeCoef> coef(B);
+  memset(coef.data(), 0, (size_t)B * sizeof(PdeCoef));
+  for (int b = 0; b < B; b++) {
+    const double* yb = y0 + (shared_init ? 0 : (size_t)b * 2 * L);
+    const double* zb = z0 + (shared_init ? 0 : (size_t)b * 4);
+    for (int j = 0; j < L; j++) { coef[b].y[j][0] = yb[j * 2]; coef[b].y[j][1] = yb[j * 2 + 1]; }  // Julia y[2,L]
+    for (int i = 0; i < 2; i++) { coef[b].z[i][0] = zb[i * 2]; coef[b].z[i][1] = zb[i * 2 + 1]; }  // Julia z[2,2]
+  }
+  PB_CUDA(cudaMemcpyAsync(pb->coef, coef.data(), (size_t)B * sizeof(PdeCoef), cudaMemcpyHostToDevice, ctx->stream));
+  PB_TRY(launch_moments(ctx, pb, pb->u));
+  PB_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = pb;
+  return SMM_OK;
+}
+
+extern "C" int smm_pde_batch_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, int32_t nsteps, int32_t scheme) {
+  SMM_REQUIRE(ctx, ctx && pb, "smm_pde_batch_step: NULL argument");
+  SMM_REQUIRE(ctx, nsteps >= 0 && dt > 0, "smm_pde_batch_step: need nsteps >= 0 and dt > 0");
+  SMM_REQUIRE(ctx, scheme >= SMM_RK_EULER && scheme <= SMM_RK_RK4, "smm_pde_batch_step: unknown scheme %d", scheme);
+  SMM_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (nsteps == 0) return SMM_OK;
+  // the kernel chain of one step is captured once per (scheme, dt) and replayed
+  auto key = std::make_pair((int)scheme, dt);
+  auto it = pb->graphs.find(key);
+  if (it == pb->graphs.end()) {
+    cudaGraph_t graph;
+    SMM_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    int64_t l0 = ctx->launches;
+    int rc = enqueue_step(ctx, pb, dt, scheme);
+    ctx->launches = l0;
+    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    if (rc != SMM_OK) { if (e == cudaSuccess) cudaGraphDestroy(graph); return rc; }
+    SMM_CUDA(ctx, e);
+    cudaGraphExec_t exec;
+    SMM_CUDA(ctx, cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    it = pb->graphs.emplace(key, exec).first;
+  }
+  const int per_step = (scheme == SMM_RK_EULER ? 1 : scheme == SMM_RK_HEUN ? 2 : scheme == SMM_RK_SSPRK3 ? 3 : 4) * 2;
+  smm_tic(ctx, SMM_K_STENCIL);
+  for (int s = 0; s < nsteps; s++) SMM_CUDA(ctx, cudaGraphLaunch(it->second, ctx->stream));
+  smm_toc(ctx, SMM_K_STENCIL);
+  ctx->launches += (int64_t)per_step * nsteps;
+  pb->steps_taken += nsteps;
+  return SMM_OK;
+}
+
+static int batch_read_ode(smm_ctx* ctx, smm_pde_batch* pb, double* z, double* y, double* dz, double* dy) {
+  std::vector<PdeCoef> coef(pb->B);
+  SMM_CUDA(ctx, cudaMemcpyAsync(coef.data(), pb->coef, (size_t)pb->B * sizeof(PdeCoef), cudaMemcpyDeviceToHost, ctx->stream));
+  SMM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  const int L = pb->L;
+  for (int b = 0; b < pb->B; b++) {
+    for (int j = 0; j < L; j++)
+      for (int d = 0; d < 2; d++) {
+        if (y) y[((size_t)b * L + j) * 2 + d] = coef[b].y[j][d];
+        if (dy) dy[((size_t)b * L + j) * 2 + d] = coef[b].dy[j][d];
+      }
+    for (int i = 0; i < 2; i++)
+      for (int d = 0; d < 2; d++) {
+        if (z) z[((size_t)b * 2 + i) * 2 + d] = coef[b].z[i][d];
+        if (dz) dz[((size_t)b * 2 + i) * 2 + d] = coef[b].dz[i][d];
+      }
+  }
+  return SMM_OK;
+}
+
+static int download_state(smm_ctx* ctx, smm_pde_batch* pb, const void* dev, double* host) {
+  const size_t count = (size_t)pb->B * pb->per_inst;
+  const void* src = dev;
+  if (pb->precision != SMM_PREC_F64) {
+    void* tmp;
+    SMM_TRY(smm_scratch(ctx, S_STAGE, count * 8, &tmp));
+    SMM_TRY(smm_launch_convert_real_to_f64(ctx, dev, (double*)tmp, count, pb->precision));
+    src = tmp;
+  }
+  SMM_CUDA(ctx, cudaMemcpyAsync(host, src, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  return SMM_OK;
+}
+
+extern "C" int smm_pde_batch_read(smm_ctx* ctx, smm_pde_batch* pb, double* u, double* z, double* y) {
+  SMM_REQUIRE(ctx, ctx && pb, "smm_pde_batch_read: NULL argument");
+  SMM_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (u) SMM_TRY(download_state(ctx, pb, pb->u, u));
+  SMM_TRY(batch_read_ode(ctx, pb, z, y, nullptr, nullptr));
+  return smm_collect_times(ctx);
+}
+
+extern "C" int smm_pde_batch_sum_dev(smm_ctx* ctx, smm_pde_batch* pb, double* sum_u_dev, double* sum_z_dev, double* sum_y_dev) {
+  SMM_REQUIRE(ctx, ctx && pb, "smm_pde_batch_sum_dev: NULL argument");
+  SMM_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (sum_u_dev) SMM_TRY(smm_launch_ensemble_sum(ctx, pb->u, pb->precision, pb->B, pb->per_inst, sum_u_dev));
+  if (sum_z_dev || sum_y_dev) {
+    // the ODE unknowns live in PdeCoef (strided); gather on the host (tiny) and upload the sums
+    std::vector<double> z((size_t)pb->B * 4), y((size_t)pb->B * 2 * pb->L);
+    SMM_TRY(batch_read_ode(ctx, pb, z.data(), y.data(), nullptr, nullptr));
+    std::vector<double> sz(4, 0.0), sy(2 * pb->L, 0.0);
+    for (int b = 0; b < pb->B; b++) {
+      for (int e = 0; e < 4; e++) sz[e] += z[(size_t)b * 4 + e];
+      for (int e = 0; e < 2 * pb->L; e++) sy[e] += y[(size_t)b * 2 * pb->L + e];
+    }
+    if (sum_z_dev) SMM_CUDA(ctx, cudaMemcpyAsync(sum_z_dev, sz.data(), 4 * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (sum_y_dev) SMM_CUDA(ctx, cudaMemcpyAsync(sum_y_dev, sy.data(), 2 * pb->L * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SMM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return SMM_OK;
+}
+
+extern "C" int smm_pde_batch_destroy(smm_ctx* ctx, smm_pde_batch* pb) {
+  SMM_REQUIRE(ctx, ctx != nullptr, "smm_pde_batch_destroy: ctx is NULL");
+  if (pb) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); pde_free(pb); }
+  return SMM_OK;
+}
+
+extern "C" int smm_pde_rhs(smm_ctx* ctx, const smm_grid* grid, const smm_params* q, int32_t B, int32_t L,
+                           int32_t precision, const double* controlled_inf, const double* controlled_med,
+                           const double* u, const double* z, const double* y, double* du, double* dz, double* dy) {
+  SMM_REQUIRE(ctx, ctx != nullptr, "smm_pde_rhs: ctx is NULL");
+  smm_pde_batch* pb = nullptr;
+  SMM_TRY(smm_pde_batch_create(ctx, grid, q, B, L, precision, controlled_inf, controlled_med, u, z, y, 0, &pb));
+  int rc = SMM_OK;
+  do {
+    smm_tic(ctx, SMM_K_CONV);
+    if ((rc = launch_conv(ctx, pb)) != SMM_OK) break;
+    smm_toc(ctx, SMM_K_CONV);
+    StageArgs A = base_args(pb);
+    A.U = pb->u; A.un = pb->u; A.Uout = pb->Ua; A.acc = nullptr;
+    A.dt = 1.0; A.A = 0; A.Bc = 0; A.C = 1.0; A.bw = 0; A.acc_mode = ACC_NONE; A.last_stage = 0; A.do_moments = 0;
+    smm_tic(ctx, SMM_K_STENCIL);
+    if ((rc = launch_stage(ctx, pb, A)) != SMM_OK) break;
+    smm_toc(ctx, SMM_K_STENCIL);
+    if (du && (rc = download_state(ctx, pb, pb->Ua, du)) != SMM_OK) break;
+    if ((rc = batch_read_ode(ctx, pb, nullptr, nullptr, dz, dy)) != SMM_OK) break;
+    smm_collect_times(ctx);
+  } while (0);
+  pde_free(pb);
+  return rc;
+}
+
+extern "C" int smm_pde_solve(smm_ctx* ctx, const smm_grid* grid, const smm_params* q, int32_t B, int32_t L,
+                             int32_t precision, const double* controlled_inf, const double* controlled_med,
+                             const double* u0, const double* z0, const double* y0, double dt, int32_t nsteps,
+                             int32_t scheme, int32_t nsave, const int32_t* savesteps, double* us, double* zs,
+                             double* ys, double* sum_us, double* sum_zs, double* sum_ys) {
+  SMM_REQUIRE(ctx, ctx != nullptr, "smm_pde_solve: ctx is NULL");
+  SMM_REQUIRE(ctx, nsteps >= 0 && dt > 0, "smm_pde_solve: need nsteps >= 0 and dt > 0");
+  SMM_REQUIRE(ctx, nsave >= 0 && (nsave == 0 || savesteps), "smm_pde_solve: savesteps missing");
+  for (int m = 0; m < nsave; m++) {
+    SMM_REQUIRE(ctx, savesteps[m] >= 0 && savesteps[m] <= nsteps, "smm_pde_solve: savesteps[%d]=%d outside 0..nsteps", m, savesteps[m]);
+    SMM_REQUIRE(ctx, m == 0 || savesteps[m] > savesteps[m - 1], "smm_pde_solve: savesteps must be strictly ascending");
+  }
+  smm_pde_batch* pb = nullptr;
+  SMM_TRY(smm_pde_batch_create(ctx, grid, q, B, L, precision, controlled_inf, controlled_med, u0, z0, y0, 0, &pb));
+  int rc = SMM_OK;
+  const size_t per = pb->per_inst;
+  std::vector<double> ubuf, zbuf((size_t)B * 4), ybuf((size_t)B * 2 * L);
+  if (us || sum_us) ubuf.resize((size_t)B * per);
+  int done = 0;
+  for (int m = 0; m <= nsave && rc == SMM_OK; m++) {
+    const int target = m < nsave ? savesteps[m] : nsteps;
+    if ((rc = smm_pde_batch_step(ctx, pb, dt, target - done, scheme)) != SMM_OK) break;
+    done = target;
+    if (m == nsave) break;
+    if ((rc = smm_pde_batch_read(ctx, pb, ubuf.empty() ? nullptr : ubuf.data(), zbuf.data(), ybuf.data())) != SMM_OK) break;
+    SMM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // scatter into the Julia layouts us[Nx,Ny,2,L,nsave,B], zs[2,2,nsave,B], ys[2,L,nsave,B]
+    for (int b = 0; b < B; b++) {
+      if (us) memcpy(us + ((size_t)b * nsave + m) * per, ubuf.data() + (size_t)b * per, per * 8);
+      if (zs) memcpy(zs + ((size_t)b * nsave + m) * 4, zbuf.data() + (size_t)b * 4, 4 * 8);
+      if (ys) memcpy(ys + ((size_t)b * nsave + m) * 2 * L, ybuf.data() + (size_t)b * 2 * L, (size_t)2 * L * 8);
+    }
+    if (sum_us) {
+      double* o = sum_us + (size_t)m * per;
+      for (size_t e = 0; e < per; e++) { double s = 0; for (int b = 0; b < B; b++) s += ubuf[(size_t)b * per + e]; o[e] = s; }
+    }
+    if (sum_zs) for (int e = 0; e < 4; e++) { double s = 0; for (int b = 0; b < B; b++) s += zbuf[(size_t)b * 4 + e]; sum_zs[(size_t)m * 4 + e] = s; }
+    if (sum_ys) for (int e = 0; e < 2 * L; e++) { double s = 0; for (int b = 0; b < B; b++) s += ybuf[(size_t)b * 2 * L + e]; sum_ys[(size_t)m * 2 * L + e] = s; }
+  }
+  if (rc == SMM_OK) { cudaStreamSynchronize(ctx->stream); smm_collect_times(ctx); }
+  pde_free(pb);
+  return rc;
+}

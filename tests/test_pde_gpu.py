@@ -1,0 +1,166 @@
+"""GPU parity of the PDE right-hand side and fixed-step integrator against the Float64 oracle,
+through the C ABI.  Bar: densities within 1e-5 (FP32 vs the reference's Float64), per evaluation
+(relative to max|du|) and at final time (relative to max|u|) against the oracle running the same
+RK tableau."""
+import numpy as np
+import pytest
+
+import socialmediamodel_b200 as smm
+from oracle import abm_oracle as A
+from oracle import pde_oracle as P
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-5
+TOL64 = 1e-11
+
+
+def oracle_p(p):
+    return P.pde_construct(dx=p.dx, dy=p.dy, domain=p.domain)
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / np.abs(b).max()
+
+
+@pytest.fixture(scope="module")
+def coarse():
+    p = smm.PDEconstructcoarse()
+    q = smm.parameters()
+    uzy0, q2 = smm.constructinitial("4inf", (p, q))
+    return p, q2, uzy0
+
+
+def perturbed_state(p, q, uzy0, seed=0):
+    rng = np.random.default_rng(seed)
+    u0, z0, y0 = uzy0.x
+    u = u0 * (1 + 0.3 * rng.random(u0.shape)) + 0.002 * rng.random(u0.shape)
+    return u, z0 + 0.1 * rng.standard_normal(z0.shape), y0 + 0.1 * rng.standard_normal(y0.shape)
+
+
+@pytest.mark.parametrize("precision,tol", [("f64", TOL64), ("f32", TOL32)])
+def test_rhs_parity_coarse(coarse, precision, tol):
+    p, q, uzy0 = coarse
+    po = oracle_p(p)
+    for u, z, y in (uzy0.x, perturbed_state(p, q, uzy0)):
+        du, dz, dy = smm.pde_rhs(u, z, y, p=p, q=q, precision=precision)
+        dur, dzr, dyr = P.rhs(u, z, y, po, dict(q))
+        assert rel(du, dur) < tol, rel(du, dur)
+        assert np.abs(dz - dzr).max() < max(tol, 1e-9) * max(np.abs(dzr).max(), 1e-3)
+        assert np.abs(dy - dyr).max() < max(tol, 1e-9) * max(np.abs(dyr).max(), 1e-3)
+
+
+def test_rhs_matches_materialised_K_matrix(coarse):
+    """The Toeplitz kernel reproduces the reference's dense K_matrix/W_matrix gemv (pde.jl:49-59)."""
+    p, q, uzy0 = coarse
+    po = P.pde_construct_coarse(materialise=True)
+    u, z, y = perturbed_state(p, q, uzy0, 3)
+    du, dz, dy = smm.pde_rhs(u, z, y, p=p, q=q, precision="f64")
+    dur, _, _ = P.rhs(u, z, y, po, dict(q), force="dense")
+    assert rel(du, dur) < 1e-10
+
+
+def test_rhs_default_grid_f32_and_reference_f_signature():
+    p = smm.PDEconstruct()
+    q = smm.parameters()
+    uzy0, q2 = smm.constructinitial("4inf", (p, q))
+    duzy = smm.ArrayPartition(*[np.zeros_like(a) for a in uzy0.x])
+    assert smm.f(duzy, uzy0, (p, q2), 0.0) is None
+    dur, dzr, dyr = P.rhs(*uzy0.x, oracle_p(p), dict(q))
+    assert rel(duzy.x[0], dur) < TOL32
+    assert abs(np.abs(dur).max() - 9.61) < 0.02                     # survey probe: max|du| = 9.61 at 89^2
+    np.testing.assert_allclose(duzy.x[1], -uzy0.x[1] / 100.0, atol=1e-7)   # dz = -z/frictionM at t = 0
+
+
+def test_rhs_controlled_L5_zero_mass_and_batch(coarse):
+    p, q, uzy0 = coarse
+    u0, z0, y0 = uzy0.x
+    u = np.concatenate([u0, np.zeros_like(u0[..., :1])], axis=3)
+    y = np.concatenate([y0, np.array([[0.2], [-0.3]])], axis=1)
+    q5 = q.merge(L=5, controlled_inf=np.array([0, 0, 0, 0, 1.0]), controlled_med=np.array([0.0, 1.0]))
+    q6 = q5.merge(controlled_inf=np.array([0, 3.0, 0, 0, 1.0]), controlled_med=np.array([0.0, 0.0]), eta=1.0, a=2.0,
+                  controltarget2=np.array([[-1.0, 0.5]]), controlspeed2=0.7)
+    po = oracle_p(p)
+    uB = np.stack([u, u * 1.1], axis=-1); zB = np.stack([z0, z0], axis=-1); yB = np.stack([y, y], axis=-1)
+    du, dz, dy = smm.pde_rhs(uB, zB, yB, p=p, q=[q5, q6], precision="f64")
+    for k, (qq, uu) in enumerate(((q5, u), (q6, u * 1.1))):
+        dur, dzr, dyr = P.rhs(uu, z0, y, po, dict(qq), qq.controlled_inf, qq.controlled_med)
+        assert rel(du[..., k], dur) < TOL64
+        np.testing.assert_allclose(dy[..., k], dyr, atol=1e-12)
+        np.testing.assert_allclose(dz[..., k], dzr, atol=1e-12)
+    assert np.isfinite(du).all()
+
+
+@pytest.mark.parametrize("scheme", ["euler", "heun", "ssprk3", "rk4"])
+def test_fixed_step_trajectory_parity_f64(coarse, scheme):
+    p, q, uzy0 = coarse
+    po = oracle_p(p)
+    u0, z0, y0 = uzy0.x
+    dt, nsteps = 1e-3, 6
+    out = smm.pde_solve_raw(p, [q], u0, z0, y0, dt=dt, nsteps=nsteps, savesteps=[0, 3, 6], scheme=scheme, precision="f64")
+    saved = P.rk_solve(u0, z0, y0, nsteps, dt, po, dict(q), scheme=scheme, save_every=3)
+    for m, (k, ur, zr, yr) in enumerate(saved):
+        assert rel(out["us"][..., m, 0], ur) < 1e-10, (scheme, k)
+        np.testing.assert_allclose(out["zs"][..., m, 0], zr, atol=1e-11)
+        np.testing.assert_allclose(out["ys"][..., m, 0], yr, atol=1e-11)
+
+
+def test_rk4_trajectory_parity_f32_and_convergence(coarse):
+    p, q, uzy0 = coarse
+    po = oracle_p(p)
+    u0, z0, y0 = uzy0.x
+    T, n = 0.05, 50
+    out = smm.pde_solve_raw(p, [q], u0, z0, y0, dt=T / n, nsteps=n, savesteps=[n], precision="f32")
+    ur, zr, yr = P.rk_solve(u0, z0, y0, n, T / n, po, dict(q))
+    assert rel(out["us"][..., 0, 0], ur) < TOL32                      # same tableau, FP32 vs Float64
+    assert np.abs(out["ys"][..., 0, 0] - yr).max() < 1e-6
+    ua, za, ya = P.adaptive_solve(u0, z0, y0, T, po, dict(q))
+    assert rel(out["us"][..., 0, 0], ua) < 5e-5                       # fixed step is converged (cf. tests/test_oracle_kats)
+
+
+def test_pdesolve_reference_api(coarse):
+    p, q, _ = coarse
+    sol, (p2, q2) = smm.PDEsolve(0.02, p=p, q=smm.parameters(), precision="f64")
+    assert sol.t[0] == 0.0 and abs(sol.t[-1] - 0.02) < 1e-15
+    assert "controlled_inf" in q2 and "controlled_med" in q2          # pde.jl:178
+    u, z, y = smm.sol2uyz(sol, 0.02)
+    assert u.shape == (47, 47, 2, 4) and z.shape == (2, 2) and y.shape == (2, 4)
+    um = sol(0.013).x[0]                                              # dense output between saved steps
+    assert np.isfinite(um).all()
+    po = oracle_p(p)
+    uzy0, _ = smm.constructinitial("4inf", (p, smm.parameters()))
+    n = len(sol.t) - 1
+    ur, _, _ = P.rk_solve(*uzy0.x, n, 0.02 / n, po, dict(smm.parameters()))
+    assert rel(u, ur) < 1e-10
+
+
+def test_pdesolveensemble_sweep_matches_single_solves(coarse):
+    p, q, _ = coarse
+    qs = [smm.parameters(a=a, eta=eta) for a, eta in ((0.5, 15.0), (2.0, 1.0), (1.0, 15.0))]
+    us, zs, ys, P_ = smm.PDEsolveensemble(0.012, 3, savepoints=3, p=p, qs=qs, save=False, dt=1e-3, precision="f64")
+    assert us.shape == (47, 47, 2, 4, 3, 3) and zs.shape == (2, 2, 3, 3) and ys.shape == (2, 4, 3, 3)
+    po = oracle_p(p)
+    uzy0, _ = smm.constructinitial("4inf", (p, qs[0]))
+    for k, qq in enumerate(qs):
+        ur, zr, yr = P.rk_solve(*uzy0.x, 12, 1e-3, po, dict(qq))
+        assert rel(us[..., 2, k], ur) < 1e-10
+        np.testing.assert_allclose(ys[..., 2, k], yr, atol=1e-11)
+    np.testing.assert_array_equal(us[..., 0, 0], uzy0.x[0])            # save point 1 is t = 0 (ensemble.jl:65)
+
+
+def test_batch_resident_and_sums(coarse):
+    import torch
+    p, q, uzy0 = coarse
+    qs = [q.merge(sigma=s) for s in (0.25, 0.5, 0.75, 1.0)]
+    pb = smm.PDEBatch(p, qs, *uzy0.x, precision="f32")
+    pb.step(5e-4, 10)
+    u, z, y = pb.read()
+    s = torch.zeros(u[..., 0].size, dtype=torch.float64, device="cuda")
+    pb.sum_dev(s.data_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(s.cpu().numpy().reshape(u[..., 0].shape, order="F"), u.sum(axis=-1), rtol=1e-12, atol=1e-12)
+    po = oracle_p(p)
+    for k in (0, 3):
+        ur, _, _ = P.rk_solve(*uzy0.x, 10, 5e-4, po, dict(qs[k]))
+        assert rel(u[..., k], ur) < TOL32
+    pb.close()
