@@ -1,0 +1,89 @@
+"""PDE workloads of bench.py (secondary lines under "workloads"): C3 = PDEsolve on the default
+89x89x2x4 grid (one instance; launch/latency-bound, reported as us per step), and a bounded
+sample of C4 = a parameter sweep of PDE instances on refined grids (HBM-bound stage kernel)."""
+import numpy as np
+
+
+def _peaks():
+    from bench import measured_peaks
+    return measured_peaks()
+
+
+def _sweep_qs(smm, B):
+    """deterministic parameter lattice of C4."""
+    qs = []
+    for a in (0.5, 1.0, 2.0, 3.0):
+        for b in (1.0, 2.0, 4.0, 6.0):
+            for c in (1.0, 2.0, 3.0, 4.0):
+                for eta in (1.0, 15.0):
+                    for sigma in (0.25, 0.5, 0.75, 1.0):
+                        qs.append(smm.parameters(a=a, b=b, c=c, eta=eta, sigma=sigma))
+    return qs[:B]
+
+
+def run_pde_c3(ctx, steps=400, dt=1e-3):
+    import socialmediamodel_b200 as smm
+    p, q = smm.PDEconstruct(), smm.parameters()
+    uzy0, q2 = smm.constructinitial("4inf", (p, q))
+    pb = smm.PDEBatch(p, [q2], *uzy0.x, precision="f32", ctx=ctx)
+    pb.step(dt, 20); ctx.sync()
+    ms = []
+    for _ in range(3):
+        pb.step(dt, steps); ctx.sync()
+        ms.append(ctx.kernel_ms(4) / steps)
+    us_step = float(np.median(ms)) * 1e3
+    u, z, y = pb.read()
+    pb.close()
+    cells = p.N_x * p.N_y * 2 * 4
+    return dict(workload="C3 PDEsolve 89x89x2x4, uniforminit, RK4 dt=1e-3, one instance, CUDA graph per step",
+                metric="pde_cell_steps_per_s", value=cells / (us_step * 1e-6), us_per_step=us_step,
+                kernels_per_step=8, mass=float(u.sum() * p.dV), finite=bool(np.isfinite(u).all()),
+                note="63 368 cells: launch/latency-bound, not HBM-bound (SURVEY 8d)")
+
+
+def run_pde_sweep(ctx, dx=0.025, B=64, steps=10, dt=None):
+    import socialmediamodel_b200 as smm
+    p = smm.PDEconstruct(dx=dx)
+    qs = _sweep_qs(smm, B)
+    uzy0, _ = smm.constructinitial("4inf", (p, qs[0]))
+    dt = dt or min(smm.default_dt(p, q) for q in qs)
+    pb = smm.PDEBatch(p, qs, *uzy0.x, precision="f32", shared_init=True, ctx=ctx)
+    pb.step(dt, 2); ctx.sync()
+    ms = []
+    for _ in range(3):
+        pb.step(dt, steps); ctx.sync()
+        ms.append(ctx.kernel_ms(4) / steps)
+    ms_step = float(np.median(ms))
+    u, z, y = pb.read(want_u=False)
+    pb.close()
+    cells = p.N_x * p.N_y * 2 * 4 * B
+    peaks = _peaks()
+    ach = cells * 76 / (ms_step * 1e-3) / 1e9          # 19 B per cell per RK stage
+    N = p.N_x * p.N_y
+    conv_fma = 3.0 * N * N * B * 4                       # direct Toeplitz: 3 N FMA per grid point per RHS
+    return dict(workload=f"C4 sample: {B} PDE instances {p.N_x}x{p.N_y}x2x4, parameter lattice, RK4 dt={dt:.2e}",
+                metric="pde_cell_steps_per_s", value=cells / (ms_step * 1e-3), ms_per_step=ms_step,
+                finite=bool(np.isfinite(y).all()),
+                roofline=dict(kernel="pde_stage_kernel<float> + pde_conv_kernel<float>", bound="hbm", achieved=ach,
+                              peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"], traffic=None,
+                              bytes_per_cell_step=76, peak_source=peaks["source"],
+                              conv_tfma_per_s=conv_fma / (ms_step * 1e-3) / 1e12,
+                              note="step time includes the direct Toeplitz convolution (FP32-pipe-bound, 37.2 TFMA/s peak)"))
+
+
+def run_pde_workloads(ctx):
+    out = {}
+    for name, fn in (("pde_C3", lambda: run_pde_c3(ctx)),
+                     ("pde_sweep_177", lambda: run_pde_sweep(ctx, dx=0.025, B=16, steps=4))):
+        try:
+            out[name] = fn()
+        except Exception as e:
+            out[name] = dict(error=f"{type(e).__name__}: {e}")
+    return out
+
+
+if __name__ == "__main__":
+    import json
+
+    import socialmediamodel_b200 as smm
+    print(json.dumps(run_pde_workloads(smm.Context.default()), indent=1))

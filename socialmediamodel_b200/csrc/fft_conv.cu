@@ -1,0 +1,336 @@
+// fft_conv.cu -- K6 (scalable form): the interaction force F = (w*(x'-x)rho)/(w*rho) of
+// pde.jl:49-59 as a zero-padded FFT correlation.  The reference multiplies by the dense
+// K_matrix/W_matrix (O(N^2) per right-hand side, 248 GB at 353x353); the operator is block
+// Toeplitz, so three P x P circular convolutions (P = pow2 >= 2N-1) give the same sums in
+// O(N log N).  Hand-written radix-2 shared-memory FFTs (no cuFFT):
+//
+//   fft_rows_fwd   two real rows per complex FFT (DIF, natural -> bit-reversed), split into the two
+//                  half spectra                                       rho[b][iy][ix] -> A[b][iy][kx]
+//   fft_cols       per group of COLS kx-columns: DIF forward over y, multiply by the three kernel
+//                  spectra (stored bit-reversed in ky, pre-scaled by 1/P^2), DIT inverse, keep
+//                  iy < Ny                                              A -> G[k][b][iy][kx], k=0..2
+//   fft_rows_inv   Hermitian-extend, two real rows per complex DIT inverse, keep ix < Nx, divide
+//                                                                        G -> Fx, Fy [b][iy][ix]
+// The kernel spectra are computed once per grid with the same kernels instantiated in Float64.
+#include "smm_internal.h"
+
+namespace {
+
+template <typename real2> __device__ __forceinline__ real2 cadd(real2 a, real2 b) { a.x += b.x; a.y += b.y; return a; }
+template <typename real2> __device__ __forceinline__ real2 csub(real2 a, real2 b) { a.x -= b.x; a.y -= b.y; return a; }
+template <typename real2> __device__ __forceinline__ real2 cmul(real2 a, real2 b) { return mk2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+template <typename real2> __device__ __forceinline__ real2 cmulc(real2 a, real2 b) { return mk2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
+
+__device__ __forceinline__ int brev_p(int i, int logP) { return (int)(__brev((unsigned)i) >> (32 - logP)); }
+
+// ncol independent length-P FFTs in shared memory (column stride cs), decimation in frequency:
+// natural-order input, bit-reversed output.  tw[k] = exp(-2 pi i k / P), k < P/2.
+template <typename real>
+__device__ void fft_dif_fwd(typename vec2<real>::type* sh, int ncol, int cs, int P, int logP,
+                            const typename vec2<real>::type* tw) {
+  using real2 = typename vec2<real>::type;
+  const int tid = threadIdx.x, nt = blockDim.x, hp = P >> 1;
+  for (int s = logP; s >= 1; s--) {
+    const int half = 1 << (s - 1), ts = P >> s;
+    for (int t = tid; t < ncol * hp; t += nt) {
+      const int c = t >> (logP - 1), bt = t & (hp - 1);
+      const int j = bt & (half - 1), i0 = ((bt >> (s - 1)) << s) + j;
+      real2* x = sh + c * cs;
+      const real2 a = x[i0], b = x[i0 + half];
+      x[i0] = cadd(a, b);
+      x[i0 + half] = cmul(csub(a, b), tw[j * ts]);
+    }
+    __syncthreads();
+  }
+}
+
+// decimation in time with conjugate twiddles: bit-reversed input, natural-order output (unscaled inverse)
+template <typename real>
+__device__ void fft_dit_inv(typename vec2<real>::type* sh, int ncol, int cs, int P, int logP,
+                            const typename vec2<real>::type* tw) {
+  using real2 = typename vec2<real>::type;
+  const int tid = threadIdx.x, nt = blockDim.x, hp = P >> 1;
+  for (int s = 1; s <= logP; s++) {
+    const int half = 1 << (s - 1), ts = P >> s;
+    for (int t = tid; t < ncol * hp; t += nt) {
+      const int c = t >> (logP - 1), bt = t & (hp - 1);
+      const int j = bt & (half - 1), i0 = ((bt >> (s - 1)) << s) + j;
+      real2* x = sh + c * cs;
+      const real2 a = x[i0], b = cmulc(x[i0 + half], tw[j * ts]);
+      x[i0] = cadd(a, b);
+      x[i0 + half] = csub(a, b);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename real>
+__global__ void twiddle_kernel(int P, typename vec2<real>::type* tw) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= P / 2) return;
+  double s, c;
+  sincospi(-2.0 * (double)k / (double)P, &s, &c);
+  tw[k] = mk2((real)c, (real)s);
+}
+
+// circular kernel images c_k[dy mod P][dx mod P] (Float64): w, -w*hx*dx, -w*hy*dy  (pde.jl:14-20 with
+// the correlation written as a convolution: out[i] = sum_j T[j-i] rho[j] = sum_j T~[i-j] rho[j])
+__global__ void kernel_image_kernel(int Nx, int Ny, int P, double hx, double hy, double* img) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)P * P) return;
+  int py = (int)(e / P), px = (int)(e % P);
+  int dy = py < P / 2 ? py : py - P, dx = px < P / 2 ? px : px - P;
+  double w = 0.0;
+  if (abs(dx) <= Nx - 1 && abs(dy) <= Ny - 1) {
+    double ddx = hx * dx, ddy = hy * dy;
+    w = exp(-sqrt(ddx * ddx + ddy * ddy));
+  }
+  img[e] = w;
+  img[(size_t)P * P + e] = -w * hx * dx;
+  img[2 * (size_t)P * P + e] = -w * hy * dy;
+}
+
+// rows forward: in[batch][nrows][rowlen] real -> out[batch][nrows][P/2+1] complex.  CTA = one row pair.
+template <typename real>
+__global__ void __launch_bounds__(256) fft_rows_fwd_kernel(int nrows, int rowlen, int P, int logP, const real* __restrict__ in,
+                                    typename vec2<real>::type* __restrict__ out,
+                                    const typename vec2<real>::type* __restrict__ twg) {
+  using real2 = typename vec2<real>::type;
+  extern __shared__ __align__(16) unsigned char smem[];
+  real2* sh = reinterpret_cast<real2*>(smem);
+  real2* tw = sh + P;
+  const int b = blockIdx.y, ra = blockIdx.x * 2, rb = ra + 1;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const real* rowa = in + ((size_t)b * nrows + ra) * rowlen;
+  const real* rowb = in + ((size_t)b * nrows + rb) * rowlen;
+  const bool hasb = rb < nrows;
+  for (int i = tid; i < P / 2; i += nt) tw[i] = twg[i];
+  for (int i = tid; i < P; i += nt) sh[i] = i < rowlen ? mk2(rowa[i], hasb ? rowb[i] : (real)0) : mk2((real)0, (real)0);
+  __syncthreads();
+  fft_dif_fwd<real>(sh, 1, P, P, logP, tw);
+  const int hp1 = P / 2 + 1;
+  real2* oa = out + ((size_t)b * nrows + ra) * hp1;
+  real2* ob = out + ((size_t)b * nrows + rb) * hp1;
+  for (int k = tid; k < hp1; k += nt) {
+    const real2 zk = sh[brev_p(k, logP)], zm = sh[brev_p((P - k) & (P - 1), logP)];
+    oa[k] = mk2((real)0.5 * (zk.x + zm.x), (real)0.5 * (zk.y - zm.y));
+    if (hasb) ob[k] = mk2((real)0.5 * (zk.y + zm.y), (real)-0.5 * (zk.x - zm.x));
+  }
+}
+
+// columns.  MODE 0: convolution (forward, x3 kernel spectra, inverse, keep iy < nkeep).
+//           MODE 1: spectrum only: out[k=blockIdx.y][kx][ky bit-reversed] scaled by `scale`.
+template <typename real, int MODE>
+__global__ void __launch_bounds__(512) fft_cols_kernel(int nrows, int nkeep, int P, int logP, int cols, double scale,
+                                const typename vec2<real>::type* __restrict__ A,
+                                const typename vec2<real>::type* __restrict__ khat,
+                                typename vec2<real>::type* __restrict__ G,
+                                const typename vec2<real>::type* __restrict__ twg, size_t gstride) {
+  using real2 = typename vec2<real>::type;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int cs = P + 1;
+  real2* R = reinterpret_cast<real2*>(smem);       // [cols][cs]
+  real2* Wk = R + (size_t)cols * cs;               // [cols][cs] (MODE 0)
+  real2* tw = MODE == 0 ? Wk + (size_t)cols * cs : Wk;
+  const int hp1 = P / 2 + 1;
+  const int b = blockIdx.y, kx0 = blockIdx.x * cols;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < P / 2; i += nt) tw[i] = twg[i];
+  const real2* Ab = A + (size_t)b * nrows * hp1;
+  for (int e = tid; e < P * cols; e += nt) {
+    const int jy = e / cols, c = e - jy * cols;
+    real2 v = mk2((real)0, (real)0);
+    if (jy < nrows && kx0 + c < hp1) v = Ab[(size_t)jy * hp1 + kx0 + c];
+    R[c * cs + jy] = v;
+  }
+  __syncthreads();
+  fft_dif_fwd<real>(R, cols, cs, P, logP, tw);
+  if (MODE == 1) {
+    for (int e = tid; e < P * cols; e += nt) {
+      const int c = e / P, i = e - c * P;
+      if (kx0 + c < hp1) {
+        real2 v = R[c * cs + i];
+        G[((size_t)b * hp1 + kx0 + c) * P + i] = mk2((real)(v.x * scale), (real)(v.y * scale));
+      }
+    }
+    return;
+  }
+  for (int k = 0; k < 3; k++) {
+    for (int e = tid; e < P * cols; e += nt) {
+      const int c = e / P, i = e - c * P;
+      real2 v = mk2((real)0, (real)0);
+      if (kx0 + c < hp1) v = cmul(R[c * cs + i], khat[((size_t)k * hp1 + kx0 + c) * P + i]);
+      Wk[c * cs + i] = v;
+    }
+    __syncthreads();
+    fft_dit_inv<real>(Wk, cols, cs, P, logP, tw);
+    real2* Gk = G + (size_t)k * gstride + (size_t)b * nkeep * hp1;
+    for (int e = tid; e < nkeep * cols; e += nt) {
+      const int iy = e / cols, c = e - iy * cols;
+      if (kx0 + c < hp1) Gk[(size_t)iy * hp1 + kx0 + c] = Wk[c * cs + iy];
+    }
+    __syncthreads();
+  }
+}
+
+// rows inverse + division: G[k][b][iy][kx] -> Fx, Fy [b][iy][ix].  CTA = one row pair, 3 FFTs.
+template <typename real>
+__global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, int P, int logP, const typename vec2<real>::type* __restrict__ G,
+                                    size_t gstride, real* __restrict__ Fx, real* __restrict__ Fy,
+                                    const typename vec2<real>::type* __restrict__ twg) {
+  using real2 = typename vec2<real>::type;
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int cs = P + 1;
+  real2* sh = reinterpret_cast<real2*>(smem);  // [3][cs]
+  real2* tw = sh + 3 * cs;
+  const int hp1 = P / 2 + 1;
+  const int b = blockIdx.y, ra = blockIdx.x * 2, rb = ra + 1;
+  const bool hasb = rb < Ny;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < P / 2; i += nt) tw[i] = twg[i];
+  for (int e = tid; e < 3 * P; e += nt) {
+    const int k = e / P, kk = e - k * P;
+    const bool up = kk > P / 2;
+    const int src = up ? P - kk : kk;
+    const real2* Gk = G + (size_t)k * gstride + (size_t)b * Ny * hp1;
+    real2 a = Gk[(size_t)ra * hp1 + src];
+    real2 bb = hasb ? Gk[(size_t)rb * hp1 + src] : mk2((real)0, (real)0);
+    if (up) { a.y = -a.y; bb.y = -bb.y; }
+    sh[k * cs + brev_p(kk, logP)] = mk2(a.x - bb.y, a.y + bb.x);  // A + i B
+  }
+  __syncthreads();
+  fft_dit_inv<real>(sh, 3, cs, P, logP, tw);
+  for (int ix = tid; ix < Nx; ix += nt) {
+    const real2 o0 = sh[ix], ox = sh[cs + ix], oy = sh[2 * cs + ix];
+    const size_t oa = ((size_t)b * Ny + ra) * Nx + ix;
+    Fx[oa] = ox.x / o0.x;  // pde.jl:58 force ./ norms
+    Fy[oa] = oy.x / o0.x;
+    if (hasb) {
+      Fx[oa + Nx] = ox.y / o0.y;
+      Fy[oa + Nx] = oy.y / o0.y;
+    }
+  }
+}
+
+template <typename real> int cols_for(int P) {
+  int c = (int)(65536 / ((size_t)P * 2 * sizeof(real)));
+  return c < 1 ? 1 : (c > 8 ? 8 : c);
+}
+
+}  // namespace
+
+struct smm_fft_plan {
+  int Nx, Ny, P, logP, B, precision;
+  void* tw;    // real2 [P/2]
+  void* khat;  // real2 [3][P/2+1][P]
+  void* ahat;  // real2 [B][Ny][P/2+1]
+  void* g;     // real2 [3][B][Ny][P/2+1]
+};
+
+void smm_fft_plan_destroy(smm_fft_plan* p) {
+  if (!p) return;
+  void* ptrs[] = {p->tw, p->khat, p->ahat, p->g};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  delete p;
+}
+
+template <typename real>
+static int set_smem(smm_ctx* ctx, int P, int cols) {
+  using real2 = typename vec2<real>::type;
+  size_t sm_cols = ((size_t)2 * cols * (P + 1) + P / 2) * sizeof(real2);
+  size_t sm_cols1 = ((size_t)cols * (P + 1) + P / 2) * sizeof(real2);
+  size_t sm_rows = ((size_t)P + P / 2) * sizeof(real2);
+  size_t sm_inv = ((size_t)3 * (P + 1) + P / 2) * sizeof(real2);
+  SMM_CUDA(ctx, cudaFuncSetAttribute(fft_cols_kernel<real, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cols));
+  SMM_CUDA(ctx, cudaFuncSetAttribute(fft_cols_kernel<real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cols1));
+  SMM_CUDA(ctx, cudaFuncSetAttribute(fft_rows_fwd_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rows));
+  SMM_CUDA(ctx, cudaFuncSetAttribute(fft_rows_inv_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_inv));
+  return SMM_OK;
+}
+
+int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, double hx, double hy, int B, int precision, smm_fft_plan** out) {
+  *out = nullptr;
+  int need = 2 * (Nx > Ny ? Nx : Ny) - 1, P = 32, logP = 5;
+  while (P < need) { P <<= 1; logP++; }
+  SMM_REQUIRE(ctx, P <= 2048, "FFT convolution: grid %dx%d needs P=%d > 2048", Nx, Ny, P);
+  smm_fft_plan* p = new smm_fft_plan();
+  p->Nx = Nx; p->Ny = Ny; p->P = P; p->logP = logP; p->B = B; p->precision = precision;
+  p->tw = p->khat = p->ahat = p->g = nullptr;
+  const size_t c2 = precision == SMM_PREC_F64 ? 16 : 8;
+  const int hp1 = P / 2 + 1;
+#define PL_CUDA(expr)                                                                                    \
+  do {                                                                                                   \
+    cudaError_t e__ = (expr);                                                                            \
+    if (e__ != cudaSuccess) {                                                                            \
+      smm_fft_plan_destroy(p);                                                                           \
+      for (void* t : tmp) if (t) cudaFree(t);                                                            \
+      cudaGetLastError();                                                                                \
+      return smm_fail(ctx, e__ == cudaErrorMemoryAllocation ? SMM_ERR_NOMEM : SMM_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(e__)); \
+    }                                                                                                    \
+  } while (0)
+  void* tmp[4] = {nullptr, nullptr, nullptr, nullptr};  // img, twd, ahat_d, khat_d
+  PL_CUDA(cudaMalloc(&p->tw, (size_t)(P / 2) * c2));
+  PL_CUDA(cudaMalloc(&p->khat, (size_t)3 * hp1 * P * c2));
+  PL_CUDA(cudaMalloc(&p->ahat, (size_t)B * Ny * hp1 * c2));
+  PL_CUDA(cudaMalloc(&p->g, (size_t)3 * B * Ny * hp1 * c2));
+  PL_CUDA(cudaMalloc(&tmp[0], (size_t)3 * P * P * 8));
+  PL_CUDA(cudaMalloc(&tmp[1], (size_t)(P / 2) * 16));
+  PL_CUDA(cudaMalloc(&tmp[2], (size_t)3 * P * hp1 * 16));
+  if (precision != SMM_PREC_F64) PL_CUDA(cudaMalloc(&tmp[3], (size_t)3 * hp1 * P * 16));
+  {
+    int rc = set_smem<double>(ctx, P, cols_for<double>(P));
+    if (rc == SMM_OK && precision != SMM_PREC_F64) rc = set_smem<float>(ctx, P, cols_for<float>(P));
+    if (rc != SMM_OK) { smm_fft_plan_destroy(p); for (void* t : tmp) if (t) cudaFree(t); return rc; }
+  }
+  // twiddles (Float64 and working precision), kernel images, their spectra in Float64
+  twiddle_kernel<double><<<(P / 2 + 255) / 256, 256, 0, ctx->stream>>>(P, (double2*)tmp[1]);
+  if (precision == SMM_PREC_F64) twiddle_kernel<double><<<(P / 2 + 255) / 256, 256, 0, ctx->stream>>>(P, (double2*)p->tw);
+  else twiddle_kernel<float><<<(P / 2 + 255) / 256, 256, 0, ctx->stream>>>(P, (float2*)p->tw);
+  kernel_image_kernel<<<(unsigned)(((size_t)P * P + 255) / 256), 256, 0, ctx->stream>>>(Nx, Ny, P, hx, hy, (double*)tmp[0]);
+  {
+    const int cols = cols_for<double>(P);
+    size_t sm_rows = ((size_t)P + P / 2) * 16;
+    fft_rows_fwd_kernel<double><<<dim3(P / 2, 3), 256, sm_rows, ctx->stream>>>(P, P, P, logP, (const double*)tmp[0], (double2*)tmp[2], (const double2*)tmp[1]);
+    size_t sm_cols1 = ((size_t)cols * (P + 1) + P / 2) * 16;
+    double2* kd = precision == SMM_PREC_F64 ? (double2*)p->khat : (double2*)tmp[3];
+    fft_cols_kernel<double, 1><<<dim3((hp1 + cols - 1) / cols, 3), 512, sm_cols1, ctx->stream>>>(
+        P, 0, P, logP, cols, 1.0 / ((double)P * (double)P), (const double2*)tmp[2], nullptr, kd, (const double2*)tmp[1], 0);
+    ctx->launches += 5;
+    PL_CUDA(cudaGetLastError());
+    if (precision != SMM_PREC_F64) {
+      int rc = smm_launch_convert_f64_to_real(ctx, (const double*)tmp[3], p->khat, (size_t)3 * hp1 * P * 2, precision);
+      if (rc != SMM_OK) { smm_fft_plan_destroy(p); for (void* t : tmp) if (t) cudaFree(t); return rc; }
+    }
+  }
+  PL_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (void* t : tmp) if (t) cudaFree(t);
+#undef PL_CUDA
+  *out = p;
+  return SMM_OK;
+}
+
+template <typename real>
+static int fft_conv_launch(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, void* Fx, void* Fy) {
+  using real2 = typename vec2<real>::type;
+  const int P = p->P, logP = p->logP, hp1 = P / 2 + 1, cols = cols_for<real>(P);
+  const size_t gstride = (size_t)p->B * p->Ny * hp1;
+  size_t sm_rows = ((size_t)P + P / 2) * sizeof(real2);
+  size_t sm_cols = ((size_t)2 * cols * (P + 1) + P / 2) * sizeof(real2);
+  size_t sm_inv = ((size_t)3 * (P + 1) + P / 2) * sizeof(real2);
+  const int rt = P >= 512 ? 256 : 128;
+  fft_rows_fwd_kernel<real><<<dim3((p->Ny + 1) / 2, p->B), rt, sm_rows, ctx->stream>>>(
+      p->Ny, p->Nx, P, logP, (const real*)rhosum, (real2*)p->ahat, (const real2*)p->tw);
+  const int ct = (P * cols) / 2 >= 2048 ? 512 : 256;
+  fft_cols_kernel<real, 0><<<dim3((hp1 + cols - 1) / cols, p->B), ct, sm_cols, ctx->stream>>>(
+      p->Ny, p->Ny, P, logP, cols, 1.0, (const real2*)p->ahat, (const real2*)p->khat, (real2*)p->g, (const real2*)p->tw, gstride);
+  fft_rows_inv_kernel<real><<<dim3((p->Ny + 1) / 2, p->B), rt, sm_inv, ctx->stream>>>(
+      p->Nx, p->Ny, P, logP, (const real2*)p->g, gstride, (real*)Fx, (real*)Fy, (const real2*)p->tw);
+  ctx->launches += 3;
+  SMM_CUDA(ctx, cudaGetLastError());
+  return SMM_OK;
+}
+
+int smm_fft_conv(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, void* Fx, void* Fy) {
+  return p->precision == SMM_PREC_F64 ? fft_conv_launch<double>(ctx, p, rhosum, Fx, Fy)
+                                      : fft_conv_launch<float>(ctx, p, rhosum, Fx, Fy);
+}

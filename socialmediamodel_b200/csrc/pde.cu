@@ -12,6 +12,10 @@
 //                         influencer/media ODE right-hand sides (:239-265), the rate factors
 //                         (pde.jl:35-47) and advances the ODE unknowns (Float64).
 // Layout in HBM: u[b][j][i][iy][ix] (= Julia u[Nx,Ny,2,L,B], x fastest), rhosum/Fx/Fy[b][iy][ix].
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
 #include <map>
 
 #include "smm_internal.h"
@@ -378,6 +382,7 @@ struct smm_pde_batch {
   size_t conv_smem;
   std::map<std::pair<int, double>, cudaGraphExec_t> graphs;
   int64_t steps_taken;
+  smm_fft_plan* fft;  // null = direct Toeplitz kernel
 };
 
 static void pde_free(smm_pde_batch* pb) {
@@ -385,6 +390,7 @@ static void pde_free(smm_pde_batch* pb) {
   void* ptrs[] = {pb->u, pb->Ua, pb->Ub, pb->acc, pb->rhosum, pb->Fx, pb->Fy, pb->wext, pb->partials, pb->counters, pb->coef, pb->ode, pb->inst};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& g : pb->graphs) cudaGraphExecDestroy(g.second);
+  smm_fft_plan_destroy(pb->fft);
   delete pb;
 }
 
@@ -410,6 +416,7 @@ static int launch_moments(smm_ctx* ctx, smm_pde_batch* pb, const void* U) {
 }
 
 static int launch_conv(smm_ctx* ctx, smm_pde_batch* pb) {
+  if (pb->fft) return smm_fft_conv(ctx, pb->fft, pb->rhosum, pb->Fx, pb->Fy);
   dim3 grid((pb->Nx + CT - 1) / CT, (pb->Ny + CT - 1) / CT, pb->B);
   const int threads = CT * CT * NS;
   const double h = pb->grid.dx;
@@ -523,6 +530,7 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
   pb->u = pb->Ua = pb->Ub = pb->acc = pb->rhosum = pb->Fx = pb->Fy = pb->wext = nullptr;
   pb->partials = nullptr; pb->counters = nullptr; pb->coef = nullptr; pb->ode = nullptr; pb->inst = nullptr;
   pb->steps_taken = 0;
+  pb->fft = nullptr;
   pb->rs = precision == SMM_PREC_F64 ? 8 : 4;
   pb->plane = (size_t)grid->Nx * grid->Ny;
   pb->per_inst = pb->plane * 2 * L;
@@ -557,6 +565,13 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
   if (pb->conv_smem > 48 * 1024) {
     if (precision == SMM_PREC_F64) PB_CUDA(cudaFuncSetAttribute(pde_conv_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb->conv_smem));
     else PB_CUDA(cudaFuncSetAttribute(pde_conv_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb->conv_smem));
+  }
+  // interaction force: FFT correlation (default), or the direct O(N^2) kernel when SMM_PDE_CONV=direct
+  {
+    const char* ev = getenv("SMM_PDE_CONV");
+    const int need = 2 * std::max(grid->Nx, grid->Ny) - 1;
+    if (!(ev && strcmp(ev, "direct") == 0) && need <= 2048)
+      PB_TRY(smm_fft_plan_create(ctx, grid->Nx, grid->Ny, grid->dx, grid->dy, B, precision, &pb->fft));
   }
   // initial state: u (converted to `real`), coef.y/z
   const int ninit = shared_init ? 1 : B;

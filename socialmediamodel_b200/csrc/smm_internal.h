@@ -93,3 +93,9 @@ int smm_launch_pack_xy(smm_ctx* ctx, const double* xy, void* x2, size_t n, int p
 int smm_launch_unpack_xy(smm_ctx* ctx, const void* x2, double* xy, size_t n, int precision);  // real2[n] -> [2][n] f64
 int smm_launch_convert_i32_to_u8(smm_ctx* ctx, const int32_t* in, unsigned char* out, size_t count);
 int smm_launch_convert_u8_to_i32(smm_ctx* ctx, const unsigned char* in, int32_t* out, size_t count);
+
+// FFT-based Toeplitz correlation for the PDE interaction force (fft_conv.cu)
+struct smm_fft_plan;
+int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, double hx, double hy, int B, int precision, smm_fft_plan** out);
+int smm_fft_conv(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, void* Fx, void* Fy);
+void smm_fft_plan_destroy(smm_fft_plan* p);

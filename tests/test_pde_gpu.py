@@ -164,3 +164,31 @@ def test_batch_resident_and_sums(coarse):
         ur, _, _ = P.rk_solve(*uzy0.x, 10, 5e-4, po, dict(qs[k]))
         assert rel(u[..., k], ur) < TOL32
     pb.close()
+
+
+def test_direct_toeplitz_kernel_agrees_with_fft_path(coarse, monkeypatch):
+    """SMM_PDE_CONV=direct selects the O(N^2) smem-tiled Toeplitz kernel; default is the FFT path."""
+    p, q, uzy0 = coarse
+    u, z, y = perturbed_state(p, q, uzy0, 5)
+    du_fft, _, _ = smm.pde_rhs(u, z, y, p=p, q=q, precision="f64")
+    monkeypatch.setenv("SMM_PDE_CONV", "direct")
+    du_dir, _, _ = smm.pde_rhs(u, z, y, p=p, q=q, precision="f64")
+    du32, _, _ = smm.pde_rhs(u, z, y, p=p, q=q, precision="f32")
+    monkeypatch.delenv("SMM_PDE_CONV")
+    assert rel(du_fft, du_dir) < 1e-11
+    dur, _, _ = P.rhs(u, z, y, oracle_p(p), dict(q))
+    assert rel(du32, dur) < TOL32
+
+
+@pytest.mark.parametrize("dx,N", [(0.025, 177), (0.0125, 353)])
+def test_rhs_refined_grids_f32(dx, N):
+    """C4 grids: the reference cannot build K_matrix here (248 GB at 353^2); parity is against the
+    oracle's Float64 FFT evaluation of the same Toeplitz sums."""
+    p = smm.PDEconstruct(dx=dx)
+    assert p.N_x == N
+    q = smm.parameters()
+    uzy0, q2 = smm.constructinitial("4inf", (p, q))
+    du, dz, dy = smm.pde_rhs(*uzy0.x, p=p, q=q2, precision="f32")
+    dur, dzr, dyr = P.rhs(*uzy0.x, oracle_p(p), dict(q))
+    assert rel(du, dur) < TOL32, rel(du, dur)
+    assert np.abs(dy - dyr).max() < 1e-7 and np.abs(dz - dzr).max() < 1e-7
