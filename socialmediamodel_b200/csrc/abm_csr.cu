@@ -13,6 +13,8 @@
 //
 // No grid-wide barrier and no host round trip; three accumulator buffers rotate (read k%3,
 // write (k+1)%3, clear (k+2)%3).  HBM-bound: 23 + 12*deg bytes per agent-step.
+#include <string.h>
+
 #include "abm_device.cuh"
 #include "smm_internal.h"
 
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(kPopThreads) pop_step_kernel(PopArgs A) {
   float* fnx = reinterpret_cast<float*>(frac + L);                  // FP32 copies for the guarded decision
   float* fny = fnx + L;
   float* ffrac = fny + L;
+  double* att_scr = reinterpret_cast<double*>(ffrac + L + (L & 1)) + (tid >> 5) * L;  // [nwarps][L]
 
   // ---- prologue -------------------------------------------------------------------------
   for (int t = tid; t < 2 * L * 3; t += kPopThreads) bins[t] = 0;
@@ -141,11 +144,13 @@ __global__ void __launch_bounds__(kPopThreads) pop_step_kernel(PopArgs A) {
   real2* xw = static_cast<real2*>(A.x_new);
   const double noise_x = sdt * K.sigma;
   unsigned int nfallback = 0;
-  for (size_t j = (size_t)blockIdx.x * kPopThreads + tid; j < (size_t)n; j += (size_t)gridDim.x * kPopThreads) {
+  for (size_t base = (size_t)blockIdx.x * kPopThreads; base < (size_t)n; base += (size_t)gridDim.x * kPopThreads) {
+    const bool valid = base + tid < (size_t)n;          // warp-uniform loop; tail lanes idle but shuffle
+    const size_t j = valid ? base + tid : (size_t)n - 1;
     const real2 xj = xo[j];
     real ax = 0, ay = 0, ws = 0;
     if (A.rowptr) {
-      const int e0 = A.rowptr[j], e1 = A.rowptr[j + 1];
+      const int e0 = A.rowptr[j], e1 = valid ? A.rowptr[j + 1] : e0;
 #pragma unroll 4
       for (int e = e0; e < e1; e++) {  // abm.jl:51,57-62
         real2 p = xo[A.colidx[e]];
@@ -181,24 +186,23 @@ __global__ void __launch_bounds__(kPopThreads) pop_step_kernel(PopArgs A) {
     double xn0 = reflect1(x + K.dt * fx + noise_x * xi0, K.lo0, K.hi0);
     double xn1 = reflect1(y + K.dt * fy + noise_x * xi1, K.lo1, K.hi1);
     int fnew;
-    bool decided = false;
     if (sizeof(real) == 4 && A.xi == nullptr) {
       // Philox uniforms are 24-bit, exactly representable in FP32
-      decided = switch_decision_f32_guarded((float)xj.x, (float)xj.y, sj, fj, fnx, fny, ffrac, L, (float)K.eta,
-                                            (float)K.dt, (float)u1, (float)u2, 2e-5f, &fnew);
-    }
-    if (!decided) {
+      fnew = warp_switch_decision(valid, (float)xj.x, (float)xj.y, sj, fj, (float)u1, (float)u2, fnx, fny, ffrac, enx, eny,
+                                  frac, L, (float)K.eta, (float)K.dt, K.eta, K.dt, 2e-5f, att_scr, &nfallback);
+    } else {
       fnew = switch_decision_f64(x, y, sj, fj, enx, eny, frac, L, K.eta, K.dt, u1, u2);
-      nfallback++;
     }
-    const real2 pn = mk2((real)xn0, (real)xn1);
-    xw[j] = pn;
-    A.follow[j] = (unsigned char)fnew;
-    // class sums of the NEW state for the next launch (fixed point: order-independent)
-    const int c = fnew * 2 + (sj == 1 ? 1 : 0);
-    atomicAdd(reinterpret_cast<unsigned long long*>(&bins[c * 3 + 0]), (unsigned long long)__double2ll_rn((double)pn.x * A.fx_scale));
-    atomicAdd(reinterpret_cast<unsigned long long*>(&bins[c * 3 + 1]), (unsigned long long)__double2ll_rn((double)pn.y * A.fx_scale));
-    atomicAdd(reinterpret_cast<unsigned long long*>(&bins[c * 3 + 2]), 1ull);
+    if (valid) {
+      const real2 pn = mk2((real)xn0, (real)xn1);
+      xw[j] = pn;
+      A.follow[j] = (unsigned char)fnew;
+      // class sums of the NEW state for the next launch (fixed point: order-independent)
+      const int c = fnew * 2 + (sj == 1 ? 1 : 0);
+      atomicAdd(reinterpret_cast<unsigned long long*>(&bins[c * 3 + 0]), (unsigned long long)__double2ll_rn((double)pn.x * A.fx_scale));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&bins[c * 3 + 1]), (unsigned long long)__double2ll_rn((double)pn.y * A.fx_scale));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&bins[c * 3 + 2]), 1ull);
+    }
   }
   __syncthreads();
   for (int t = tid; t < 2 * L * 3; t += kPopThreads)
@@ -228,7 +232,7 @@ __global__ void cvt_kernel(const Tin* __restrict__ in, Tout* __restrict__ out, s
 }
 
 size_t pop_smem_bytes(int L, int M) {
-  return (size_t)2 * L * 3 * 8 + sizeof(double) * (4 * (L + M) + L) + sizeof(float) * 3 * L + 16;
+  return (size_t)2 * L * 3 * 8 + sizeof(double) * (4 * (L + M) + L) + sizeof(float) * (3 * L + 2) + sizeof(double) * (kPopThreads / 32) * L + 16;
 }
 
 }  // namespace
@@ -269,8 +273,27 @@ int smm_launch_pop_step(smm_ctx* ctx, smm_abm_pop* p, const void* xi, const doub
   A.fallback_count = p->fallback_count;
   size_t sm = pop_smem_bytes(p->k.L, p->k.M);
   int grid = pop_grid(ctx, p->k.n);
+  if (p->l2_persist_bytes > 0) {
+    // keep the gathered (old) position array resident in L2; the colidx stream and the new
+    // positions pass through as streaming traffic
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    size_t win = (size_t)p->k.n * 2 * (p->precision == SMM_PREC_F64 ? 8 : 4);
+    if (win > p->l2_window_max) win = p->l2_window_max;
+    av.accessPolicyWindow.base_ptr = const_cast<void*>(A.x_old);
+    av.accessPolicyWindow.num_bytes = win;
+    av.accessPolicyWindow.hitRatio = (float)(p->l2_persist_bytes >= win ? 1.0 : (double)p->l2_persist_bytes / (double)win);
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+  }
   if (p->precision == SMM_PREC_F64) pop_step_kernel<double><<<grid, kPopThreads, sm, ctx->stream>>>(A);
   else pop_step_kernel<float><<<grid, kPopThreads, sm, ctx->stream>>>(A);
+  if (p->l2_persist_bytes > 0) {
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+  }
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());
   p->step++;

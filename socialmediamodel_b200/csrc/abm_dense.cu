@@ -11,10 +11,10 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;
 
 template <typename real>
-__global__ void __launch_bounds__(kThreads) abm_dense_kernel(AbmDenseArgs A) {
+__global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) {
   using real2 = typename vec2<real>::type;
   const AbmConst& K = A.k;
   const int n = K.n, L = K.L, M = K.M, NT = A.NT;
@@ -164,31 +164,11 @@ __global__ void __launch_bounds__(kThreads) abm_dense_kernel(AbmDenseArgs A) {
     }
     __syncthreads();
 
-    // ---- P3: per agent: attraction over all agents, influence, Euler-Maruyama, switch
-    for (int j = tid; j < n; j += kThreads) {
-      const real2 xj = xc[j];
-      real ax = 0, ay = 0, ws = 0;
-      if (A.rowptr == nullptr) {
-#pragma unroll 8
-        for (int i = 0; i < n; i++) {  // abm.jl:57-62; every lane reads the same address: smem broadcast
-          real2 p = xc[i];
-          real dx = p.x - xj.x, dy = p.y - xj.y;
-          real w = w_of_r2(dx * dx + dy * dy);
-          ws += w;
-          ax += w * dx;
-          ay += w * dy;
-        }
-      } else {  // sparse follower network shared by the realizations (row j of IndNet, abm.jl:51)
-        for (int e = A.rowptr[j]; e < A.rowptr[j + 1]; e++) {
-          real2 p = xc[A.colidx[e]];
-          real dx = p.x - xj.x, dy = p.y - xj.y;
-          real w = w_of_r2(dx * dx + dy * dy);
-          ws += w;
-          ax += w * dx;
-          ay += w * dy;
-        }
-        if (ws == (real)0) ws = (real)1;  // no neighbours: zero force (abm.jl:52-53)
-      }
+    // ---- P3: per agent: attraction over all agents, influence, Euler-Maruyama, switch.
+    // Two agents per thread (j0, j0 + kThreads): each broadcast partner load feeds two pair
+    // evaluations, and 128-thread CTAs let every realization of a 1 024-member ensemble be
+    // resident at once (7 CTAs per SM) instead of two waves of 256-thread CTAs.
+    auto finish = [&](int j, real2 xj, real ax, real ay, real ws) {
       const int sj = st[j], fj = fol[j];
       const double x = (double)xj.x, y = (double)xj.y;
       const int mrow = sj == 1 ? 1 : 0;  // abm.jl:74-78
@@ -213,6 +193,38 @@ __global__ void __launch_bounds__(kThreads) abm_dense_kernel(AbmDenseArgs A) {
       int fnew = switch_decision_f64(x, y, sj, fj, infx + nxt * L, infy + nxt * L, frac, L, K.eta, K.dt, u1, u2);
       xn[j] = mk2((real)xn0, (real)xn1);
       fol[j] = fnew;  // only this thread reads fol[j] during P3
+    };
+    for (int j0 = tid; j0 < n; j0 += 2 * kThreads) {
+      const int j1 = j0 + kThreads;
+      const bool has1 = j1 < n;
+      const real2 xa = xc[j0], xb = xc[has1 ? j1 : j0];
+      real ax0 = 0, ay0 = 0, ws0 = 0, ax1 = 0, ay1 = 0, ws1 = 0;
+      if (A.rowptr == nullptr) {
+#pragma unroll 4
+        for (int i = 0; i < n; i++) {  // abm.jl:57-62; every lane reads the same address: smem broadcast
+          const real2 p = xc[i];
+          const real dx0 = p.x - xa.x, dy0 = p.y - xa.y, dx1 = p.x - xb.x, dy1 = p.y - xb.y;
+          const real w0 = w_of_r2(dx0 * dx0 + dy0 * dy0), w1 = w_of_r2(dx1 * dx1 + dy1 * dy1);
+          ws0 += w0; ax0 += w0 * dx0; ay0 += w0 * dy0;
+          ws1 += w1; ax1 += w1 * dx1; ay1 += w1 * dy1;
+        }
+      } else {  // sparse follower network shared by the realizations (row j of IndNet, abm.jl:51)
+        for (int e = A.rowptr[j0]; e < A.rowptr[j0 + 1]; e++) {
+          const real2 p = xc[A.colidx[e]];
+          const real dx = p.x - xa.x, dy = p.y - xa.y, w = w_of_r2(dx * dx + dy * dy);
+          ws0 += w; ax0 += w * dx; ay0 += w * dy;
+        }
+        if (has1)
+          for (int e = A.rowptr[j1]; e < A.rowptr[j1 + 1]; e++) {
+            const real2 p = xc[A.colidx[e]];
+            const real dx = p.x - xb.x, dy = p.y - xb.y, w = w_of_r2(dx * dx + dy * dy);
+            ws1 += w; ax1 += w * dx; ay1 += w * dy;
+          }
+        if (ws0 == (real)0) ws0 = (real)1;  // no neighbours: zero force (abm.jl:52-53)
+        if (ws1 == (real)0) ws1 = (real)1;
+      }
+      finish(j0, xa, ax0, ay0, ws0);
+      if (has1) finish(j1, xb, ax1, ay1, ws1);
     }
     __syncthreads();
     cur = nxt;

@@ -70,3 +70,121 @@ __device__ __forceinline__ bool switch_decision_f32_guarded(float x, float y, in
   *out = L - 1;
   return true;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative switch decision for many influencers (population kernel, L up to 256).
+//   phase 1 (per lane, all lanes active): lam = sum_i att_i in FP32, thr = 1-exp(-lam dt);
+//           |u1-thr| outside the guard band decides "stay"/"switch"; inside -> FP64.
+//   phase 2 (per switching lane, whole warp): the 32 lanes evaluate att_i for i = lane, lane+32, ..
+//           in parallel, a shuffle scan builds the CDF, a ballot finds the first i with cs >= u2;
+//           any |cs-u2| within the band up to that i -> FP64.
+//   FP64 (rare, whole warp): lanes evaluate att_i in Float64 in parallel into shared memory, lane 0
+//           performs the reference's sequential sums (abm.jl:123-130) so the result is the oracle's.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// att scratch: one double[Lpad] per warp in shared memory
+__device__ __forceinline__ int warp_switch_decision(bool valid, float x, float y, int st, int follow, float u1, float u2,
+                                                    const float* infx, const float* infy, const float* frac,
+                                                    const double* dinfx, const double* dinfy, const double* dfrac,
+                                                    int L, float eta, float dt, double deta, double ddt, float band,
+                                                    double* att_scratch, unsigned int* nfallback) {
+  const int lane = threadIdx.x & 31;
+  // ---- phase 1
+  float lam = 0.f;
+  for (int i = 0; i < L; i++) {
+    float d0 = x - infx[i], d1 = y - infy[i];
+    float g2 = (float)st * frac[i];
+    if (g2 < 0.1f) g2 = 0.1f;
+    lam += eta * w_of_r2(fmaf(d0, d0, d1 * d1)) * g2;
+  }
+  int status = 0;  // 0 stay, 1 switch (FP32-decided), 2 needs FP64
+  if (valid && lam == lam) {  // NaN lock (Q5): stay
+    float thr = -expm1f(-lam * dt);
+    float gap = u1 - thr;
+    if (fabsf(gap) <= band * fmaxf(thr, 1e-3f)) status = 2;
+    else if (gap < 0.f) status = 1;
+  }
+  int result = follow;
+  // ---- phase 2: cooperative CDF walk for the FP32-decided switchers
+  unsigned sw = __ballot_sync(0xffffffffu, status == 1);
+  while (sw) {
+    const int src = __ffs(sw) - 1;
+    sw &= sw - 1;
+    const float sx = __shfl_sync(0xffffffffu, x, src), sy = __shfl_sync(0xffffffffu, y, src);
+    const float sst = (float)__shfl_sync(0xffffffffu, st, src);
+    const float sinv = 1.0f / __shfl_sync(0xffffffffu, lam, src), su2 = __shfl_sync(0xffffffffu, u2, src);
+    float carry = 0.f;
+    int found = -1;
+    bool fuzzy = false;
+    for (int i0 = 0; i0 < L && found < 0 && !fuzzy; i0 += 32) {
+      const int i = i0 + lane;
+      float a = 0.f;
+      if (i < L) {
+        float d0 = sx - infx[i], d1 = sy - infy[i];
+        float g2 = sst * frac[i];
+        if (g2 < 0.1f) g2 = 0.1f;
+        a = eta * w_of_r2(fmaf(d0, d0, d1 * d1)) * g2 * sinv;
+      }
+      const float cs = carry + warp_incl_scan(a, lane);
+      const float g = cs - su2;
+      const bool last = i == L - 1;                      // the clamp index (Q7) needs no comparison
+      const unsigned hit = __ballot_sync(0xffffffffu, i < L && (g >= 0.f || last));
+      const unsigned near = __ballot_sync(0xffffffffu, i < L && !last && fabsf(g) <= band);
+      if (hit) {
+        const int h = __ffs(hit) - 1;
+        found = i0 + h;
+        if (near & ((2u << h) - 1u)) fuzzy = true;       // a borderline comparison at or before the hit
+      } else if (near) {
+        fuzzy = true;
+      }
+      carry = __shfl_sync(0xffffffffu, cs, 31);
+    }
+    if (lane == src) {
+      if (fuzzy || found < 0) status = 2;
+      else result = found;
+    }
+  }
+  // ---- FP64 re-evaluation (guard band), cooperative
+  unsigned fb = __ballot_sync(0xffffffffu, status == 2);
+  while (fb) {
+    const int src = __ffs(fb) - 1;
+    fb &= fb - 1;
+    const double sx = (double)__shfl_sync(0xffffffffu, x, src), sy = (double)__shfl_sync(0xffffffffu, y, src);
+    const double sst = (double)__shfl_sync(0xffffffffu, st, src);
+    for (int i = lane; i < L; i += 32) {
+      double d0 = sx - dinfx[i], d1 = sy - dinfy[i];
+      double dist = exp(-sqrt(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1))));
+      double g2 = __dmul_rn(sst, dfrac[i]);
+      if (g2 < SMM_THETA) g2 = SMM_THETA;
+      att_scratch[i] = __dmul_rn(__dmul_rn(deta, dist), g2);
+    }
+    __syncwarp();
+    if (lane == src) {
+      double lamd = 0.0;
+      for (int i = 0; i < L; i++) lamd = __dadd_rn(lamd, att_scratch[i]);
+      double thr = 1.0 - exp(-__dmul_rn(lamd, ddt));
+      if ((double)u1 < thr) {
+        double cs = 0.0;
+        int k = L - 1;
+        for (int i = 0; i < L; i++) {
+          cs = __dadd_rn(cs, att_scratch[i] / lamd);
+          if (!(cs < (double)u2)) { k = i; break; }
+        }
+        result = k;
+      } else {
+        result = follow;
+      }
+      (*nfallback)++;
+    }
+    __syncwarp();
+  }
+  return result;
+}

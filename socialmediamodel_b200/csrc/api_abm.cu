@@ -1,4 +1,6 @@
 // api_abm.cu -- context management and the ABM entry points of the C ABI (include/smm_b200.h).
+#include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -593,6 +595,22 @@ extern "C" int smm_abm_pop_create(smm_ctx* ctx, const smm_params* q, int32_t pre
   int shift = 61 - (int)ceil(log2((double)n * std::max(maxabs, 1.0)));
   if (shift > 50) shift = 50;
   p->fx_scale = ldexp(1.0, shift);
+  {
+    // L2 persistence window for the position gathers (SMM_POP_L2_PERSIST=0 disables)
+    const char* ev = getenv("SMM_POP_L2_PERSIST");
+    cudaDeviceProp prop;
+    p->l2_persist_bytes = p->l2_window_max = 0;
+    if (!(ev && ev[0] == '0') && rowptr && cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess &&
+        prop.persistingL2CacheMaxSize > 0) {
+      size_t want = std::min((size_t)prop.persistingL2CacheMaxSize, n * 2 * (precision == SMM_PREC_F64 ? (size_t)8 : (size_t)4));
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+        p->l2_persist_bytes = want;
+        p->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+      } else {
+        cudaGetLastError();
+      }
+    }
+  }
   const size_t rs = precision == SMM_PREC_F64 ? 8 : 4;
   for (int i = 0; i < 2; i++) { POP_CUDA(cudaMalloc(&p->x[i], n * 2 * rs)); POP_CUDA(cudaMalloc((void**)&p->ent[i], 2 * (L + M) * 8)); }
   for (int i = 0; i < 3; i++) { POP_CUDA(cudaMalloc((void**)&p->acc[i], 2 * L * 3 * 8)); POP_CUDA(cudaMemsetAsync(p->acc[i], 0, 2 * L * 3 * 8, ctx->stream)); }
