@@ -24,21 +24,23 @@ template <typename real2> __device__ __forceinline__ real2 cmulc(real2 a, real2 
 __device__ __forceinline__ int brev_p(int i, int logP) { return (int)(__brev((unsigned)i) >> (32 - logP)); }
 
 // ncol independent length-P FFTs in shared memory (column stride cs), decimation in frequency:
-// natural-order input, bit-reversed output.  tw[k] = exp(-2 pi i k / P), k < P/2.
+// natural-order input, bit-reversed output.  Twiddles are stored stage-major, tw[half + j] =
+// exp(-2 pi i j / (2 half)) for j < half (half = 1, 2, .., P/2): consecutive lanes read consecutive
+// words (the strided form tw[j * P/2^s] was up to 32-way bank-conflicted in the middle stages).
 template <typename real>
 __device__ void fft_dif_fwd(typename vec2<real>::type* sh, int ncol, int cs, int P, int logP,
                             const typename vec2<real>::type* tw) {
   using real2 = typename vec2<real>::type;
   const int tid = threadIdx.x, nt = blockDim.x, hp = P >> 1;
   for (int s = logP; s >= 1; s--) {
-    const int half = 1 << (s - 1), ts = P >> s;
+    const int half = 1 << (s - 1);
     for (int t = tid; t < ncol * hp; t += nt) {
       const int c = t >> (logP - 1), bt = t & (hp - 1);
       const int j = bt & (half - 1), i0 = ((bt >> (s - 1)) << s) + j;
       real2* x = sh + c * cs;
       const real2 a = x[i0], b = x[i0 + half];
       x[i0] = cadd(a, b);
-      x[i0 + half] = cmul(csub(a, b), tw[j * ts]);
+      x[i0 + half] = cmul(csub(a, b), tw[half + j]);
     }
     __syncthreads();
   }
@@ -51,12 +53,12 @@ __device__ void fft_dit_inv(typename vec2<real>::type* sh, int ncol, int cs, int
   using real2 = typename vec2<real>::type;
   const int tid = threadIdx.x, nt = blockDim.x, hp = P >> 1;
   for (int s = 1; s <= logP; s++) {
-    const int half = 1 << (s - 1), ts = P >> s;
+    const int half = 1 << (s - 1);
     for (int t = tid; t < ncol * hp; t += nt) {
       const int c = t >> (logP - 1), bt = t & (hp - 1);
       const int j = bt & (half - 1), i0 = ((bt >> (s - 1)) << s) + j;
       real2* x = sh + c * cs;
-      const real2 a = x[i0], b = cmulc(x[i0 + half], tw[j * ts]);
+      const real2 a = x[i0], b = cmulc(x[i0 + half], tw[half + j]);
       x[i0] = cadd(a, b);
       x[i0 + half] = csub(a, b);
     }
@@ -66,11 +68,14 @@ __device__ void fft_dit_inv(typename vec2<real>::type* sh, int ncol, int cs, int
 
 template <typename real>
 __global__ void twiddle_kernel(int P, typename vec2<real>::type* tw) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= P / 2) return;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;  // e = half + j
+  if (e >= P) return;
+  if (e == 0) { tw[0] = mk2((real)1, (real)0); return; }
+  int half = 1 << (31 - __clz(e));
+  int j = e - half;
   double s, c;
-  sincospi(-2.0 * (double)k / (double)P, &s, &c);
-  tw[k] = mk2((real)c, (real)s);
+  sincospi(-(double)j / (double)half, &s, &c);    // exp(-2 pi i j / (2 half))
+  tw[e] = mk2((real)c, (real)s);
 }
 
 // circular kernel images c_k[dy mod P][dx mod P] (Float64): w, -w*hx*dx, -w*hy*dy  (pde.jl:14-20 with
@@ -104,7 +109,7 @@ __global__ void __launch_bounds__(256) fft_rows_fwd_kernel(int nrows, int rowlen
   const real* rowa = in + ((size_t)b * nrows + ra) * rowlen;
   const real* rowb = in + ((size_t)b * nrows + rb) * rowlen;
   const bool hasb = rb < nrows;
-  for (int i = tid; i < P / 2; i += nt) tw[i] = twg[i];
+  for (int i = tid; i < P; i += nt) tw[i] = twg[i];
   for (int i = tid; i < P; i += nt) sh[i] = i < rowlen ? mk2(rowa[i], hasb ? rowb[i] : (real)0) : mk2((real)0, (real)0);
   __syncthreads();
   fft_dif_fwd<real>(sh, 1, P, P, logP, tw);
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(512) fft_cols_kernel(int nrows, int nkeep, int
   const int hp1 = P / 2 + 1;
   const int b = blockIdx.y, kx0 = blockIdx.x * cols;
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < P / 2; i += nt) tw[i] = twg[i];
+  for (int i = tid; i < P; i += nt) tw[i] = twg[i];
   const real2* Ab = A + (size_t)b * nrows * hp1;
   for (int e = tid; e < P * cols; e += nt) {
     const int jy = e / cols, c = e - jy * cols;
@@ -187,7 +192,7 @@ __global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, int P
   const int b = blockIdx.y, ra = blockIdx.x * 2, rb = ra + 1;
   const bool hasb = rb < Ny;
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < P / 2; i += nt) tw[i] = twg[i];
+  for (int i = tid; i < P; i += nt) tw[i] = twg[i];
   for (int e = tid; e < 3 * P; e += nt) {
     const int k = e / P, kk = e - k * P;
     const bool up = kk > P / 2;
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, int P
 }
 
 template <typename real> int cols_for(int P) {
-  int c = (int)(65536 / ((size_t)P * 2 * sizeof(real)));
+  int c = (int)(32768 / ((size_t)P * 2 * sizeof(real)));  // <= 32 KB per buffer: 3 CTAs per SM at P = 1024
   return c < 1 ? 1 : (c > 8 ? 8 : c);
 }
 
@@ -221,7 +226,7 @@ template <typename real> int cols_for(int P) {
 
 struct smm_fft_plan {
   int Nx, Ny, P, logP, B, precision;
-  void* tw;    // real2 [P/2]
+  void* tw;    // real2 [P], stage-major
   void* khat;  // real2 [3][P/2+1][P]
   void* ahat;  // real2 [B][Ny][P/2+1]
   void* g;     // real2 [3][B][Ny][P/2+1]
@@ -237,10 +242,10 @@ void smm_fft_plan_destroy(smm_fft_plan* p) {
 template <typename real>
 static int set_smem(smm_ctx* ctx, int P, int cols) {
   using real2 = typename vec2<real>::type;
-  size_t sm_cols = ((size_t)2 * cols * (P + 1) + P / 2) * sizeof(real2);
-  size_t sm_cols1 = ((size_t)cols * (P + 1) + P / 2) * sizeof(real2);
-  size_t sm_rows = ((size_t)P + P / 2) * sizeof(real2);
-  size_t sm_inv = ((size_t)3 * (P + 1) + P / 2) * sizeof(real2);
+  size_t sm_cols = ((size_t)2 * cols * (P + 1) + P) * sizeof(real2);
+  size_t sm_cols1 = ((size_t)cols * (P + 1) + P) * sizeof(real2);
+  size_t sm_rows = ((size_t)P + P) * sizeof(real2);
+  size_t sm_inv = ((size_t)3 * (P + 1) + P) * sizeof(real2);
   SMM_CUDA(ctx, cudaFuncSetAttribute(fft_cols_kernel<real, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cols));
   SMM_CUDA(ctx, cudaFuncSetAttribute(fft_cols_kernel<real, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_cols1));
   SMM_CUDA(ctx, cudaFuncSetAttribute(fft_rows_fwd_kernel<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_rows));
@@ -269,12 +274,12 @@ int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, double hx, double hy, int 
     }                                                                                                    \
   } while (0)
   void* tmp[4] = {nullptr, nullptr, nullptr, nullptr};  // img, twd, ahat_d, khat_d
-  PL_CUDA(cudaMalloc(&p->tw, (size_t)(P / 2) * c2));
+  PL_CUDA(cudaMalloc(&p->tw, (size_t)P * c2));
   PL_CUDA(cudaMalloc(&p->khat, (size_t)3 * hp1 * P * c2));
   PL_CUDA(cudaMalloc(&p->ahat, (size_t)B * Ny * hp1 * c2));
   PL_CUDA(cudaMalloc(&p->g, (size_t)3 * B * Ny * hp1 * c2));
   PL_CUDA(cudaMalloc(&tmp[0], (size_t)3 * P * P * 8));
-  PL_CUDA(cudaMalloc(&tmp[1], (size_t)(P / 2) * 16));
+  PL_CUDA(cudaMalloc(&tmp[1], (size_t)P * 16));
   PL_CUDA(cudaMalloc(&tmp[2], (size_t)3 * P * hp1 * 16));
   if (precision != SMM_PREC_F64) PL_CUDA(cudaMalloc(&tmp[3], (size_t)3 * hp1 * P * 16));
   {
@@ -283,15 +288,15 @@ int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, double hx, double hy, int 
     if (rc != SMM_OK) { smm_fft_plan_destroy(p); for (void* t : tmp) if (t) cudaFree(t); return rc; }
   }
   // twiddles (Float64 and working precision), kernel images, their spectra in Float64
-  twiddle_kernel<double><<<(P / 2 + 255) / 256, 256, 0, ctx->stream>>>(P, (double2*)tmp[1]);
-  if (precision == SMM_PREC_F64) twiddle_kernel<double><<<(P / 2 + 255) / 256, 256, 0, ctx->stream>>>(P, (double2*)p->tw);
-  else twiddle_kernel<float><<<(P / 2 + 255) / 256, 256, 0, ctx->stream>>>(P, (float2*)p->tw);
+  twiddle_kernel<double><<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, (double2*)tmp[1]);
+  if (precision == SMM_PREC_F64) twiddle_kernel<double><<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, (double2*)p->tw);
+  else twiddle_kernel<float><<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, (float2*)p->tw);
   kernel_image_kernel<<<(unsigned)(((size_t)P * P + 255) / 256), 256, 0, ctx->stream>>>(Nx, Ny, P, hx, hy, (double*)tmp[0]);
   {
     const int cols = cols_for<double>(P);
-    size_t sm_rows = ((size_t)P + P / 2) * 16;
+    size_t sm_rows = ((size_t)P + P) * 16;
     fft_rows_fwd_kernel<double><<<dim3(P / 2, 3), 256, sm_rows, ctx->stream>>>(P, P, P, logP, (const double*)tmp[0], (double2*)tmp[2], (const double2*)tmp[1]);
-    size_t sm_cols1 = ((size_t)cols * (P + 1) + P / 2) * 16;
+    size_t sm_cols1 = ((size_t)cols * (P + 1) + P) * 16;
     double2* kd = precision == SMM_PREC_F64 ? (double2*)p->khat : (double2*)tmp[3];
     fft_cols_kernel<double, 1><<<dim3((hp1 + cols - 1) / cols, 3), 512, sm_cols1, ctx->stream>>>(
         P, 0, P, logP, cols, 1.0 / ((double)P * (double)P), (const double2*)tmp[2], nullptr, kd, (const double2*)tmp[1], 0);
@@ -312,15 +317,19 @@ int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, double hx, double hy, int 
 template <typename real>
 static int fft_conv_launch(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, void* Fx, void* Fy) {
   using real2 = typename vec2<real>::type;
-  const int P = p->P, logP = p->logP, hp1 = P / 2 + 1, cols = cols_for<real>(P);
+  const int P = p->P, logP = p->logP, hp1 = P / 2 + 1;
+  // columns per CTA: as many as shared memory allows for big batches (coalescing), fewer for small
+  // problems so that the column kernel still fills the GPU (C3: one 89x89 instance -> 129 CTAs)
+  int cols = cols_for<real>(P);
+  while (cols > 1 && (size_t)((hp1 + cols - 1) / cols) * p->B < (size_t)2 * ctx->sm_count) cols >>= 1;
   const size_t gstride = (size_t)p->B * p->Ny * hp1;
-  size_t sm_rows = ((size_t)P + P / 2) * sizeof(real2);
-  size_t sm_cols = ((size_t)2 * cols * (P + 1) + P / 2) * sizeof(real2);
-  size_t sm_inv = ((size_t)3 * (P + 1) + P / 2) * sizeof(real2);
+  size_t sm_rows = ((size_t)P + P) * sizeof(real2);
+  size_t sm_cols = ((size_t)2 * cols * (P + 1) + P) * sizeof(real2);
+  size_t sm_inv = ((size_t)3 * (P + 1) + P) * sizeof(real2);
   const int rt = P >= 512 ? 256 : 128;
   fft_rows_fwd_kernel<real><<<dim3((p->Ny + 1) / 2, p->B), rt, sm_rows, ctx->stream>>>(
       p->Ny, p->Nx, P, logP, (const real*)rhosum, (real2*)p->ahat, (const real2*)p->tw);
-  const int ct = (P * cols) / 2 >= 2048 ? 512 : 256;
+  const int ct = (P * cols) / 2 >= 2048 ? 512 : ((P * cols) / 2 >= 256 ? 256 : 128);
   fft_cols_kernel<real, 0><<<dim3((hp1 + cols - 1) / cols, p->B), ct, sm_cols, ctx->stream>>>(
       p->Ny, p->Ny, P, logP, cols, 1.0, (const real2*)p->ahat, (const real2*)p->khat, (real2*)p->g, (const real2*)p->tw, gstride);
   fft_rows_inv_kernel<real><<<dim3((p->Ny + 1) / 2, p->B), rt, sm_inv, ctx->stream>>>(

@@ -191,99 +191,174 @@ __global__ void __launch_bounds__(BX* BY) pde_moments_kernel(StageArgs A) {
   moments_epilogue(A, b, part_w, sm, FIN_INIT);
 }
 
-// K7 fused stage kernel
-template <typename real>
+// Ticket for the last CTA of an instance; the per-CTA partial moments are already in A.partials.
+__device__ void moments_ticket(const StageArgs& A, int b, double* sm, int mode) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int nblk = gridDim.x * gridDim.y;
+  __shared__ bool is_last2;
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    unsigned prev = atomicAdd(&A.counters[b], 1u);
+    is_last2 = (prev == (unsigned)(nblk - 1));
+  }
+  __syncthreads();
+  if (is_last2) {
+    __threadfence();
+    finalize_instance(A, b, nblk, mode, sm);
+    if (tid == 0) A.counters[b] = 0;
+  }
+}
+
+// K7 fused stage kernel.  CTA = 32 x 8 grid points; all 2L density planes of the CTA's tile (with a
+// one-cell halo) and the force tiles are first staged in shared memory with bulk coalesced loads
+// (~11 independent loads in flight per thread), then every thread evaluates its grid point for all
+// planes from shared memory.  LT = compile-time L (loops unroll, centres stay in registers);
+// LT = 0 is the runtime-L fallback.
+constexpr int TW = BX + 2, TH = BY + 2;
+template <typename real, int LT>
 __global__ void __launch_bounds__(BX* BY) pde_stage_kernel(StageArgs A) {
-  const int L = A.L, Nx = A.Nx, Ny = A.Ny, b = blockIdx.z;
-  const int ix = blockIdx.x * BX + threadIdx.x, iy = blockIdx.y * BY + threadIdx.y;
-  const int tid = threadIdx.y * BX + threadIdx.x;
+  const int L = LT ? LT : A.L;
+  const int NP = 2 * L;
+  const int Nx = A.Nx, Ny = A.Ny, b = blockIdx.z;
+  const int bx0 = blockIdx.x * BX, by0 = blockIdx.y * BY;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ix = bx0 + tx, iy = by0 + ty;
+  const int tid = ty * BX + tx;
   const bool in = ix < Nx && iy < Ny;
-  const int lane = threadIdx.x, warp = threadIdx.y;
-  __shared__ double part_w[BY * 2 * LMAX * 3];
+  extern __shared__ __align__(16) unsigned char smem_stage[];
+  real* tile = reinterpret_cast<real*>(smem_stage);   // [NP][TH][TW]
+  real* sFx = tile + (size_t)NP * TH * TW;             // [BY][TW]   a * Fx with x halo
+  real* sFy = sFx + BY * TW;                           // [TH][BX]   a * Fy with y halo
+  real* mom = sFy + TH * BX;                           // [BY][NP][32]
   __shared__ double sm[2 * LMAX * 3];
   __shared__ real s_yx[LMAX], s_yy[LMAX], s_R[2][LMAX], s_zx[2], s_zy[2];
-  __shared__ real s_par[5];  // a, b, c, D, (unused)
+  __shared__ real s_par[4];
   if (tid < L) {
     s_yx[tid] = (real)A.coef[b].y[tid][0]; s_yy[tid] = (real)A.coef[b].y[tid][1];
     s_R[0][tid] = (real)A.coef[b].R[0][tid]; s_R[1][tid] = (real)A.coef[b].R[1][tid];
   }
   if (tid < 2) { s_zx[tid] = (real)A.coef[b].z[tid][0]; s_zy[tid] = (real)A.coef[b].z[tid][1]; }
   if (tid == 0) { s_par[0] = (real)A.inst[b].a; s_par[1] = (real)A.inst[b].b; s_par[2] = (real)A.inst[b].c; s_par[3] = (real)A.inst[b].D; }
-  __syncthreads();
-  const real pa = s_par[0], pb = s_par[1], pc = s_par[2], D = s_par[3];
-  const real h = (real)A.dx, ih = (real)(1.0 / A.dx), ih2 = (real)(1.0 / (A.dx * A.dx));
-  const real Ddx = (real)((double)D / A.dx), Ddy = (real)((double)D / A.dy);  // pde.jl:231-234 (Q12)
   const size_t plane = (size_t)Nx * Ny;
-  const int cx = min(ix, Nx - 1), cy = min(iy, Ny - 1);  // clamped so that out-of-grid lanes stay in bounds
-  const int xm_i = max(cx - 1, 0), xp_i = min(cx + 1, Nx - 1), ym_i = max(cy - 1, 0), yp_i = min(cy + 1, Ny - 1);
-  const size_t o_c = (size_t)cy * Nx + cx, o_xm = (size_t)cy * Nx + xm_i, o_xp = (size_t)cy * Nx + xp_i;
-  const size_t o_ym = (size_t)ym_i * Nx + cx, o_yp = (size_t)yp_i * Nx + cx;
-  const real X = (real)(A.gx0 + cx * A.dx), Y = (real)(A.gy0 + cy * A.dy);
-  const real* Fx = static_cast<const real*>(A.Fx) + (size_t)b * plane;
-  const real* Fy = static_cast<const real*>(A.Fy) + (size_t)b * plane;
-  const real aFx_c = pa * Fx[o_c], aFx_m = pa * Fx[o_xm], aFx_p = pa * Fx[o_xp];
-  const real aFy_c = pa * Fy[o_c], aFy_m = pa * Fy[o_ym], aFy_p = pa * Fy[o_yp];
-  const real* U = static_cast<const real*>(A.U) + (size_t)b * 2 * L * plane;
-  const real* un = static_cast<const real*>(A.un) + (size_t)b * 2 * L * plane;
-  real* Uout = static_cast<real*>(A.Uout) + (size_t)b * 2 * L * plane;
-  real* acc = A.acc ? static_cast<real*>(A.acc) + (size_t)b * 2 * L * plane : nullptr;
-
-  // pass 1: per medium, sum of densities and of rates at this grid point (pde.jl:220-225)
-  real rsum[2] = {0, 0}, gsum[2] = {0, 0};
-  for (int j = 0; j < L; j++) {
-    real E = fast_exp_neg_dist(X - s_yx[j], Y - s_yy[j]);
-    for (int i = 0; i < 2; i++) {
-      rsum[i] += U[(size_t)(j * 2 + i) * plane + o_c];
-      gsum[i] += E * s_R[i][j];
+  const real* U = static_cast<const real*>(A.U) + (size_t)b * NP * plane;
+  // ---- stage the tiles (clamped at the domain edge; the clamped values are never used there)
+  for (int e = tid; e < NP * TH * TW; e += BX * BY) {
+    const int p = e / (TH * TW), r = e - p * (TH * TW);
+    const int yy = r / TW, xx = r - yy * TW;
+    const int gx = min(max(bx0 + xx - 1, 0), Nx - 1), gy = min(max(by0 + yy - 1, 0), Ny - 1);
+    tile[e] = U[(size_t)p * plane + (size_t)gy * Nx + gx];
+  }
+  __syncthreads();  // s_par visible
+  {
+    const real pa0 = s_par[0];
+    const real* Fx = static_cast<const real*>(A.Fx) + (size_t)b * plane;
+    const real* Fy = static_cast<const real*>(A.Fy) + (size_t)b * plane;
+    for (int e = tid; e < BY * TW; e += BX * BY) {
+      const int yy = e / TW, xx = e - yy * TW;
+      const int gx = min(max(bx0 + xx - 1, 0), Nx - 1), gy = min(by0 + yy, Ny - 1);
+      sFx[e] = pa0 * Fx[(size_t)gy * Nx + gx];
+    }
+    for (int e = tid; e < TH * BX; e += BX * BY) {
+      const int yy = e / BX, xx = e - yy * BX;
+      const int gx = min(bx0 + xx, Nx - 1), gy = min(max(by0 + yy - 1, 0), Ny - 1);
+      sFy[e] = pa0 * Fy[(size_t)gy * Nx + gx];
     }
   }
+  __syncthreads();
+  const real pb = s_par[1], pc = s_par[2], D = s_par[3];
+  const real h = (real)A.dx, ih = (real)(1.0 / A.dx), ih2 = (real)(1.0 / (A.dx * A.dx));
+  const real Ddx = (real)((double)D / A.dx), Ddy = (real)((double)D / A.dy);  // pde.jl:231-234 (Q12)
+  const int cx = min(ix, Nx - 1), cy = min(iy, Ny - 1);
+  const real X = (real)(A.gx0 + cx * A.dx), Y = (real)(A.gy0 + cy * A.dy);
   const real bc = pb + pc;
+  // plane-independent parts of the velocity a F + b (y_j - x) + c (z_i - x)   (pde.jl:214)
+  const real vxc0 = sFx[ty * TW + tx + 1] - bc * X, vxm0 = sFx[ty * TW + tx] - bc * (X - h), vxp0 = sFx[ty * TW + tx + 2] - bc * (X + h);
+  const real vyc0 = sFy[(ty + 1) * BX + tx] - bc * Y, vym0 = sFy[ty * BX + tx] - bc * (Y - h), vyp0 = sFy[(ty + 2) * BX + tx] - bc * (Y + h);
+  const bool x_lo = cx == 0, x_hi = cx == Nx - 1, y_lo = cy == 0, y_hi = cy == Ny - 1;
+  const real* tc = tile + (ty + 1) * TW + tx + 1;  // centre of plane 0
+
+  // per medium: sum of densities and of rates at this grid point (pde.jl:220-225)
+  real rsum[2] = {0, 0}, gsum[2] = {0, 0};
+  real E[LT ? LT : 1];
+#pragma unroll
+  for (int j = 0; j < L; j++) {
+    const real Ej = fast_exp_neg_dist(X - s_yx[j], Y - s_yy[j]);
+    if (LT) E[LT ? j : 0] = Ej;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      rsum[i] += tc[(j * 2 + i) * TH * TW];
+      gsum[i] += Ej * s_R[i][j];
+    }
+  }
+  const real* un = static_cast<const real*>(A.un) + (size_t)b * NP * plane;
+  real* Uout = static_cast<real*>(A.Uout) + (size_t)b * NP * plane;
+  real* acc = A.acc ? static_cast<real*>(A.acc) + (size_t)b * NP * plane : nullptr;
+  const size_t o_c = (size_t)cy * Nx + cx;
   const real dtA = (real)A.A, dtB = (real)A.Bc, dtC = (real)(A.C * A.dt), dtw = (real)(A.bw * A.dt);
   real rs_out = 0;
+#pragma unroll
   for (int j = 0; j < L; j++) {
-    const real E = fast_exp_neg_dist(X - s_yx[j], Y - s_yy[j]);
+    const real Ej = LT ? E[LT ? j : 0] : fast_exp_neg_dist(X - s_yx[j], Y - s_yy[j]);
+#pragma unroll
     for (int i = 0; i < 2; i++) {
-      const size_t po = (size_t)(j * 2 + i) * plane;
-      const real c = U[po + o_c], vxm = U[po + o_xm], vxp = U[po + o_xp], vym = U[po + o_ym], vyp = U[po + o_yp];
-      // velocity = a F + b (y_j - x) + c (z_i - x)   (pde.jl:214)
-      const real bx = pb * s_yx[j] + pc * s_zx[i], by = pb * s_yy[j] + pc * s_zy[i];
-      const real fxc = c * (aFx_c + bx - bc * X), fxm = vxm * (aFx_m + bx - bc * (X - h)), fxp = vxp * (aFx_p + bx - bc * (X + h));
-      const real fyc = c * (aFy_c + by - bc * Y), fym = vym * (aFy_m + by - bc * (Y - h)), fyp = vyp * (aFy_p + by - bc * (Y + h));
-      // divergence with C (pde.jl:79-87,216-217) and diffusion with MassM (pde.jl:68-77,228); the
+      const int p = j * 2 + i;
+      const real* t = tc + p * TH * TW;
+      const real c = t[0], vxm = t[-1], vxp = t[1], vym = t[-TW], vyp = t[TW];
+      const real bxv = pb * s_yx[j] + pc * s_zx[i], byv = pb * s_yy[j] + pc * s_zy[i];
+      const real fxc = c * (vxc0 + bxv), fxm = vxm * (vxm0 + bxv), fxp = vxp * (vxp0 + bxv);
+      const real fyc = c * (vyc0 + byv), fym = vym * (vym0 + byv), fyp = vyp * (vyp0 + byv);
+      // divergence with C (pde.jl:79-87,216-217), diffusion with MassM (pde.jl:68-77,228); the
       // reference builds both operators from dx and applies them in x AND y
-      real ddx, lapx, ddy, lapy, bnd = 0;
-      if (cx == 0) { ddx = (fxp - fxc) * ih; lapx = (vxp - c) * ih2; bnd -= Ddx * fxc; }
-      else if (cx == Nx - 1) { ddx = (fxc - fxm) * ih; lapx = (vxm - c) * ih2; bnd += Ddx * fxc; }
-      else { ddx = (fxp - fxm) * ((real)0.5 * ih); lapx = (vxm - (real)2 * c + vxp) * ih2; }
-      if (cy == 0) { ddy = (fyp - fyc) * ih; lapy = (vyp - c) * ih2; bnd -= Ddy * fyc; }
-      else if (cy == Ny - 1) { ddy = (fyc - fym) * ih; lapy = (vym - c) * ih2; bnd += Ddy * fyc; }
-      else { ddy = (fyp - fym) * ((real)0.5 * ih); lapy = (vym - (real)2 * c + vyp) * ih2; }
-      const real G = E * s_R[i][j];
+      real ddx = (fxp - fxm) * ((real)0.5 * ih), lapx = (vxm - (real)2 * c + vxp) * ih2;
+      real ddy = (fyp - fym) * ((real)0.5 * ih), lapy = (vym - (real)2 * c + vyp) * ih2, bnd = 0;
+      if (x_lo) { ddx = (fxp - fxc) * ih; lapx = (vxp - c) * ih2; bnd -= Ddx * fxc; }
+      if (x_hi) { ddx = (fxc - fxm) * ih; lapx = (vxm - c) * ih2; bnd += Ddx * fxc; }
+      if (y_lo) { ddy = (fyp - fyc) * ih; lapy = (vyp - c) * ih2; bnd -= Ddy * fyc; }
+      if (y_hi) { ddy = (fyc - fym) * ih; lapy = (vym - c) * ih2; bnd += Ddy * fyc; }
+      const real G = Ej * s_R[i][j];
       const real reac = -c * (gsum[i] - G) + G * (rsum[i] - c);
       const real k = D * (lapx + lapy) + bnd - (ddx + ddy) + reac;  // pde.jl:236
-      // RK stage update
+      const size_t po = (size_t)p * plane + o_c;
       real out = dtC * k;
-      if (dtA != (real)0) out += dtA * un[po + o_c];
+      if (dtA != (real)0) out += dtA * un[po];
       if (dtB != (real)0) out += dtB * c;
-      if (A.acc_mode == ACC_INIT) { if (in) acc[po + o_c] = un[po + o_c] + dtw * k; }
-      else if (A.acc_mode == ACC_ADD) { if (in) acc[po + o_c] += dtw * k; }
-      else if (A.acc_mode == ACC_FINAL) out = acc[po + o_c] + dtw * k;
-      if (in) Uout[po + o_c] = out;
-      if (A.do_moments) {
-        const real v = in ? out : (real)0;
-        rs_out += v;
-        real s0 = warp_sum(v), s1 = warp_sum(v * X);
-        if (lane == 0) {
-          double* o = part_w + (warp * 2 * L + (j * 2 + i)) * 3;
-          o[0] = (double)s0; o[1] = (double)s1; o[2] = (double)s0 * (double)Y;
-        }
+      if (A.acc_mode == ACC_INIT) { if (in) acc[po] = un[po] + dtw * k; }
+      else if (A.acc_mode == ACC_ADD) { if (in) acc[po] += dtw * k; }
+      else if (A.acc_mode == ACC_FINAL) out = acc[po] + dtw * k;
+      if (in) Uout[po] = out;
+      const real v = in ? out : (real)0;
+      rs_out += v;
+      mom[(ty * NP + p) * 32 + tx] = v;
+    }
+  }
+  if (!A.do_moments) return;
+  if (in) static_cast<real*>(A.rhosum_out)[(size_t)b * plane + o_c] = rs_out;
+  __syncthreads();
+  // block-level moments: warp `w` reduces plane w, w + 8, ..: column sums over the 8 rows in fixed
+  // order, then one shuffle tree over the 32 columns (deterministic)
+  {
+    const int nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
+    const real Xl = (real)(A.gx0 + min(bx0 + tx, Nx - 1) * A.dx);
+    for (int p = ty; p < NP; p += BY) {
+      real s0 = 0, sy = 0;
+#pragma unroll
+      for (int w = 0; w < BY; w++) {
+        const real v = mom[(w * NP + p) * 32 + tx];
+        s0 += v;
+        sy += v * (real)(A.gy0 + min(by0 + w, Ny - 1) * A.dy);
+      }
+      real sx = warp_sum(s0 * Xl);
+      s0 = warp_sum(s0);
+      sy = warp_sum(sy);
+      if (tx == 0) {
+        double* o = A.partials + ((size_t)b * nblk + blk) * (NP * 3) + p * 3;
+        o[0] = (double)s0; o[1] = (double)sx; o[2] = (double)sy;
+        __threadfence();
       }
     }
   }
-  if (A.do_moments) {
-    if (in) static_cast<real*>(A.rhosum_out)[(size_t)b * plane + o_c] = rs_out;
-    moments_epilogue(A, b, part_w, sm, FIN_STAGE);
-  }
+  moments_ticket(A, b, sm, FIN_STAGE);
 }
 
 // K6 direct Toeplitz correlation.  CTA = 8x8 output points x NS input slices; wext[ady][d + Nx-1]
@@ -431,13 +506,27 @@ static int launch_conv(smm_ctx* ctx, smm_pde_batch* pb) {
   return SMM_OK;
 }
 
-static int launch_stage(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
+static size_t stage_smem(int L, size_t rs) { return rs * ((size_t)2 * L * TH * TW + BY * TW + TH * BX + (size_t)BY * 2 * L * 32); }
+
+template <typename real, int LT>
+static int launch_stage_t(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
   dim3 grid(pb->nbx, pb->nby, pb->B), block(BX, BY);
-  if (pb->precision == SMM_PREC_F64) pde_stage_kernel<double><<<grid, block, 0, ctx->stream>>>(A);
-  else pde_stage_kernel<float><<<grid, block, 0, ctx->stream>>>(A);
+  const size_t sm = stage_smem(pb->L, sizeof(real));
+  if (sm > 48 * 1024) SMM_CUDA(ctx, cudaFuncSetAttribute(pde_stage_kernel<real, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  pde_stage_kernel<real, LT><<<grid, block, sm, ctx->stream>>>(A);
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;
+}
+
+static int launch_stage(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
+  const bool f64 = pb->precision == SMM_PREC_F64;
+  switch (pb->L) {
+    case 4: return f64 ? launch_stage_t<double, 4>(ctx, pb, A) : launch_stage_t<float, 4>(ctx, pb, A);
+    case 5: return f64 ? launch_stage_t<double, 5>(ctx, pb, A) : launch_stage_t<float, 5>(ctx, pb, A);
+    case 6: return f64 ? launch_stage_t<double, 6>(ctx, pb, A) : launch_stage_t<float, 6>(ctx, pb, A);
+    default: return f64 ? launch_stage_t<double, 0>(ctx, pb, A) : launch_stage_t<float, 0>(ctx, pb, A);
+  }
 }
 
 // one RK step = nstages x (conv, stage).  Buffer roles: u = step start / result, Ua/Ub stage states.

@@ -1,0 +1,37 @@
+"""Print the key metrics (+ top source lines by stall samples) of an .ncu-rep:  python tools_ncu_summary.py rep [kernel_index]"""
+import csv
+import subprocess
+import sys
+
+KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
+        'launch__occupancy_limit_warps', 'launch__grid_size', 'launch__block_size', 'smsp__inst_executed.sum',
+        'smsp__thread_inst_executed_per_inst_executed.ratio', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__inst_executed_op_shared_ld.sum', 'smsp__inst_executed_op_shared_st.sum',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
+        'lts__t_bytes.sum', 'sm__cycles_elapsed.avg']
+
+
+def main(rep, idx=0):
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h = rows[0]
+    v = rows[2 + idx]
+    ki = h.index('Kernel Name')
+    print('kernel:', v[ki][:90])
+    stalls = []
+    for i, n in enumerate(h):
+        if n in KEYS:
+            print(f'  {n:80s} {rows[1][i]:10s} {v[i]}')
+        if 'issue_stalled' in n and 'per_issue_active' in n and 'not_issued' not in n:
+            stalls.append((float(v[i]), n.split('issue_stalled_')[1].split('_per_issue')[0]))
+    print('  stalls/issue:', ', '.join(f'{n}={x:.2f}' for x, n in sorted(stalls, reverse=True)[:7]))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0)
