@@ -32,7 +32,8 @@ struct PopArgs {
   unsigned char* follow;
   const signed char* state;
   const int32_t* rowptr;  // null = all-to-all
-  const int32_t* colidx;
+  const int32_t* colidx;  // SELL-32: colidx[slice_ptr[j/32] + t*32 + (j%32)] = t-th neighbour of agent j
+  const int64_t* slice_ptr;
   const double* ent_old;  // [2][L+M]: x block then y block
   double* ent_new;
   const long long* acc_read;  // [2L][3]
@@ -64,6 +65,19 @@ __global__ void __launch_bounds__(kPopThreads) pop_accumulate_kernel(int n, int 
   __syncthreads();
   for (int t = threadIdx.x; t < 2 * L * 3; t += blockDim.x)
     if (bins[t] != 0) atomicAdd(reinterpret_cast<unsigned long long*>(&acc[t]), (unsigned long long)bins[t]);
+}
+
+// random 8/16-byte gathers have no reuse within a CTA: read-only path, do not allocate in L1 (keeps the
+// colidx rows, which every thread re-reads sector by sector, resident there)
+__device__ __forceinline__ float2 ld_gather(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ld_gather(const double2* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
 }
 
 template <typename real>
@@ -150,10 +164,13 @@ __global__ void __launch_bounds__(kPopThreads) pop_step_kernel(PopArgs A) {
     const real2 xj = xo[j];
     real ax = 0, ay = 0, ws = 0;
     if (A.rowptr) {
+      // sliced-ELL neighbour lists: lane l of a warp reads colidx[sp + t*32 + l] -> one coalesced
+      // wavefront per neighbour slot instead of 32 (per-thread CSR rows made this kernel L1-bound)
       const int e0 = A.rowptr[j], e1 = valid ? A.rowptr[j + 1] : e0;
+      const int32_t* nb = A.colidx + (valid ? A.slice_ptr[(base + tid) >> 5] : 0) + (tid & 31);
 #pragma unroll 4
-      for (int e = e0; e < e1; e++) {  // abm.jl:51,57-62
-        real2 p = xo[A.colidx[e]];
+      for (int e = e0; e < e1; e++, nb += 32) {  // abm.jl:51,57-62
+        real2 p = ld_gather(xo + *nb);
         real dx = p.x - xj.x, dy = p.y - xj.y;
         real w = w_of_r2(dx * dx + dy * dy);
         ws += w; ax += w * dx; ay += w * dy;
@@ -231,6 +248,19 @@ __global__ void cvt_kernel(const Tin* __restrict__ in, Tout* __restrict__ out, s
   for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) out[j] = (Tout)in[j];
 }
 
+// CSR -> SELL-32 (one warp per slice of 32 consecutive agents; padding = the agent itself, never read)
+__global__ void csr_to_sell_kernel(int n, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ csr,
+                                   const int64_t* __restrict__ slice_ptr, int32_t* __restrict__ sell) {
+  const int lane = threadIdx.x & 31;
+  const size_t slice = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t j = slice * 32 + lane;
+  if (slice * 32 >= (size_t)n) return;
+  const int64_t sp = slice_ptr[slice];
+  const int width = (int)((slice_ptr[slice + 1] - sp) >> 5);
+  const int e0 = j < (size_t)n ? rowptr[j] : 0, deg = j < (size_t)n ? rowptr[j + 1] - e0 : 0;
+  for (int t = 0; t < width; t++) sell[sp + (int64_t)t * 32 + lane] = t < deg ? csr[e0 + t] : (int32_t)(j < (size_t)n ? j : 0);
+}
+
 size_t pop_smem_bytes(int L, int M) {
   return (size_t)2 * L * 3 * 8 + sizeof(double) * (4 * (L + M) + L) + sizeof(float) * (3 * L + 2) + sizeof(double) * (kPopThreads / 32) * L + 16;
 }
@@ -267,6 +297,7 @@ int smm_launch_pop_step(smm_ctx* ctx, smm_abm_pop* p, const void* xi, const doub
   A.x_old = p->x[cur]; A.x_new = p->x[cur ^ 1];
   A.follow = p->follow; A.state = p->state;
   A.rowptr = p->has_net ? p->rowptr : nullptr; A.colidx = p->has_net ? p->colidx : nullptr;
+  A.slice_ptr = p->has_net ? p->slice_ptr : nullptr;
   A.ent_old = p->ent[cur]; A.ent_new = p->ent[cur ^ 1];
   A.acc_read = p->acc[p->step % 3]; A.acc_write = p->acc[(p->step + 1) % 3]; A.acc_clear = p->acc[(p->step + 2) % 3];
   A.xi = xi; A.u1 = u1; A.u2 = u2;
@@ -326,6 +357,14 @@ int smm_launch_convert_i32_to_u8(smm_ctx* ctx, const int32_t* in, unsigned char*
 }
 int smm_launch_convert_u8_to_i32(smm_ctx* ctx, const unsigned char* in, int32_t* out, size_t count) {
   cvt_kernel<unsigned char, int32_t><<<strided_grid(ctx, count), 256, 0, ctx->stream>>>(in, out, count);
+  ctx->launches++;
+  SMM_CUDA(ctx, cudaGetLastError());
+  return SMM_OK;
+}
+
+int smm_launch_csr_to_sell(smm_ctx* ctx, int n, const int32_t* rowptr, const int32_t* csr, const int64_t* slice_ptr, int32_t* sell) {
+  const size_t nslices = ((size_t)n + 31) / 32;
+  csr_to_sell_kernel<<<(unsigned)((nslices * 32 + 255) / 256), 256, 0, ctx->stream>>>(n, rowptr, csr, slice_ptr, sell);
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;

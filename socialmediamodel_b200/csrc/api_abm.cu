@@ -545,6 +545,7 @@ static void pop_free(smm_abm_pop* p) {
   if (p->state) cudaFree(p->state);
   if (p->rowptr) cudaFree(p->rowptr);
   if (p->colidx) cudaFree(p->colidx);
+  if (p->slice_ptr) cudaFree(p->slice_ptr);
   if (p->fallback_count) cudaFree(p->fallback_count);
   delete p;
 }
@@ -619,10 +620,24 @@ extern "C" int smm_abm_pop_create(smm_ctx* ctx, const smm_params* q, int32_t pre
   POP_CUDA(cudaMalloc((void**)&p->fallback_count, 8));
   POP_CUDA(cudaMemsetAsync(p->fallback_count, 0, 8, ctx->stream));
   if (rowptr) {
+    // neighbour lists are kept in sliced-ELL form (slices of 32 agents, width = max degree of the slice)
+    const size_t nslices = (n + 31) / 32;
+    std::vector<int64_t> sp(nslices + 1, 0);
+    for (size_t sl = 0; sl < nslices; sl++) {
+      int w = 0;
+      for (size_t j = sl * 32; j < std::min(n, sl * 32 + 32); j++) w = std::max(w, rowptr[j + 1] - rowptr[j]);
+      sp[sl + 1] = sp[sl] + (int64_t)w * 32;
+    }
+    const size_t sell_count = std::max((size_t)sp[nslices], (size_t)1);
     POP_CUDA(cudaMalloc((void**)&p->rowptr, (n + 1) * 4));
-    POP_CUDA(cudaMalloc((void**)&p->colidx, std::max(nnz, (size_t)1) * 4));
+    POP_CUDA(cudaMalloc((void**)&p->colidx, sell_count * 4));
+    POP_CUDA(cudaMalloc((void**)&p->slice_ptr, (nslices + 1) * 8));
     POP_CUDA(cudaMemcpyAsync(p->rowptr, rowptr, (n + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    POP_CUDA(cudaMemcpyAsync(p->colidx, colidx, nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    POP_CUDA(cudaMemcpyAsync(p->slice_ptr, sp.data(), (nslices + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    void* csr;
+    POP_TRY(upload(ctx, S_COLIDX, colidx, std::max(nnz, (size_t)1) * 4, &csr));
+    POP_TRY(smm_launch_csr_to_sell(ctx, (int)n, p->rowptr, (const int32_t*)csr, p->slice_ptr, p->colidx));
+    POP_CUDA(cudaStreamSynchronize(ctx->stream));  // sp goes out of scope
   }
   void* tmp;
   POP_TRY(upload(ctx, S_STAGE, x0, n * 2 * 8, &tmp));

@@ -82,7 +82,8 @@ struct smm_abm_pop {
   unsigned char* follow;  // [n]
   signed char* state;     // [n]
   int32_t* rowptr;
-  int32_t* colidx;
+  int32_t* colidx;     // SELL-32 layout (see abm_csr.cu)
+  int64_t* slice_ptr;  // [n/32 + 1] offsets into colidx
   double* ent[2];    // [2][L+M] influencer then media positions (x block, y block), double-buffered
   long long* acc[3]; // fixed-point class sums [2L][3] = (sum x, sum y, count), 3-way rotation
   unsigned long long* fallback_count;  // FP64 re-evaluations of the switch decision so far
@@ -90,6 +91,7 @@ struct smm_abm_pop {
 };
 int smm_launch_pop_accumulate(smm_ctx* ctx, smm_abm_pop* p, int buf, int accslot);
 int smm_launch_pop_step(smm_ctx* ctx, smm_abm_pop* p, const void* xi, const double* u1, const double* u2);
+int smm_launch_csr_to_sell(smm_ctx* ctx, int n, const int32_t* rowptr, const int32_t* csr, const int64_t* slice_ptr, int32_t* sell);
 int smm_launch_pack_xy(smm_ctx* ctx, const double* xy, void* x2, size_t n, int precision);    // [2][n] f64 -> real2[n]
 int smm_launch_unpack_xy(smm_ctx* ctx, const void* x2, double* xy, size_t n, int precision);  // real2[n] -> [2][n] f64
 int smm_launch_convert_i32_to_u8(smm_ctx* ctx, const int32_t* in, unsigned char* out, size_t count);
