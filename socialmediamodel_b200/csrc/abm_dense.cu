@@ -36,7 +36,10 @@ __global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) 
   int* bcnt = reinterpret_cast<int*>(bsy + (L + M));       // [L+M]
   int* bss = bcnt + (L + M);                               // [L+M] sum of states per bin
   int* fol = bss + (L + M);                                // [npad]
-  signed char* st = reinterpret_cast<signed char*>(fol + npad);  // [npad]
+  float* finx = reinterpret_cast<float*>(fol + npad);      // [L] FP32 copies of the UPDATED influencers / fractions
+  float* finy = finx + L;                                  //     for the guarded FP32 switch decision
+  float* ffr = finy + L;
+  signed char* st = reinterpret_cast<signed char*>(ffr + L);  // [npad]
 
   // ---- load the initial condition --------------------------------------------------------
   const real* x0 = static_cast<const real*>(A.x0) + (size_t)r * 2 * n;
@@ -157,7 +160,9 @@ __global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) 
       py = reflect1(py, K.lo1, K.hi1);
       if (is_inf) {
         infx[nxt * L + e] = px; infy[nxt * L + e] = py;
-        frac[e] = (double)bss[e] / (double)cnt;  // abm.jl:99; 0/0 = NaN (Q5)
+        const double fr_e = (double)bss[e] / (double)cnt;  // abm.jl:99; 0/0 = NaN (Q5)
+        frac[e] = fr_e;
+        finx[e] = (float)px; finy[e] = (float)py; ffr[e] = (float)fr_e;
       } else {
         medx[nxt * M + e] = px; medy[nxt * M + e] = py;
       }
@@ -190,7 +195,13 @@ __global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) 
       xn0 = reflect1(xn0, K.lo0, K.hi0);           // abm.jl:201
       xn1 = reflect1(xn1, K.lo1, K.hi1);
       // abm.jl:207: OLD x, OLD follower fractions, UPDATED influencers (Q1)
-      int fnew = switch_decision_f64(x, y, sj, fj, infx + nxt * L, infy + nxt * L, frac, L, K.eta, K.dt, u1, u2);
+      // Philox uniforms are 24-bit (exact in FP32): decide in FP32 with a guard band, Float64 inside it
+      int fnew = fj;
+      bool decided = false;
+      if (sizeof(real) == 4 && A.noise_mode != SMM_NOISE_INJECTED)
+        decided = switch_decision_f32_guarded((float)xj.x, (float)xj.y, sj, fj, finx, finy, ffr, L, (float)K.eta, (float)K.dt,
+                                              (float)u1, (float)u2, 2e-5f, &fnew);
+      if (!decided) fnew = switch_decision_f64(x, y, sj, fj, infx + nxt * L, infy + nxt * L, frac, L, K.eta, K.dt, u1, u2);
       xn[j] = mk2((real)xn0, (real)xn1);
       fol[j] = fnew;  // only this thread reads fol[j] during P3
     };
@@ -297,7 +308,7 @@ __global__ void abm_draws_kernel(int n, uint64_t seed, uint32_t realization, int
 size_t dense_smem_bytes(int n, int L, int M, size_t real_size) {
   int npad = (n + 3) & ~3;
   return 2 * (size_t)npad * 2 * real_size + sizeof(double) * (4 * L + 4 * M + L + 2 * (L + M)) +
-         sizeof(int) * (2 * (L + M) + npad) + npad + 16;
+         sizeof(int) * (2 * (L + M) + npad) + sizeof(float) * 3 * L + npad + 16;
 }
 
 }  // namespace

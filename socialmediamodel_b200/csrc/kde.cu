@@ -11,27 +11,40 @@
 
 namespace {
 
-constexpr int KC = 32;  // agents per staged chunk
-constexpr int TX = 8, TY = 4;
+__device__ __forceinline__ void ld4(float* d, const float* s) {
+  float4 a = *reinterpret_cast<const float4*>(s);
+  d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+}
+__device__ __forceinline__ void ld4(double* d, const double* s) {
+  double2 a = reinterpret_cast<const double2*>(s)[0], b = reinterpret_cast<const double2*>(s)[1];
+  d[0] = a.x; d[1] = a.y; d[2] = b.x; d[3] = b.y;
+}
+
+constexpr int KC = 32;            // agents per staged chunk
+constexpr int KW = 8;             // warps per CTA
+constexpr int TXL = 3;            // x columns per lane (stride 32)  -> 96 columns per pass
+constexpr int TYW = 12;           // y rows per warp                 -> 96 rows per pass
+constexpr int SPAN = 96;
 
 __device__ __forceinline__ float gauss1d(float d, float inv2s2) { return __expf(-d * d * inv2s2); }
 __device__ __forceinline__ double gauss1d(double d, double inv2s2) { return exp(-d * d * inv2s2); }
 
+// One CTA (8 warps) per snapshot.  Lane l of every warp owns grid columns l, l+32, l+64 of the current
+// 96-column pass, warp w owns rows 12w..12w+11: per staged agent a thread reads 3 ex values
+// (consecutive lanes -> conflict-free) and 12 ey values (same address in all lanes -> broadcast, as
+// three 128-bit loads) for 36 FMAs, and the stores of a warp are 128-byte contiguous rows.
 template <typename real>
-__global__ void kde_kernel(KdeArgs A) {
+__global__ void __launch_bounds__(KW * 32) kde_kernel(KdeArgs A) {
   const int n = A.n, L = A.L, Nx = A.Nx, Ny = A.Ny;
   const int ncls = 2 * L;
   const int s = blockIdx.x;
   const int r = s / A.nsave;
-  const int txn = blockDim.x, tyn = blockDim.y;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int tid = ty * txn + tx, nthreads = txn * tyn;
-  const int NxP = (Nx + TX - 1) / TX * TX, NyP = (Ny + TY - 1) / TY * TY;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = KW * 32;
 
   extern __shared__ __align__(16) unsigned char smem[];
-  real* ex = reinterpret_cast<real*>(smem);        // [KC][NxP]
-  real* ey = ex + (size_t)KC * NxP;                // [KC][NyP]
-  real* ax = ey + (size_t)KC * NyP;                // [n] agent x sorted by class
+  real* ex = reinterpret_cast<real*>(smem);        // [KC][SPAN]
+  real* ey = ex + (size_t)KC * SPAN;               // [KC][SPAN]
+  real* ax = ey + (size_t)KC * SPAN;               // [n] agent x sorted by class
   real* ay = ax + n;                               // [n]
   int* off = reinterpret_cast<int*>(ay + n);       // [ncls+1]
 
@@ -62,50 +75,45 @@ __global__ void kde_kernel(KdeArgs A) {
   const real scale = (real)(1.0 / (double)n / (2.0 * 3.14159265358979323846 * A.sigma * A.sigma));
   real* us = static_cast<real*>(A.us) + (size_t)s * ncls * Nx * Ny;
 
-  for (int sy0 = 0; sy0 < NyP; sy0 += tyn * TY) {
-    for (int sx0 = 0; sx0 < NxP; sx0 += txn * TX) {
-      const int ix0 = sx0 + tx * TX, iy0 = sy0 + ty * TY;
-      const bool active = ix0 < NxP && iy0 < NyP;
+  for (int sy0 = 0; sy0 < Ny; sy0 += SPAN) {
+    for (int sx0 = 0; sx0 < Nx; sx0 += SPAN) {
+      const int iy0 = sy0 + warp * TYW;
       for (int c = 0; c < ncls; c++) {
-        real acc[TY][TX];
+        real acc[TYW][TXL];
 #pragma unroll
-        for (int b = 0; b < TY; b++)
+        for (int b = 0; b < TYW; b++)
 #pragma unroll
-          for (int a = 0; a < TX; a++) acc[b][a] = 0;
+          for (int a = 0; a < TXL; a++) acc[b][a] = 0;
         for (int k0 = off[c]; k0 < off[c + 1]; k0 += KC) {
           const int kc = min(KC, off[c + 1] - k0);
           __syncthreads();  // previous chunk fully consumed
-          for (int e = tid; e < kc * NxP; e += nthreads) {
-            int k = e / NxP, ix = e - k * NxP;
-            ex[e] = ix < Nx ? gauss1d((real)(A.gx0 + ix * A.dx) - ax[k0 + k], inv2s2) : (real)0;
-          }
-          for (int e = tid; e < kc * NyP; e += nthreads) {
-            int k = e / NyP, iy = e - k * NyP;
-            ey[e] = iy < Ny ? gauss1d((real)(A.gy0 + iy * A.dy) - ay[k0 + k], inv2s2) : (real)0;
+          for (int e = tid; e < kc * SPAN; e += nthreads) {
+            const int k = e / SPAN, i = e - k * SPAN;
+            const int gx = sx0 + i, gy = sy0 + i;
+            ex[e] = gx < Nx ? gauss1d((real)(A.gx0 + gx * A.dx) - ax[k0 + k], inv2s2) : (real)0;
+            ey[e] = gy < Ny ? gauss1d((real)(A.gy0 + gy * A.dy) - ay[k0 + k], inv2s2) : (real)0;
           }
           __syncthreads();
-          if (active) {
-            for (int k = 0; k < kc; k++) {
-              real vx[TX], vy[TY];
+          for (int k = 0; k < kc; k++) {
+            real vx[TXL], vy[TYW];
 #pragma unroll
-              for (int a = 0; a < TX; a++) vx[a] = ex[k * NxP + ix0 + a];
+            for (int a = 0; a < TXL; a++) vx[a] = ex[k * SPAN + lane + 32 * a];
 #pragma unroll
-              for (int b = 0; b < TY; b++) vy[b] = ey[k * NyP + iy0 + b];
+            for (int b = 0; b < TYW; b += 4) ld4(vy + b, ey + k * SPAN + warp * TYW + b);
 #pragma unroll
-              for (int b = 0; b < TY; b++)
+            for (int b = 0; b < TYW; b++)
 #pragma unroll
-                for (int a = 0; a < TX; a++) acc[b][a] += vx[a] * vy[b];
-            }
+              for (int a = 0; a < TXL; a++) acc[b][a] += vx[a] * vy[b];
           }
         }
-        if (active) {
-          real* o = us + (size_t)c * Nx * Ny;
+        real* o = us + (size_t)c * Nx * Ny;
 #pragma unroll
-          for (int b = 0; b < TY; b++)
+        for (int b = 0; b < TYW; b++)
 #pragma unroll
-            for (int a = 0; a < TX; a++)
-              if (ix0 + a < Nx && iy0 + b < Ny) o[(size_t)(iy0 + b) * Nx + ix0 + a] = acc[b][a] * scale;
-        }
+          for (int a = 0; a < TXL; a++) {
+            const int gx = sx0 + lane + 32 * a, gy = iy0 + b;
+            if (gx < Nx && gy < Ny) o[(size_t)gy * Nx + gx] = acc[b][a] * scale;
+          }
       }
     }
   }
@@ -131,22 +139,15 @@ __global__ void convert_kernel(const Tin* __restrict__ in, Tout* __restrict__ ou
 
 int smm_launch_kde(smm_ctx* ctx, const KdeArgs& A, int precision) {
   if (A.S <= 0) return SMM_OK;
-  int txn = (A.Nx + TX - 1) / TX;
-  if (txn > 32) txn = 32;
-  int tyn = (A.Ny + TY - 1) / TY;
-  int maxy = 512 / txn;
-  if (tyn > maxy) tyn = maxy;
   size_t rs = precision == SMM_PREC_F64 ? 8 : 4;
-  int NxP = (A.Nx + TX - 1) / TX * TX, NyP = (A.Ny + TY - 1) / TY * TY;
-  size_t sm = rs * ((size_t)KC * (NxP + NyP) + 2 * (size_t)A.n) + sizeof(int) * (4 * A.L + 2) + 16;
-  SMM_REQUIRE(ctx, sm <= 227 * 1024, "KDE kernel: n=%d / grid %dx%d need %zu B of shared memory", A.n, A.Nx, A.Ny, sm);
-  dim3 block(txn, tyn);
+  size_t sm = rs * ((size_t)2 * KC * SPAN + 2 * (size_t)A.n) + sizeof(int) * (2 * A.L + 2) + 16;
+  SMM_REQUIRE(ctx, sm <= 227 * 1024, "KDE kernel: n=%d needs %zu B of shared memory", A.n, sm);
   if (precision == SMM_PREC_F64) {
-    SMM_CUDA(ctx, cudaFuncSetAttribute(kde_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    kde_kernel<double><<<A.S, block, sm, ctx->stream>>>(A);
+    if (sm > 48 * 1024) SMM_CUDA(ctx, cudaFuncSetAttribute(kde_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kde_kernel<double><<<A.S, KW * 32, sm, ctx->stream>>>(A);
   } else {
-    SMM_CUDA(ctx, cudaFuncSetAttribute(kde_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    kde_kernel<float><<<A.S, block, sm, ctx->stream>>>(A);
+    if (sm > 48 * 1024) SMM_CUDA(ctx, cudaFuncSetAttribute(kde_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    kde_kernel<float><<<A.S, KW * 32, sm, ctx->stream>>>(A);
   }
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());
