@@ -48,7 +48,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
@@ -56,7 +56,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """start of the timed region: only samples taken after this are summarised"""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -65,7 +69,9 @@ class ClockSampler:
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        rows = [r for t, r in self.rows if t >= t_mark] or [r for t, r in self.rows[-3:]]
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -150,14 +156,15 @@ def run_abm_ensemble(args, rank, world, local):
             import torch.distributed as dist
             dist.all_reduce(sum_us); dist.all_reduce(sum_zs); dist.all_reduce(sum_ys)
 
+    sampler = ClockSampler(local); sampler.start()   # started before the warm-up so it is sampling by the timed region
     for _ in range(args.warmup):
         one_pass(); flush.fill_(1)
     barrier(world)
-    sampler = ClockSampler(local); sampler.start()
     l0 = ctx.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     kms = {"abm": [], "kde": [], "reduce": []}
     barrier(world)
+    sampler.mark()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         ev[k][0].record(stream)
@@ -342,7 +349,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--realizations", type=int, default=0, help="realizations per GPU (default 1024)")

@@ -193,15 +193,19 @@ __global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, int P
   const bool hasb = rb < Ny;
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < P; i += nt) tw[i] = twg[i];
+  // the DIT inverse wants its input bit-reversed: iterate over shared-memory positions (conflict-free
+  // stores) and fetch spectrum index brev(pos) from the 4 KB global row (L1-resident) -- scattering
+  // into bit-reversed shared addresses instead was a 32-way bank conflict
   for (int e = tid; e < 3 * P; e += nt) {
-    const int k = e / P, kk = e - k * P;
+    const int k = e / P, pos = e - k * P;
+    const int kk = brev_p(pos, logP);
     const bool up = kk > P / 2;
     const int src = up ? P - kk : kk;
     const real2* Gk = G + (size_t)k * gstride + (size_t)b * Ny * hp1;
     real2 a = Gk[(size_t)ra * hp1 + src];
     real2 bb = hasb ? Gk[(size_t)rb * hp1 + src] : mk2((real)0, (real)0);
     if (up) { a.y = -a.y; bb.y = -bb.y; }
-    sh[k * cs + brev_p(kk, logP)] = mk2(a.x - bb.y, a.y + bb.x);  // A + i B
+    sh[k * cs + pos] = mk2(a.x - bb.y, a.y + bb.x);  // A + i B
   }
   __syncthreads();
   fft_dit_inv<real>(sh, 3, cs, P, logP, tw);

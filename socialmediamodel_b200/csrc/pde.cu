@@ -217,7 +217,7 @@ __device__ void moments_ticket(const StageArgs& A, int b, double* sm, int mode) 
 // LT = 0 is the runtime-L fallback.
 constexpr int TW = BX + 2, TH = BY + 2;
 template <typename real, int LT>
-__global__ void __launch_bounds__(BX* BY) pde_stage_kernel(StageArgs A) {
+__global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_kernel(StageArgs A) {
   const int L = LT ? LT : A.L;
   const int NP = 2 * L;
   const int Nx = A.Nx, Ny = A.Ny, b = blockIdx.z;
@@ -243,11 +243,25 @@ __global__ void __launch_bounds__(BX* BY) pde_stage_kernel(StageArgs A) {
   const size_t plane = (size_t)Nx * Ny;
   const real* U = static_cast<const real*>(A.U) + (size_t)b * NP * plane;
   // ---- stage the tiles (clamped at the domain edge; the clamped values are never used there)
-  for (int e = tid; e < NP * TH * TW; e += BX * BY) {
-    const int p = e / (TH * TW), r = e - p * (TH * TW);
-    const int yy = r / TW, xx = r - yy * TW;
-    const int gx = min(max(bx0 + xx - 1, 0), Nx - 1), gy = min(max(by0 + yy - 1, 0), Ny - 1);
-    tile[e] = U[(size_t)p * plane + (size_t)gy * Nx + gx];
+  // (loads are issued in batches of 6 before their shared-memory stores: the kernel is bound by
+  //  global-load latency, so the number of independent loads in flight per thread is what matters)
+  {
+    constexpr int UB = 6;
+    const int total = NP * TH * TW;
+    for (int e0 = tid; e0 < total; e0 += UB * BX * BY) {
+      real v[UB];
+#pragma unroll
+      for (int q = 0; q < UB; q++) {
+        const int e = min(e0 + q * BX * BY, total - 1);
+        const int p = e / (TH * TW), r = e - p * (TH * TW);
+        const int yy = r / TW, xx = r - yy * TW;
+        const int gx = min(max(bx0 + xx - 1, 0), Nx - 1), gy = min(max(by0 + yy - 1, 0), Ny - 1);
+        v[q] = U[(size_t)p * plane + (size_t)gy * Nx + gx];
+      }
+#pragma unroll
+      for (int q = 0; q < UB; q++)
+        if (e0 + q * BX * BY < total) tile[e0 + q * BX * BY] = v[q];
+    }
   }
   __syncthreads();  // s_par visible
   {
@@ -296,6 +310,19 @@ __global__ void __launch_bounds__(BX* BY) pde_stage_kernel(StageArgs A) {
   real* acc = A.acc ? static_cast<real*>(A.acc) + (size_t)b * NP * plane : nullptr;
   const size_t o_c = (size_t)cy * Nx + cx;
   const real dtA = (real)A.A, dtB = (real)A.Bc, dtC = (real)(A.C * A.dt), dtw = (real)(A.bw * A.dt);
+  // step-start state and accumulator of this grid point for all planes, loaded up front (independent
+  // loads in flight together; inside the plane loop they would queue behind possibly-aliasing stores)
+  constexpr int NPT = LT ? 2 * LT : 1;
+  real unv[NPT], accv[NPT];
+  const bool need_un = dtA != (real)0 || A.acc_mode == ACC_INIT;
+  const bool need_acc = A.acc_mode == ACC_ADD || A.acc_mode == ACC_FINAL;
+  if (LT) {
+#pragma unroll
+    for (int p = 0; p < NPT; p++) {
+      unv[p] = need_un ? un[(size_t)p * plane + o_c] : (real)0;
+      accv[p] = need_acc ? acc[(size_t)p * plane + o_c] : (real)0;
+    }
+  }
   real rs_out = 0;
 #pragma unroll
   for (int j = 0; j < L; j++) {
@@ -320,12 +347,14 @@ __global__ void __launch_bounds__(BX* BY) pde_stage_kernel(StageArgs A) {
       const real reac = -c * (gsum[i] - G) + G * (rsum[i] - c);
       const real k = D * (lapx + lapy) + bnd - (ddx + ddy) + reac;  // pde.jl:236
       const size_t po = (size_t)p * plane + o_c;
+      const real unp = LT ? unv[LT ? p : 0] : (need_un ? un[po] : (real)0);
+      const real accp = LT ? accv[LT ? p : 0] : (need_acc ? acc[po] : (real)0);
       real out = dtC * k;
-      if (dtA != (real)0) out += dtA * un[po];
+      if (dtA != (real)0) out += dtA * unp;
       if (dtB != (real)0) out += dtB * c;
-      if (A.acc_mode == ACC_INIT) { if (in) acc[po] = un[po] + dtw * k; }
-      else if (A.acc_mode == ACC_ADD) { if (in) acc[po] += dtw * k; }
-      else if (A.acc_mode == ACC_FINAL) out = acc[po] + dtw * k;
+      if (A.acc_mode == ACC_INIT) { if (in) acc[po] = unp + dtw * k; }
+      else if (A.acc_mode == ACC_ADD) { if (in) acc[po] = accp + dtw * k; }
+      else if (A.acc_mode == ACC_FINAL) out = accp + dtw * k;
       if (in) Uout[po] = out;
       const real v = in ? out : (real)0;
       rs_out += v;
