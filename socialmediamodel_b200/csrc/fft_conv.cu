@@ -30,17 +30,34 @@ __device__ __forceinline__ int brev_p(int i, int logP) { return (int)(__brev((un
 template <typename real>
 __device__ void fft_dif_fwd(typename vec2<real>::type* sh, int ncol, int cs, int P, int logP,
                             const typename vec2<real>::type* tw) {
+  // radix-2^2: two butterfly stages per pass in registers (half the shared-memory traffic and barriers)
   using real2 = typename vec2<real>::type;
-  const int tid = threadIdx.x, nt = blockDim.x, hp = P >> 1;
-  for (int s = logP; s >= 1; s--) {
-    const int half = 1 << (s - 1);
-    for (int t = tid; t < ncol * hp; t += nt) {
-      const int c = t >> (logP - 1), bt = t & (hp - 1);
-      const int j = bt & (half - 1), i0 = ((bt >> (s - 1)) << s) + j;
-      real2* x = sh + c * cs;
-      const real2 a = x[i0], b = x[i0 + half];
-      x[i0] = cadd(a, b);
-      x[i0 + half] = cmul(csub(a, b), tw[half + j]);
+  const int tid = threadIdx.x, nt = blockDim.x, qp = P >> 2;
+  int s = logP;
+  for (; s >= 2; s -= 2) {
+    const int q = 1 << (s - 2);
+    for (int t = tid; t < ncol * qp; t += nt) {
+      const int c = t >> (logP - 2), bt = t & (qp - 1);
+      const int j = bt & (q - 1), i0 = ((bt >> (s - 2)) << s) + j;
+      real2* x = sh + c * cs + i0;
+      const real2 a0 = x[0], a1 = x[q], a2 = x[2 * q], a3 = x[3 * q];
+      const real2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), tw[2 * q + j]);
+      const real2 b1 = cadd(a1, a3), b3 = cmul(csub(a1, a3), tw[3 * q + j]);
+      const real2 w = tw[q + j];
+      x[0] = cadd(b0, b1);
+      x[q] = cmul(csub(b0, b1), w);
+      x[2 * q] = cadd(b2, b3);
+      x[3 * q] = cmul(csub(b2, b3), w);
+    }
+    __syncthreads();
+  }
+  if (s == 1) {  // odd log2 P: last radix-2 stage (twiddle 1)
+    for (int t = tid; t < ncol * (P >> 1); t += nt) {
+      const int c = t >> (logP - 1), bt = t & ((P >> 1) - 1);
+      real2* x = sh + c * cs + 2 * bt;
+      const real2 a = x[0], b = x[1];
+      x[0] = cadd(a, b);
+      x[1] = csub(a, b);
     }
     __syncthreads();
   }
@@ -51,16 +68,34 @@ template <typename real>
 __device__ void fft_dit_inv(typename vec2<real>::type* sh, int ncol, int cs, int P, int logP,
                             const typename vec2<real>::type* tw) {
   using real2 = typename vec2<real>::type;
-  const int tid = threadIdx.x, nt = blockDim.x, hp = P >> 1;
-  for (int s = 1; s <= logP; s++) {
-    const int half = 1 << (s - 1);
-    for (int t = tid; t < ncol * hp; t += nt) {
-      const int c = t >> (logP - 1), bt = t & (hp - 1);
-      const int j = bt & (half - 1), i0 = ((bt >> (s - 1)) << s) + j;
-      real2* x = sh + c * cs;
-      const real2 a = x[i0], b = cmulc(x[i0 + half], tw[half + j]);
-      x[i0] = cadd(a, b);
-      x[i0 + half] = csub(a, b);
+  const int tid = threadIdx.x, nt = blockDim.x, qp = P >> 2;
+  int s = 1;
+  if (logP & 1) {  // odd log2 P: first radix-2 stage (twiddle 1)
+    for (int t = tid; t < ncol * (P >> 1); t += nt) {
+      const int c = t >> (logP - 1), bt = t & ((P >> 1) - 1);
+      real2* x = sh + c * cs + 2 * bt;
+      const real2 a = x[0], b = x[1];
+      x[0] = cadd(a, b);
+      x[1] = csub(a, b);
+    }
+    __syncthreads();
+    s = 2;
+  }
+  for (; s + 1 <= logP; s += 2) {  // stages s and s+1
+    const int q = 1 << (s - 1);
+    for (int t = tid; t < ncol * qp; t += nt) {
+      const int c = t >> (logP - 2), bt = t & (qp - 1);
+      const int j = bt & (q - 1), i0 = ((bt >> (s - 1)) << (s + 1)) + j;
+      real2* x = sh + c * cs + i0;
+      const real2 a0 = x[0], a2 = x[2 * q];
+      const real2 w1 = tw[q + j];
+      const real2 t1 = cmulc(x[q], w1), t3 = cmulc(x[3 * q], w1);
+      const real2 b0 = cadd(a0, t1), b1 = csub(a0, t1), b2 = cadd(a2, t3), b3 = csub(a2, t3);
+      const real2 u2 = cmulc(b2, tw[2 * q + j]), u3 = cmulc(b3, tw[3 * q + j]);
+      x[0] = cadd(b0, u2);
+      x[2 * q] = csub(b0, u2);
+      x[q] = cadd(b1, u3);
+      x[3 * q] = csub(b1, u3);
     }
     __syncthreads();
   }
