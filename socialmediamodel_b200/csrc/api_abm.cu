@@ -75,6 +75,8 @@ extern "C" int smm_ctx_destroy(smm_ctx* ctx) {
     if (ctx->ev0[i]) cudaEventDestroy(ctx->ev0[i]);
     if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
   }
+  for (int i = 0; i < 2; i++) { if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]); if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return SMM_OK;
@@ -305,6 +307,9 @@ struct EnsembleRequest {
   void* d_xs; int32_t* d_follows; double* d_infs; double* d_meds; double* d_ys; double* d_zs; int64_t* d_numbers;
   signed char* d_state;
   void* d_us;  // caller-provided (dev API) or scratch
+  double* ys_ext; double* zs_ext;  // caller-provided device slices (chunked ensembles) or null = scratch
+  bool numbers_keep;               // accumulate into d_numbers instead of clearing it
+  bool no_reset;                   // keep the kernel timers of the previous chunk
 };
 
 int run_ensemble(smm_ctx* ctx, EnsembleRequest& E, const char* who) {
@@ -327,7 +332,7 @@ int run_ensemble(smm_ctx* ctx, EnsembleRequest& E, const char* who) {
     SMM_REQUIRE(ctx, E.noise.mode == SMM_NOISE_PHILOX, "%s: unknown noise mode %d", who, E.noise.mode);
   SMM_REQUIRE(ctx, E.first >= 0 && E.first + E.R <= 0xffffffffLL, "%s: realization index out of the 32-bit counter range", who);
   SMM_CUDA(ctx, cudaSetDevice(ctx->device));
-  reset_times(ctx);
+  if (!E.no_reset) reset_times(ctx);
 
   const int precision = E.precision;
   const size_t rs = precision == SMM_PREC_F64 ? 8 : 4;
@@ -395,12 +400,15 @@ int run_ensemble(smm_ctx* ctx, EnsembleRequest& E, const char* who) {
   if (E.want_infs) { SMM_TRY(smm_scratch(ctx, S_INFS, R * (NT + 1) * 2 * L * 8, &p)); A.infs = (double*)p; }
   if (E.want_meds) { SMM_TRY(smm_scratch(ctx, S_MEDS, R * (NT + 1) * 2 * M * 8, &p)); A.meds = (double*)p; }
   if (E.want_yz && nsave) {
-    SMM_TRY(smm_scratch(ctx, S_YS, R * nsave * L * 2 * 8, &p)); A.ys = (double*)p;
-    SMM_TRY(smm_scratch(ctx, S_ZS, R * nsave * M * 2 * 8, &p)); A.zs = (double*)p;
+    if (E.ys_ext) { A.ys = E.ys_ext; A.zs = E.zs_ext; }
+    else {
+      SMM_TRY(smm_scratch(ctx, S_YS, R * nsave * L * 2 * 8, &p)); A.ys = (double*)p;
+      SMM_TRY(smm_scratch(ctx, S_ZS, R * nsave * M * 2 * 8, &p)); A.zs = (double*)p;
+    }
   }
   if (E.want_numbers) {
     if (!E.d_numbers) { SMM_TRY(smm_scratch(ctx, S_NUMBERS, (NT + 1) * L * M * 8, &p)); E.d_numbers = (int64_t*)p; }
-    SMM_CUDA(ctx, cudaMemsetAsync(E.d_numbers, 0, (NT + 1) * L * M * 8, ctx->stream));
+    if (!E.numbers_keep) SMM_CUDA(ctx, cudaMemsetAsync(E.d_numbers, 0, (NT + 1) * L * M * 8, ctx->stream));
     A.numbers = E.d_numbers;
   }
 
@@ -468,39 +476,104 @@ extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t preci
   SMM_REQUIRE(ctx, noise != nullptr, "smm_abm_ensemble: noise is NULL");
   SMM_TRY(check_grid(ctx, grid, "smm_abm_ensemble"));
   SMM_REQUIRE(ctx, kde_sigma > 0, "smm_abm_ensemble: kde_sigma must be > 0");
-  EnsembleRequest E;
-  memset(&E, 0, sizeof E);
-  E.q = q; E.precision = precision; E.NT = NT; E.R = R; E.first = first_realization;
-  E.x0 = x0; E.state = state; E.follow0 = follow0; E.inf0 = inf0; E.media0 = media0;
-  E.rowptr = rowptr; E.colidx = colidx; E.noise = *noise; E.nsave = nsave; E.savesteps = savesteps;
-  E.want_kde = us || sum_us; E.kde_sigma = kde_sigma; E.grid = *grid;
-  E.want_yz = zs || ys || sum_zs || sum_ys; E.want_numbers = numbers != nullptr;
-  SMM_TRY(run_ensemble(ctx, E, "smm_abm_ensemble"));
-  const size_t L = q->L, M = q->M;
+  SMM_TRY(check_params(ctx, q, "smm_abm_ensemble"));
+  SMM_REQUIRE(ctx, R >= 1 && NT >= 0 && nsave >= 0, "smm_abm_ensemble: need R >= 1, NT >= 0, nsave >= 0");
+  SMM_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = q->n, L = q->L, M = q->M;
   const size_t per_real = (size_t)grid->Nx * grid->Ny * 2 * L * nsave;
-  void* p;
-  if (sum_us && nsave) {
-    SMM_TRY(smm_scratch(ctx, S_SUMUS, per_real * 8, &p));
-    smm_tic(ctx, SMM_K_REDUCE);
-    SMM_TRY(smm_launch_ensemble_sum(ctx, E.d_us, precision, R, per_real, (double*)p));
-    smm_toc(ctx, SMM_K_REDUCE);
-    SMM_TRY(download(ctx, p, per_real * 8, sum_us));
+  // The per-realization densities are by far the largest output (2 GB for 1 024 realizations at 89x89):
+  // realizations are processed in chunks and the device->host copy of chunk c overlaps the
+  // simulation of chunk c+1 (copy stream, double-buffered Float64 staging).
+  int nchunks = 1;
+  if (us && nsave && R >= 512) nchunks = std::min(4, R / 256);
+  const int Rc0 = (R + nchunks - 1) / nchunks;
+  if (nchunks > 1 && !ctx->copy_stream) {
+    SMM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      SMM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming));
+      SMM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copied[i], cudaEventDisableTiming));
+    }
   }
+  void *d_ys_all = nullptr, *d_zs_all = nullptr, *d_numbers = nullptr, *d_sum_us = nullptr;
+  const bool want_yz = zs || ys || sum_zs || sum_ys;
+  if (want_yz && nsave) {
+    SMM_TRY(smm_scratch(ctx, S_YS_ALL, (size_t)R * nsave * L * 2 * 8, &d_ys_all));
+    SMM_TRY(smm_scratch(ctx, S_ZS_ALL, (size_t)R * nsave * M * 2 * 8, &d_zs_all));
+  }
+  if (numbers) SMM_TRY(smm_scratch(ctx, S_NUMBERS, (size_t)(NT + 1) * L * M * 8, &d_numbers));
+  if (sum_us && nsave) SMM_TRY(smm_scratch(ctx, S_SUMUS, per_real * 8, &d_sum_us));
+  struct Pending { int chunk; size_t r0, rc; };
+  Pending pending = {-1, 0, 0};
+  void* stage[2] = {nullptr, nullptr};
+  auto issue_copy = [&](const Pending& pc) -> int {  // D2H of a converted chunk on the copy stream
+    const int sl = pc.chunk & 1;
+    SMM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[sl], 0));
+    SMM_CUDA(ctx, cudaMemcpyAsync(us + pc.r0 * per_real, stage[sl], pc.rc * per_real * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    SMM_CUDA(ctx, cudaEventRecord(ctx->ev_copied[sl], ctx->copy_stream));
+    return SMM_OK;
+  };
+  for (int c = 0; c < nchunks; c++) {
+    const size_t r0 = (size_t)c * Rc0, rc = std::min((size_t)Rc0, (size_t)R - r0);
+    if (rc == 0) break;
+    EnsembleRequest E;
+    memset(&E, 0, sizeof E);
+    E.q = q; E.precision = precision; E.NT = NT; E.R = (int)rc; E.first = first_realization + (int64_t)r0;
+    if (x0) { E.x0 = x0 + r0 * 2 * n; E.state = state ? state + r0 * n : nullptr; E.follow0 = follow0 ? follow0 + r0 * n : nullptr;
+              E.inf0 = inf0 ? inf0 + r0 * 2 * L : nullptr; E.media0 = media0 ? media0 + r0 * 2 * M : nullptr; }
+    else { E.x0 = nullptr; E.state = state; E.follow0 = follow0; E.inf0 = inf0; E.media0 = media0; }
+    E.rowptr = rowptr; E.colidx = colidx; E.noise = *noise;
+    if (noise->mode == SMM_NOISE_INJECTED) {
+      if (noise->xi) E.noise.xi = noise->xi + r0 * NT * 2 * n;
+      if (noise->u1) E.noise.u1 = noise->u1 + r0 * NT * n;
+      if (noise->u2) E.noise.u2 = noise->u2 + r0 * NT * n;
+      if (noise->xi_inf) E.noise.xi_inf = noise->xi_inf + r0 * NT * L * 2;
+      if (noise->xi_med) E.noise.xi_med = noise->xi_med + r0 * NT * M * 2;
+    }
+    E.nsave = nsave; E.savesteps = savesteps;
+    E.want_kde = us || sum_us; E.kde_sigma = kde_sigma; E.grid = *grid;
+    E.want_yz = want_yz; E.want_numbers = numbers != nullptr;
+    if (want_yz && nsave) { E.ys_ext = (double*)d_ys_all + r0 * nsave * L * 2; E.zs_ext = (double*)d_zs_all + r0 * nsave * M * 2; }
+    E.d_numbers = (int64_t*)d_numbers; E.numbers_keep = c > 0; E.no_reset = c > 0;
+    SMM_TRY(run_ensemble(ctx, E, "smm_abm_ensemble"));
+    if (sum_us && nsave) {
+      smm_tic(ctx, SMM_K_REDUCE);
+      SMM_TRY(smm_launch_ensemble_sum(ctx, E.d_us, precision, (int)rc, per_real, (double*)d_sum_us, c > 0));
+      smm_toc(ctx, SMM_K_REDUCE);
+    }
+    if (us && nsave) {
+      if (nchunks == 1) {
+        SMM_TRY(download_real(ctx, E.d_us, rc * per_real, precision, us));
+      } else {
+        const int sl = c & 1;
+        SMM_TRY(smm_scratch(ctx, sl ? S_STAGE_B : S_STAGE_A, (size_t)Rc0 * per_real * 8, &stage[sl]));
+        if (c >= 2) SMM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[sl], 0));  // staging slot free again
+        SMM_TRY(smm_launch_convert_real_to_f64(ctx, E.d_us, (double*)stage[sl], rc * per_real, precision));
+        SMM_CUDA(ctx, cudaEventRecord(ctx->ev_ready[sl], ctx->stream));
+        // the previous chunk's copy is issued only now, after this chunk's kernels are queued, so that a
+        // host-blocking copy into pageable memory still overlaps them
+        if (pending.chunk >= 0) SMM_TRY(issue_copy(pending));
+        pending = {c, r0, rc};
+      }
+    }
+  }
+  if (pending.chunk >= 0) SMM_TRY(issue_copy(pending));
+  void* p;
+  if (sum_us && nsave) SMM_TRY(download(ctx, d_sum_us, per_real * 8, sum_us));
   if (sum_zs && nsave) {
     SMM_TRY(smm_scratch(ctx, S_SUMZS, nsave * M * 2 * 8, &p));
-    SMM_TRY(smm_launch_small_sum(ctx, E.d_zs, R, (int)(nsave * M * 2), (double*)p));
+    SMM_TRY(smm_launch_small_sum(ctx, (const double*)d_zs_all, R, (int)(nsave * M * 2), (double*)p));
     SMM_TRY(download(ctx, p, nsave * M * 2 * 8, sum_zs));
   }
   if (sum_ys && nsave) {
     SMM_TRY(smm_scratch(ctx, S_SUMYS, nsave * L * 2 * 8, &p));
-    SMM_TRY(smm_launch_small_sum(ctx, E.d_ys, R, (int)(nsave * L * 2), (double*)p));
+    SMM_TRY(smm_launch_small_sum(ctx, (const double*)d_ys_all, R, (int)(nsave * L * 2), (double*)p));
     SMM_TRY(download(ctx, p, nsave * L * 2 * 8, sum_ys));
   }
-  if (zs) SMM_TRY(download(ctx, E.d_zs, (size_t)R * nsave * M * 2 * 8, zs));
-  if (ys) SMM_TRY(download(ctx, E.d_ys, (size_t)R * nsave * L * 2 * 8, ys));
-  if (numbers) SMM_TRY(download(ctx, E.d_numbers, (size_t)(NT + 1) * L * M * 8, numbers));
-  if (us) SMM_TRY(download_real(ctx, E.d_us, (size_t)R * per_real, precision, us));
+  if (zs && nsave) SMM_TRY(download(ctx, d_zs_all, (size_t)R * nsave * M * 2 * 8, zs));
+  if (ys && nsave) SMM_TRY(download(ctx, d_ys_all, (size_t)R * nsave * L * 2 * 8, ys));
+  if (numbers) SMM_TRY(download(ctx, d_numbers, (size_t)(NT + 1) * L * M * 8, numbers));
   SMM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->copy_stream) SMM_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   return smm_collect_times(ctx);
 }
 

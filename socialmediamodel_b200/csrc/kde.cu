@@ -121,10 +121,10 @@ __global__ void __launch_bounds__(KW * 32) kde_kernel(KdeArgs A) {
 
 // sum over realizations of per-realization blocks (deterministic: fixed order, f64 accumulate)
 template <typename real>
-__global__ void ensemble_sum_kernel(const real* __restrict__ us, int R, size_t per_real, double* __restrict__ out) {
+__global__ void ensemble_sum_kernel(const real* __restrict__ us, int R, size_t per_real, double* __restrict__ out, int accumulate) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= per_real) return;
-  double acc = 0.0;
+  double acc = accumulate ? out[e] : 0.0;  // chunked ensembles add their chunk to the running sum
   for (int r = 0; r < R; r++) acc += (double)us[(size_t)r * per_real + e];
   out[e] = acc;
 }
@@ -154,17 +154,17 @@ int smm_launch_kde(smm_ctx* ctx, const KdeArgs& A, int precision) {
   return SMM_OK;
 }
 
-int smm_launch_ensemble_sum(smm_ctx* ctx, const void* us, int precision, int R, size_t per_real, double* sum_us) {
+int smm_launch_ensemble_sum(smm_ctx* ctx, const void* us, int precision, int R, size_t per_real, double* sum_us, int accumulate) {
   unsigned grid = (unsigned)((per_real + 255) / 256);
-  if (precision == SMM_PREC_F64) ensemble_sum_kernel<double><<<grid, 256, 0, ctx->stream>>>((const double*)us, R, per_real, sum_us);
-  else ensemble_sum_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)us, R, per_real, sum_us);
+  if (precision == SMM_PREC_F64) ensemble_sum_kernel<double><<<grid, 256, 0, ctx->stream>>>((const double*)us, R, per_real, sum_us, accumulate);
+  else ensemble_sum_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)us, R, per_real, sum_us, accumulate);
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;
 }
 
 int smm_launch_small_sum(smm_ctx* ctx, const double* v, int R, int per_real, double* out) {
-  ensemble_sum_kernel<double><<<(per_real + 255) / 256, 256, 0, ctx->stream>>>(v, R, (size_t)per_real, out);
+  ensemble_sum_kernel<double><<<(per_real + 255) / 256, 256, 0, ctx->stream>>>(v, R, (size_t)per_real, out, 0);
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;

@@ -62,7 +62,7 @@ struct KdeArgs {
 };
 int smm_launch_kde(smm_ctx* ctx, const KdeArgs& A, int precision);
 // K4b ensemble reduction: sum over realizations (plotting.jl:361-363 numerator), f64 output
-int smm_launch_ensemble_sum(smm_ctx* ctx, const void* us, int precision, int R, size_t per_real, double* sum_us);
+int smm_launch_ensemble_sum(smm_ctx* ctx, const void* us, int precision, int R, size_t per_real, double* sum_us, int accumulate = 0);
 int smm_launch_small_sum(smm_ctx* ctx, const double* v, int R, int per_real, double* out);
 // element conversions
 int smm_launch_convert_f64_to_real(smm_ctx* ctx, const double* in, void* out, size_t count, int precision);

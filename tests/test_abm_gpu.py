@@ -287,3 +287,24 @@ def test_abm_ensemble_reference_api_and_monte_carlo():
     mean_gpu, mean_o = ys[:, :, -1, :].mean(axis=-1), ys_o.mean(axis=0)
     se = np.sqrt(ys[:, :, -1, :].var(axis=-1) / N + ys_o.var(axis=0) / N)
     assert np.all(np.abs(mean_gpu - mean_o) < 5 * se + 1e-3), (mean_gpu, mean_o, se)
+
+
+def test_abm_ensemble_chunked_copy_pipeline():
+    """R >= 512 takes the chunked path of smm_abm_ensemble (device->host copy of chunk c overlapped
+    with the simulation of chunk c+1): every realization must equal the same realization run alone,
+    and the sums must be the sums over all chunks."""
+    NT, R, sp = 6, 600, 2
+    p = smm.ABMconstruct(dx=0.55)
+    q = smm.parameters(n=24)
+    st = smm.savetimes_abm(NT, sp)
+    out = smm.abm_ensemble_raw(NT, R, p=p, q=q, savesteps=st, first_realization=1, seed=3, precision="f32")
+    for k in (0, 149, 150, 299, 300, 449, 450, 599):
+        one = smm.abm_ensemble_raw(NT, 1, p=p, q=q, savesteps=st, first_realization=1 + k, seed=3, precision="f32")
+        np.testing.assert_array_equal(out["us"][..., k], one["us"][..., 0])
+        np.testing.assert_array_equal(out["ys"][..., k], one["ys"][..., 0])
+        np.testing.assert_array_equal(out["zs"][..., k], one["zs"][..., 0])
+    np.testing.assert_allclose(out["sum_us"], out["us"].sum(axis=-1), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(out["sum_ys"], out["ys"].sum(axis=-1), rtol=1e-12)
+    assert out["numbers"].sum(axis=(0, 1)).tolist() == [R * 24] * (NT + 1)
+    pinned = smm.abm_ensemble_raw(NT, R, p=p, q=q, savesteps=st, first_realization=1, seed=3, precision="f32", pinned=True)
+    np.testing.assert_array_equal(pinned["us"], out["us"])
