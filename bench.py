@@ -131,7 +131,8 @@ def run_abm_ensemble(args, rank, world, local):
     R, NT, n, L, M, sp = cfg["R"], cfg["NT"], cfg["n"], cfg["L"], cfg["M"], cfg["savepoints"]
     p, q = smm.ABMconstruct(), smm.parameters(n=n, L=L)
     ctx = smm.Context(local)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()             # a real stream (the legacy default stream cannot be graph-captured)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     Nx, Ny = p.X.shape
     savesteps = smm.savetimes_abm(NT, sp)
@@ -308,7 +309,7 @@ def _cpu_realization(k):
 def cpu_baseline_abm(realizations=None):
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    realizations = realizations or max(cores, 8)
+    realizations = realizations or 12 * max(cores, 8)      # ~10-20 s of CPU work
     with mp.get_context("fork").Pool(cores) as pool:
         pool.map(_cpu_realization, range(cores))          # warm-up (imports)
         t0 = time.perf_counter()

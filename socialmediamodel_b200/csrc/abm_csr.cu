@@ -43,6 +43,7 @@ struct PopArgs {
   const double* u1;  // injected f64 [n]
   const double* u2;
   unsigned long long* fallback_count;  // diagnostics: agents that took the FP64 re-evaluation
+  int prefix_decision;                 // 1: prefix-sum/binary-search decision, 0: cooperative CDF walk
 };
 
 // class index c = follow*2 + (state==+1)
@@ -98,6 +99,9 @@ __global__ void __launch_bounds__(kPopThreads) pop_step_kernel(PopArgs A) {
   float* fny = fnx + L;
   float* ffrac = fny + L;
   double* att_scr = reinterpret_cast<double*>(ffrac + L + (L & 1)) + (tid >> 5) * L;  // [nwarps][L]
+  // (prefix variant) 16-byte aligned by construction: one pad word when the count of preceding 4-byte words is odd/8-byte misaligned
+  float4* tab = reinterpret_cast<float4*>(reinterpret_cast<double*>(ffrac + L + (L & 1)) + (kPopThreads / 32) * L + ((19 * L + 4 * M + (3 * L + (L & 1)) / 2) & 1));
+  float* pref = reinterpret_cast<float*>(tab + L);  // [(L+1)/2][kPopThreads]
 
   // ---- prologue -------------------------------------------------------------------------
   for (int t = tid; t < 2 * L * 3; t += kPopThreads) bins[t] = 0;
@@ -148,6 +152,10 @@ __global__ void __launch_bounds__(kPopThreads) pop_step_kernel(PopArgs A) {
       double f = ss / cnt;  // 0/0 = NaN (Q5)
       frac[t] = f;
       fnx[t] = (float)px; fny[t] = (float)py; ffrac[t] = (float)f;
+      if (A.prefix_decision) {  // eta * max(+-frac, 0.1) per state (abm.jl:115-119); NaN stays NaN (Q5)
+        const float ff = (float)f, et = (float)K.eta;
+        tab[t] = make_float4((float)px, (float)py, ff != ff ? ff : et * fmaxf(ff, 0.1f), ff != ff ? ff : et * fmaxf(-ff, 0.1f));
+      }
     }
     if (blockIdx.x == 0) { A.ent_new[t] = px; A.ent_new[(L + M) + t] = py; }
   }
@@ -205,7 +213,11 @@ __global__ void __launch_bounds__(kPopThreads) pop_step_kernel(PopArgs A) {
     int fnew;
     if (sizeof(real) == 4 && A.xi == nullptr) {
       // Philox uniforms are 24-bit, exactly representable in FP32
-      fnew = warp_switch_decision(valid, (float)xj.x, (float)xj.y, sj, fj, (float)u1, (float)u2, fnx, fny, ffrac, enx, eny,
+      if (A.prefix_decision)
+        fnew = warp_switch_decision_prefix(valid, (float)xj.x, (float)xj.y, sj, fj, (float)u1, (float)u2, tab, enx, eny, frac, L,
+                                           (float)K.dt, K.eta, K.dt, 2e-5f, pref, att_scr, &nfallback);
+      else
+        fnew = warp_switch_decision(valid, (float)xj.x, (float)xj.y, sj, fj, (float)u1, (float)u2, fnx, fny, ffrac, enx, eny,
                                   frac, L, (float)K.eta, (float)K.dt, K.eta, K.dt, 2e-5f, att_scr, &nfallback);
     } else {
       fnew = switch_decision_f64(x, y, sj, fj, enx, eny, frac, L, K.eta, K.dt, u1, u2);
@@ -261,8 +273,10 @@ __global__ void csr_to_sell_kernel(int n, const int32_t* __restrict__ rowptr, co
   for (int t = 0; t < width; t++) sell[sp + (int64_t)t * 32 + lane] = t < deg ? csr[e0 + t] : (int32_t)(j < (size_t)n ? j : 0);
 }
 
-size_t pop_smem_bytes(int L, int M) {
-  return (size_t)2 * L * 3 * 8 + sizeof(double) * (4 * (L + M) + L) + sizeof(float) * (3 * L + 2) + sizeof(double) * (kPopThreads / 32) * L + 16;
+size_t pop_smem_bytes(int L, int M, bool prefix) {
+  size_t b = (size_t)2 * L * 3 * 8 + sizeof(double) * (4 * (L + M) + L) + sizeof(float) * (3 * L + 2) + sizeof(double) * (kPopThreads / 32) * L + 16;
+  if (prefix) b += 16 + sizeof(float4) * L + sizeof(float) * (size_t)((L + 1) / 2) * kPopThreads;
+  return b;
 }
 
 }  // namespace
@@ -302,7 +316,12 @@ int smm_launch_pop_step(smm_ctx* ctx, smm_abm_pop* p, const void* xi, const doub
   A.acc_read = p->acc[p->step % 3]; A.acc_write = p->acc[(p->step + 1) % 3]; A.acc_clear = p->acc[(p->step + 2) % 3];
   A.xi = xi; A.u1 = u1; A.u2 = u2;
   A.fallback_count = p->fallback_count;
-  size_t sm = pop_smem_bytes(p->k.L, p->k.M);
+  A.prefix_decision = p->prefix_decision && p->precision != SMM_PREC_F64;
+  size_t sm = pop_smem_bytes(p->k.L, p->k.M, A.prefix_decision != 0);
+  if (sm > 48 * 1024) {
+    if (p->precision == SMM_PREC_F64) SMM_CUDA(ctx, cudaFuncSetAttribute(pop_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    else SMM_CUDA(ctx, cudaFuncSetAttribute(pop_step_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  }
   int grid = pop_grid(ctx, p->k.n);
   if (p->l2_persist_bytes > 0) {
     // keep the gathered (old) position array resident in L2; the colidx stream and the new

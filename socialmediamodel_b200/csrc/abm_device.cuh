@@ -188,3 +188,87 @@ __device__ __forceinline__ int warp_switch_decision(bool valid, float x, float y
   }
   return result;
 }
+
+// Variant of the warp decision whose cost does not depend on how many agents switch: phase 1 keeps
+// every second running sum lam_i in shared memory (pref[(L+1)/2][blockDim.x], conflict-free), phase 2
+// is a binary search over them plus one re-evaluated weight.  tab: float4 per influencer
+// {x, y, eta*max(frac,0.1), eta*max(-frac,0.1)} (a NaN fraction stays NaN: Q5).
+__device__ __forceinline__ int warp_switch_decision_prefix(bool valid, float x, float y, int st, int follow, float u1,
+                                                           float u2, const float4* tab, const double* dinfx,
+                                                           const double* dinfy, const double* dfrac, int L, float dt,
+                                                           double deta, double ddt, float band, float* pref,
+                                                           double* att_scratch, unsigned int* nfallback) {
+  const int lane = threadIdx.x & 31, nt = blockDim.x;
+  float* mypref = pref + threadIdx.x;
+  const int M2 = (L + 1) >> 1;
+  float lam = 0.f;
+#pragma unroll 4
+  for (int i = 0; i < L; i++) {  // abm.jl:103-123
+    const float4 t = tab[i];
+    const float d0 = x - t.x, d1 = y - t.y;
+    lam = fmaf(w_of_r2(fmaf(d0, d0, d1 * d1)), st == 1 ? t.z : t.w, lam);
+    if ((i & 1) || i == L - 1) mypref[(i >> 1) * nt] = lam;
+  }
+  int status = 0;  // 0 stay, 1 switch (FP32-decided), 2 needs FP64
+  if (valid && lam == lam) {  // NaN lock (Q5): stay
+    const float thr = -expm1f(-lam * dt);
+    const float gap = u1 - thr;
+    if (fabsf(gap) <= band * fmaxf(thr, 1e-3f)) status = 2;
+    else if (gap < 0.f) status = 1;
+  }
+  int result = follow;
+  {  // smallest k with lam_k / lam >= u2 (abm.jl:125-130)
+    const float target = u2 * lam;
+    int lo = 0, hi = M2 - 1;  // the last entry is the clamp (Q7)
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (mypref[mid * nt] >= target) hi = mid; else lo = mid + 1;
+    }
+    const int i0 = 2 * lo;
+    const float base = lo ? mypref[(lo - 1) * nt] : 0.f, top = mypref[lo * nt];
+    const float4 t = tab[i0];
+    const float d0 = x - t.x, d1 = y - t.y;
+    const float cs0 = fmaf(w_of_r2(fmaf(d0, d0, d1 * d1)), st == 1 ? t.z : t.w, base);  // == phase-1 value
+    const int k = (i0 + 1 < L && !(cs0 >= target)) ? i0 + 1 : i0;
+    if (status == 1) {
+      const float tol = band * lam;  // borderline comparisons at the decision boundary -> FP64
+      const float pk = k == i0 ? cs0 : top, pkm1 = k == i0 ? base : cs0;
+      const bool fz = (k < L - 1 && fabsf(pk - target) <= tol) || (k > 0 && fabsf(pkm1 - target) <= tol);
+      if (fz) status = 2; else result = k;
+    }
+  }
+  unsigned fb = __ballot_sync(0xffffffffu, status == 2);
+  while (fb) {  // FP64 re-evaluation (guard band), cooperative
+    const int src = __ffs(fb) - 1;
+    fb &= fb - 1;
+    const double sx = (double)__shfl_sync(0xffffffffu, x, src), sy = (double)__shfl_sync(0xffffffffu, y, src);
+    const double sst = (double)__shfl_sync(0xffffffffu, st, src);
+    for (int i = lane; i < L; i += 32) {
+      double d0 = sx - dinfx[i], d1 = sy - dinfy[i];
+      double dist = exp(-sqrt(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1))));
+      double g2 = __dmul_rn(sst, dfrac[i]);
+      if (g2 < SMM_THETA) g2 = SMM_THETA;
+      att_scratch[i] = __dmul_rn(__dmul_rn(deta, dist), g2);
+    }
+    __syncwarp();
+    if (lane == src) {
+      double lamd = 0.0;
+      for (int i = 0; i < L; i++) lamd = __dadd_rn(lamd, att_scratch[i]);
+      double thr = 1.0 - exp(-__dmul_rn(lamd, ddt));
+      if ((double)u1 < thr) {
+        double cs = 0.0;
+        int k = L - 1;
+        for (int i = 0; i < L; i++) {
+          cs = __dadd_rn(cs, att_scratch[i] / lamd);
+          if (!(cs < (double)u2)) { k = i; break; }
+        }
+        result = k;
+      } else {
+        result = follow;
+      }
+      (*nfallback)++;
+    }
+    __syncwarp();
+  }
+  return result;
+}

@@ -669,6 +669,7 @@ extern "C" int smm_abm_pop_create(smm_ctx* ctx, const smm_params* q, int32_t pre
   int shift = 61 - (int)ceil(log2((double)n * std::max(maxabs, 1.0)));
   if (shift > 50) shift = 50;
   p->fx_scale = ldexp(1.0, shift);
+  { const char* ev = getenv("SMM_POP_DECISION"); p->prefix_decision = (ev && strcmp(ev, "coop") == 0) ? 0 : 1; }
   {
     // L2 persistence window for the position gathers (SMM_POP_L2_PERSIST=0 disables)
     const char* ev = getenv("SMM_POP_L2_PERSIST");

@@ -487,6 +487,7 @@ struct smm_pde_batch {
   std::map<std::pair<int, double>, cudaGraphExec_t> graphs;
   int64_t steps_taken;
   smm_fft_plan* fft;  // null = direct Toeplitz kernel
+  bool no_graph;      // stream capture unavailable on the caller's stream: launch kernels directly
 };
 
 static void pde_free(smm_pde_batch* pb) {
@@ -649,6 +650,7 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
   pb->partials = nullptr; pb->counters = nullptr; pb->coef = nullptr; pb->ode = nullptr; pb->inst = nullptr;
   pb->steps_taken = 0;
   pb->fft = nullptr;
+  pb->no_graph = false;
   pb->rs = precision == SMM_PREC_F64 ? 8 : 4;
   pb->plane = (size_t)grid->Nx * grid->Ny;
   pb->per_inst = pb->plane * 2 * L;
@@ -729,19 +731,34 @@ extern "C" int smm_pde_batch_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, in
   // the kernel chain of one step is captured once per (scheme, dt) and replayed
   auto key = std::make_pair((int)scheme, dt);
   auto it = pb->graphs.find(key);
-  if (it == pb->graphs.end()) {
+  bool use_graph = !pb->no_graph;
+  if (use_graph && it == pb->graphs.end()) {
     cudaGraph_t graph;
-    SMM_CUDA(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    int64_t l0 = ctx->launches;
-    int rc = enqueue_step(ctx, pb, dt, scheme);
-    ctx->launches = l0;
-    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
-    if (rc != SMM_OK) { if (e == cudaSuccess) cudaGraphDestroy(graph); return rc; }
-    SMM_CUDA(ctx, e);
-    cudaGraphExec_t exec;
-    SMM_CUDA(ctx, cudaGraphInstantiate(&exec, graph, 0));
-    cudaGraphDestroy(graph);
-    it = pb->graphs.emplace(key, exec).first;
+    cudaError_t e0 = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+    if (e0 != cudaSuccess) {
+      // e.g. the caller lent us the legacy default stream, which cannot be captured: plain launches
+      cudaGetLastError();
+      pb->no_graph = true;
+      use_graph = false;
+    } else {
+      int64_t l0 = ctx->launches;
+      int rc = enqueue_step(ctx, pb, dt, scheme);
+      ctx->launches = l0;
+      cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+      if (rc != SMM_OK) { if (e == cudaSuccess) cudaGraphDestroy(graph); return rc; }
+      SMM_CUDA(ctx, e);
+      cudaGraphExec_t exec;
+      SMM_CUDA(ctx, cudaGraphInstantiate(&exec, graph, 0));
+      cudaGraphDestroy(graph);
+      it = pb->graphs.emplace(key, exec).first;
+    }
+  }
+  if (!use_graph) {
+    smm_tic(ctx, SMM_K_STENCIL);
+    for (int s = 0; s < nsteps; s++) SMM_TRY(enqueue_step(ctx, pb, dt, scheme));
+    smm_toc(ctx, SMM_K_STENCIL);
+    pb->steps_taken += nsteps;
+    return SMM_OK;
   }
   const int per_step = (scheme == SMM_RK_EULER ? 1 : scheme == SMM_RK_HEUN ? 2 : scheme == SMM_RK_SSPRK3 ? 3 : 4) * 2;
   smm_tic(ctx, SMM_K_STENCIL);

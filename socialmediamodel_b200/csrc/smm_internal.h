@@ -87,6 +87,7 @@ struct smm_abm_pop {
   double* ent[2];    // [2][L+M] influencer then media positions (x block, y block), double-buffered
   long long* acc[3]; // fixed-point class sums [2L][3] = (sum x, sum y, count), 3-way rotation
   unsigned long long* fallback_count;  // FP64 re-evaluations of the switch decision so far
+  int prefix_decision;  // switch-decision variant (SMM_POP_DECISION=prefix|coop)
   size_t l2_persist_bytes, l2_window_max;  // L2 persistence for the gathered position array (0 = off)
 };
 int smm_launch_pop_accumulate(smm_ctx* ctx, smm_abm_pop* p, int buf, int accslot);
