@@ -1,8 +1,8 @@
 // fft_conv.cu -- K6 (scalable form): the interaction force F = (w*(x'-x)rho)/(w*rho) of
 // pde.jl:49-59 as a zero-padded FFT correlation.  The reference multiplies by the dense
 // K_matrix/W_matrix (O(N^2) per right-hand side, 248 GB at 353x353); the operator is block
-// Toeplitz, so three P x P circular convolutions (P = pow2 >= 2N-1) give the same sums in
-// O(N log N).  Hand-written radix-2 shared-memory FFTs (no cuFFT):
+// Toeplitz, so three P x P circular convolutions (P = 2^a or 3*2^a >= 2N-1) give the same sums in
+// O(N log N).  Hand-written mixed-radix (3, 2^2, 2) shared-memory FFTs (no cuFFT):
 //
 //   fft_rows_fwd   two real rows per complex FFT (DIF, natural -> bit-reversed), split into the two
 //                  half spectra                                       rho[b][iy][ix] -> A[b][iy][kx]
@@ -12,6 +12,8 @@
 //   fft_rows_inv   Hermitian-extend, two real rows per complex DIT inverse, keep ix < Nx, divide
 //                                                                        G -> Fx, Fy [b][iy][ix]
 // The kernel spectra are computed once per grid with the same kernels instantiated in Float64.
+#include <stdlib.h>
+
 #include "smm_internal.h"
 
 namespace {
@@ -21,25 +23,76 @@ template <typename real2> __device__ __forceinline__ real2 csub(real2 a, real2 b
 template <typename real2> __device__ __forceinline__ real2 cmul(real2 a, real2 b) { return mk2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 template <typename real2> __device__ __forceinline__ real2 cmulc(real2 a, real2 b) { return mk2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a * conj(b)
 
-__device__ __forceinline__ int brev_p(int i, int logP) { return (int)(__brev((unsigned)i) >> (32 - logP)); }
+// FFT length P = r3 * m with m = 2^a and r3 in {1, 3}: P = 3*2^a avoids padding 2N-1 up to the next
+// power of two (705 -> 768 instead of 1024).  A radix-3 pass is the first pass of the forward
+// (decimation-in-frequency) transform and the last of the inverse; between them each third is an
+// independent power-of-two FFT.  Spectrum order after the forward transform ("permuted order"):
+//   position(k) = (k mod r3) * m + bitrev_a(k div r3)
+struct FftDims { int P, m, a, r3; };
+
+__device__ __forceinline__ int brev_a(int i, int a) { return a ? (int)(__brev((unsigned)i) >> (32 - a)) : 0; }
+__device__ __forceinline__ int pos_of_freq(int k, FftDims d) {
+  return d.r3 == 3 ? (k % 3) * d.m + brev_a(k / 3, d.a) : brev_a(k, d.a);
+}
+__device__ __forceinline__ int freq_of_pos(int p, FftDims d) {
+  if (d.r3 == 3) { const int r = p / d.m; return 3 * brev_a(p - r * d.m, d.a) + r; }
+  return brev_a(p, d.a);
+}
+
+// Twiddle table (P entries): [0, m) stage-major power-of-two twiddles tw[half + j] = exp(-2 pi i j/(2 half))
+// (consecutive lanes read consecutive words; the strided form tw[j * m/2^s] was up to 32-way
+// bank-conflicted), and for r3 = 3 the radix-3 twiddles tw[m + j] = exp(-2 pi i j / P), j < 2m.
+template <typename real>
+__global__ void twiddle_kernel(FftDims d, typename vec2<real>::type* tw) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.P) return;
+  double s, c;
+  if (e < d.m) {
+    if (e == 0) { tw[0] = mk2((real)1, (real)0); return; }
+    int half = 1 << (31 - __clz(e));
+    sincospi(-(double)(e - half) / (double)half, &s, &c);  // exp(-2 pi i j / (2 half))
+  } else {
+    sincospi(-2.0 * (double)(e - d.m) / (double)d.P, &s, &c);
+  }
+  tw[e] = mk2((real)c, (real)s);
+}
+
+#define SMM_W3_RE (-0.5)
+#define SMM_W3_IM (-0.86602540378443864676)  // w3 = exp(-2 pi i / 3)
 
 // ncol independent length-P FFTs in shared memory (column stride cs), decimation in frequency:
-// natural-order input, bit-reversed output.  Twiddles are stored stage-major, tw[half + j] =
-// exp(-2 pi i j / (2 half)) for j < half (half = 1, 2, .., P/2): consecutive lanes read consecutive
-// words (the strided form tw[j * P/2^s] was up to 32-way bank-conflicted in the middle stages).
+// natural-order input, permuted-order output.  Power-of-two part in radix-2^2 passes (two butterfly
+// stages per pass in registers: half the shared-memory traffic and barriers of radix 2).
 template <typename real>
-__device__ void fft_dif_fwd(typename vec2<real>::type* sh, int ncol, int cs, int P, int logP,
+__device__ void fft_dif_fwd(typename vec2<real>::type* sh, int ncol, int cs, FftDims d,
                             const typename vec2<real>::type* tw) {
-  // radix-2^2: two butterfly stages per pass in registers (half the shared-memory traffic and barriers)
   using real2 = typename vec2<real>::type;
-  const int tid = threadIdx.x, nt = blockDim.x, qp = P >> 2;
-  int s = logP;
+  const int tid = threadIdx.x, nt = blockDim.x, m = d.m, a = d.a, r3 = d.r3;
+  if (r3 == 3) {
+    const real2* t3 = tw + m;
+    for (int t = tid; t < ncol * m; t += nt) {
+      const int c = t >> a, j = t & (m - 1);
+      real2* x = sh + c * cs + j;
+      const real2 a0 = x[0], a1 = x[m], a2 = x[2 * m];
+      // y1 = a0 + w3 a1 + w3^2 a2, y2 = a0 + w3^2 a1 + w3 a2  (w3^2 = conj(w3), w3^4 = w3)
+      const real sr = a1.x + a2.x, si = a1.y + a2.y, dr = a1.x - a2.x, di = a1.y - a2.y;
+      const real tr = a0.x + (real)SMM_W3_RE * sr, ti = a0.y + (real)SMM_W3_RE * si;
+      const real ur = -(real)SMM_W3_IM * di, ui = (real)SMM_W3_IM * dr;  // i*Im(w3)*(a1-a2) = (-Im*di, Im*dr)
+      x[0] = mk2(a0.x + sr, a0.y + si);
+      x[m] = cmul(mk2(tr + ur, ti + ui), t3[j]);
+      x[2 * m] = cmul(mk2(tr - ur, ti - ui), t3[2 * j]);
+    }
+    __syncthreads();
+  }
+  const int nsub = ncol * r3, qp = m >> 2;
+  int s = a;
   for (; s >= 2; s -= 2) {
     const int q = 1 << (s - 2);
-    for (int t = tid; t < ncol * qp; t += nt) {
-      const int c = t >> (logP - 2), bt = t & (qp - 1);
+    for (int t = tid; t < nsub * qp; t += nt) {
+      const int cc = t >> (a - 2), bt = t & (qp - 1);
+      const int c = r3 == 3 ? cc / 3 : cc, r = cc - c * r3;
       const int j = bt & (q - 1), i0 = ((bt >> (s - 2)) << s) + j;
-      real2* x = sh + c * cs + i0;
+      real2* x = sh + c * cs + r * m + i0;
       const real2 a0 = x[0], a1 = x[q], a2 = x[2 * q], a3 = x[3 * q];
       const real2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), tw[2 * q + j]);
       const real2 b1 = cadd(a1, a3), b3 = cmul(csub(a1, a3), tw[3 * q + j]);
@@ -51,42 +104,46 @@ __device__ void fft_dif_fwd(typename vec2<real>::type* sh, int ncol, int cs, int
     }
     __syncthreads();
   }
-  if (s == 1) {  // odd log2 P: last radix-2 stage (twiddle 1)
-    for (int t = tid; t < ncol * (P >> 1); t += nt) {
-      const int c = t >> (logP - 1), bt = t & ((P >> 1) - 1);
-      real2* x = sh + c * cs + 2 * bt;
-      const real2 a = x[0], b = x[1];
-      x[0] = cadd(a, b);
-      x[1] = csub(a, b);
+  if (s == 1) {  // odd a: last radix-2 stage (twiddle 1)
+    for (int t = tid; t < nsub * (m >> 1); t += nt) {
+      const int cc = t >> (a - 1), bt = t & ((m >> 1) - 1);
+      const int c = r3 == 3 ? cc / 3 : cc, r = cc - c * r3;
+      real2* x = sh + c * cs + r * m + 2 * bt;
+      const real2 p = x[0], q2 = x[1];
+      x[0] = cadd(p, q2);
+      x[1] = csub(p, q2);
     }
     __syncthreads();
   }
 }
 
-// decimation in time with conjugate twiddles: bit-reversed input, natural-order output (unscaled inverse)
+// decimation in time with conjugate twiddles: permuted-order input, natural-order output (unscaled inverse)
 template <typename real>
-__device__ void fft_dit_inv(typename vec2<real>::type* sh, int ncol, int cs, int P, int logP,
+__device__ void fft_dit_inv(typename vec2<real>::type* sh, int ncol, int cs, FftDims d,
                             const typename vec2<real>::type* tw) {
   using real2 = typename vec2<real>::type;
-  const int tid = threadIdx.x, nt = blockDim.x, qp = P >> 2;
+  const int tid = threadIdx.x, nt = blockDim.x, m = d.m, a = d.a, r3 = d.r3;
+  const int nsub = ncol * r3, qp = m >> 2;
   int s = 1;
-  if (logP & 1) {  // odd log2 P: first radix-2 stage (twiddle 1)
-    for (int t = tid; t < ncol * (P >> 1); t += nt) {
-      const int c = t >> (logP - 1), bt = t & ((P >> 1) - 1);
-      real2* x = sh + c * cs + 2 * bt;
-      const real2 a = x[0], b = x[1];
-      x[0] = cadd(a, b);
-      x[1] = csub(a, b);
+  if (a & 1) {  // odd a: first radix-2 stage (twiddle 1)
+    for (int t = tid; t < nsub * (m >> 1); t += nt) {
+      const int cc = t >> (a - 1), bt = t & ((m >> 1) - 1);
+      const int c = r3 == 3 ? cc / 3 : cc, r = cc - c * r3;
+      real2* x = sh + c * cs + r * m + 2 * bt;
+      const real2 p = x[0], q2 = x[1];
+      x[0] = cadd(p, q2);
+      x[1] = csub(p, q2);
     }
     __syncthreads();
     s = 2;
   }
-  for (; s + 1 <= logP; s += 2) {  // stages s and s+1
+  for (; s + 1 <= a; s += 2) {  // stages s and s+1
     const int q = 1 << (s - 1);
-    for (int t = tid; t < ncol * qp; t += nt) {
-      const int c = t >> (logP - 2), bt = t & (qp - 1);
+    for (int t = tid; t < nsub * qp; t += nt) {
+      const int cc = t >> (a - 2), bt = t & (qp - 1);
+      const int c = r3 == 3 ? cc / 3 : cc, r = cc - c * r3;
       const int j = bt & (q - 1), i0 = ((bt >> (s - 1)) << (s + 1)) + j;
-      real2* x = sh + c * cs + i0;
+      real2* x = sh + c * cs + r * m + i0;
       const real2 a0 = x[0], a2 = x[2 * q];
       const real2 w1 = tw[q + j];
       const real2 t1 = cmulc(x[q], w1), t3 = cmulc(x[3 * q], w1);
@@ -99,18 +156,22 @@ __device__ void fft_dit_inv(typename vec2<real>::type* sh, int ncol, int cs, int
     }
     __syncthreads();
   }
-}
-
-template <typename real>
-__global__ void twiddle_kernel(int P, typename vec2<real>::type* tw) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;  // e = half + j
-  if (e >= P) return;
-  if (e == 0) { tw[0] = mk2((real)1, (real)0); return; }
-  int half = 1 << (31 - __clz(e));
-  int j = e - half;
-  double s, c;
-  sincospi(-(double)j / (double)half, &s, &c);    // exp(-2 pi i j / (2 half))
-  tw[e] = mk2((real)c, (real)s);
+  if (r3 == 3) {
+    const real2* t3 = tw + m;
+    for (int t = tid; t < ncol * m; t += nt) {
+      const int c = t >> a, j = t & (m - 1);
+      real2* x = sh + c * cs + j;
+      const real2 b0 = x[0], b1 = cmulc(x[m], t3[j]), b2 = cmulc(x[2 * m], t3[2 * j]);
+      // a1 = b0 + conj(w3) b1 + w3 b2, a2 = b0 + w3 b1 + conj(w3) b2
+      const real sr = b1.x + b2.x, si = b1.y + b2.y, dr = b1.x - b2.x, di = b1.y - b2.y;
+      const real tr = b0.x + (real)SMM_W3_RE * sr, ti = b0.y + (real)SMM_W3_RE * si;
+      const real ur = -(real)SMM_W3_IM * di, ui = (real)SMM_W3_IM * dr;
+      x[0] = mk2(b0.x + sr, b0.y + si);
+      x[m] = mk2(tr - ur, ti - ui);
+      x[2 * m] = mk2(tr + ur, ti + ui);
+    }
+    __syncthreads();
+  }
 }
 
 // circular kernel images c_k[dy mod P][dx mod P] (Float64): w, -w*hx*dx, -w*hy*dy  (pde.jl:14-20 with
@@ -132,11 +193,12 @@ __global__ void kernel_image_kernel(int Nx, int Ny, int P, double hx, double hy,
 
 // rows forward: in[batch][nrows][rowlen] real -> out[batch][nrows][P/2+1] complex.  CTA = one row pair.
 template <typename real>
-__global__ void __launch_bounds__(256) fft_rows_fwd_kernel(int nrows, int rowlen, int P, int logP, const real* __restrict__ in,
+__global__ void __launch_bounds__(256) fft_rows_fwd_kernel(int nrows, int rowlen, FftDims d, const real* __restrict__ in,
                                     typename vec2<real>::type* __restrict__ out,
                                     const typename vec2<real>::type* __restrict__ twg) {
   using real2 = typename vec2<real>::type;
   extern __shared__ __align__(16) unsigned char smem[];
+  const int P = d.P;
   real2* sh = reinterpret_cast<real2*>(smem);
   real2* tw = sh + P;
   const int b = blockIdx.y, ra = blockIdx.x * 2, rb = ra + 1;
@@ -147,12 +209,12 @@ __global__ void __launch_bounds__(256) fft_rows_fwd_kernel(int nrows, int rowlen
   for (int i = tid; i < P; i += nt) tw[i] = twg[i];
   for (int i = tid; i < P; i += nt) sh[i] = i < rowlen ? mk2(rowa[i], hasb ? rowb[i] : (real)0) : mk2((real)0, (real)0);
   __syncthreads();
-  fft_dif_fwd<real>(sh, 1, P, P, logP, tw);
+  fft_dif_fwd<real>(sh, 1, P, d, tw);
   const int hp1 = P / 2 + 1;
   real2* oa = out + ((size_t)b * nrows + ra) * hp1;
   real2* ob = out + ((size_t)b * nrows + rb) * hp1;
   for (int k = tid; k < hp1; k += nt) {
-    const real2 zk = sh[brev_p(k, logP)], zm = sh[brev_p((P - k) & (P - 1), logP)];
+    const real2 zk = sh[pos_of_freq(k, d)], zm = sh[pos_of_freq(k ? P - k : 0, d)];
     oa[k] = mk2((real)0.5 * (zk.x + zm.x), (real)0.5 * (zk.y - zm.y));
     if (hasb) ob[k] = mk2((real)0.5 * (zk.y + zm.y), (real)-0.5 * (zk.x - zm.x));
   }
@@ -161,13 +223,14 @@ __global__ void __launch_bounds__(256) fft_rows_fwd_kernel(int nrows, int rowlen
 // columns.  MODE 0: convolution (forward, x3 kernel spectra, inverse, keep iy < nkeep).
 //           MODE 1: spectrum only: out[k=blockIdx.y][kx][ky bit-reversed] scaled by `scale`.
 template <typename real, int MODE>
-__global__ void __launch_bounds__(512) fft_cols_kernel(int nrows, int nkeep, int P, int logP, int cols, double scale,
+__global__ void __launch_bounds__(512) fft_cols_kernel(int nrows, int nkeep, FftDims d, int cols, double scale,
                                 const typename vec2<real>::type* __restrict__ A,
                                 const typename vec2<real>::type* __restrict__ khat,
                                 typename vec2<real>::type* __restrict__ G,
                                 const typename vec2<real>::type* __restrict__ twg, size_t gstride) {
   using real2 = typename vec2<real>::type;
   extern __shared__ __align__(16) unsigned char smem[];
+  const int P = d.P;
   const int cs = P + 1;
   real2* R = reinterpret_cast<real2*>(smem);       // [cols][cs]
   real2* Wk = R + (size_t)cols * cs;               // [cols][cs] (MODE 0)
@@ -184,7 +247,7 @@ __global__ void __launch_bounds__(512) fft_cols_kernel(int nrows, int nkeep, int
     R[c * cs + jy] = v;
   }
   __syncthreads();
-  fft_dif_fwd<real>(R, cols, cs, P, logP, tw);
+  fft_dif_fwd<real>(R, cols, cs, d, tw);
   if (MODE == 1) {
     for (int e = tid; e < P * cols; e += nt) {
       const int c = e / P, i = e - c * P;
@@ -203,7 +266,7 @@ __global__ void __launch_bounds__(512) fft_cols_kernel(int nrows, int nkeep, int
       Wk[c * cs + i] = v;
     }
     __syncthreads();
-    fft_dit_inv<real>(Wk, cols, cs, P, logP, tw);
+    fft_dit_inv<real>(Wk, cols, cs, d, tw);
     real2* Gk = G + (size_t)k * gstride + (size_t)b * nkeep * hp1;
     for (int e = tid; e < nkeep * cols; e += nt) {
       const int iy = e / cols, c = e - iy * cols;
@@ -215,11 +278,12 @@ __global__ void __launch_bounds__(512) fft_cols_kernel(int nrows, int nkeep, int
 
 // rows inverse + division: G[k][b][iy][kx] -> Fx, Fy [b][iy][ix].  CTA = one row pair, 3 FFTs.
 template <typename real>
-__global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, int P, int logP, const typename vec2<real>::type* __restrict__ G,
+__global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, FftDims d, const typename vec2<real>::type* __restrict__ G,
                                     size_t gstride, real* __restrict__ Fx, real* __restrict__ Fy,
                                     const typename vec2<real>::type* __restrict__ twg) {
   using real2 = typename vec2<real>::type;
   extern __shared__ __align__(16) unsigned char smem[];
+  const int P = d.P;
   const int cs = P + 1;
   real2* sh = reinterpret_cast<real2*>(smem);  // [3][cs]
   real2* tw = sh + 3 * cs;
@@ -233,7 +297,7 @@ __global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, int P
   // into bit-reversed shared addresses instead was a 32-way bank conflict
   for (int e = tid; e < 3 * P; e += nt) {
     const int k = e / P, pos = e - k * P;
-    const int kk = brev_p(pos, logP);
+    const int kk = freq_of_pos(pos, d);
     const bool up = kk > P / 2;
     const int src = up ? P - kk : kk;
     const real2* Gk = G + (size_t)k * gstride + (size_t)b * Ny * hp1;
@@ -243,7 +307,7 @@ __global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, int P
     sh[k * cs + pos] = mk2(a.x - bb.y, a.y + bb.x);  // A + i B
   }
   __syncthreads();
-  fft_dit_inv<real>(sh, 3, cs, P, logP, tw);
+  fft_dit_inv<real>(sh, 3, cs, d, tw);
   for (int ix = tid; ix < Nx; ix += nt) {
     const real2 o0 = sh[ix], ox = sh[cs + ix], oy = sh[2 * cs + ix];
     const size_t oa = ((size_t)b * Ny + ra) * Nx + ix;
@@ -264,7 +328,8 @@ template <typename real> int cols_for(int P) {
 }  // namespace
 
 struct smm_fft_plan {
-  int Nx, Ny, P, logP, B, precision;
+  int Nx, Ny, P, B, precision;
+  FftDims dims;
   void* tw;    // real2 [P], stage-major
   void* khat;  // real2 [3][P/2+1][P]
   void* ahat;  // real2 [B][Ny][P/2+1]
@@ -294,11 +359,22 @@ static int set_smem(smm_ctx* ctx, int P, int cols) {
 
 int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, double hx, double hy, int B, int precision, smm_fft_plan** out) {
   *out = nullptr;
-  int need = 2 * (Nx > Ny ? Nx : Ny) - 1, P = 32, logP = 5;
-  while (P < need) { P <<= 1; logP++; }
-  SMM_REQUIRE(ctx, P <= 2048, "FFT convolution: grid %dx%d needs P=%d > 2048", Nx, Ny, P);
+  // smallest P = 2^a or 3*2^a (a >= 5) with P >= 2N-1
+  const int need = 2 * (Nx > Ny ? Nx : Ny) - 1;
+  FftDims d = {0, 0, 0, 1};
+  for (int a = 5; a <= 11 && !d.P; a++) {
+    const int p2 = 1 << a, p3 = 3 << (a - 1);  // ... 2^a  and  3*2^(a-1) < 2^(a+1)
+    if (p2 >= need) d = {p2, p2, a, 1};
+    else if (a - 1 >= 5 && p3 >= need) d = {p3, 1 << (a - 1), a - 1, 3};
+  }
+  {
+    const char* ev = getenv("SMM_FFT_POW2");  // debugging: force power-of-two lengths
+    if (ev && ev[0] == '1' && d.r3 == 3) d = {4 * d.m, 4 * d.m, d.a + 2, 1};
+  }
+  const int P = d.P;
+  SMM_REQUIRE(ctx, P > 0 && P <= 2048, "FFT convolution: grid %dx%d needs P=%d > 2048", Nx, Ny, P);
   smm_fft_plan* p = new smm_fft_plan();
-  p->Nx = Nx; p->Ny = Ny; p->P = P; p->logP = logP; p->B = B; p->precision = precision;
+  p->Nx = Nx; p->Ny = Ny; p->P = P; p->dims = d; p->B = B; p->precision = precision;
   p->tw = p->khat = p->ahat = p->g = nullptr;
   const size_t c2 = precision == SMM_PREC_F64 ? 16 : 8;
   const int hp1 = P / 2 + 1;
@@ -327,18 +403,18 @@ int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, double hx, double hy, int 
     if (rc != SMM_OK) { smm_fft_plan_destroy(p); for (void* t : tmp) if (t) cudaFree(t); return rc; }
   }
   // twiddles (Float64 and working precision), kernel images, their spectra in Float64
-  twiddle_kernel<double><<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, (double2*)tmp[1]);
-  if (precision == SMM_PREC_F64) twiddle_kernel<double><<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, (double2*)p->tw);
-  else twiddle_kernel<float><<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, (float2*)p->tw);
+  twiddle_kernel<double><<<(P + 255) / 256, 256, 0, ctx->stream>>>(d, (double2*)tmp[1]);
+  if (precision == SMM_PREC_F64) twiddle_kernel<double><<<(P + 255) / 256, 256, 0, ctx->stream>>>(d, (double2*)p->tw);
+  else twiddle_kernel<float><<<(P + 255) / 256, 256, 0, ctx->stream>>>(d, (float2*)p->tw);
   kernel_image_kernel<<<(unsigned)(((size_t)P * P + 255) / 256), 256, 0, ctx->stream>>>(Nx, Ny, P, hx, hy, (double*)tmp[0]);
   {
     const int cols = cols_for<double>(P);
     size_t sm_rows = ((size_t)P + P) * 16;
-    fft_rows_fwd_kernel<double><<<dim3(P / 2, 3), 256, sm_rows, ctx->stream>>>(P, P, P, logP, (const double*)tmp[0], (double2*)tmp[2], (const double2*)tmp[1]);
+    fft_rows_fwd_kernel<double><<<dim3(P / 2, 3), 256, sm_rows, ctx->stream>>>(P, P, d, (const double*)tmp[0], (double2*)tmp[2], (const double2*)tmp[1]);
     size_t sm_cols1 = ((size_t)cols * (P + 1) + P) * 16;
     double2* kd = precision == SMM_PREC_F64 ? (double2*)p->khat : (double2*)tmp[3];
     fft_cols_kernel<double, 1><<<dim3((hp1 + cols - 1) / cols, 3), 512, sm_cols1, ctx->stream>>>(
-        P, 0, P, logP, cols, 1.0 / ((double)P * (double)P), (const double2*)tmp[2], nullptr, kd, (const double2*)tmp[1], 0);
+        P, 0, d, cols, 1.0 / ((double)P * (double)P), (const double2*)tmp[2], nullptr, kd, (const double2*)tmp[1], 0);
     ctx->launches += 5;
     PL_CUDA(cudaGetLastError());
     if (precision != SMM_PREC_F64) {
@@ -356,7 +432,8 @@ int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, double hx, double hy, int 
 template <typename real>
 static int fft_conv_launch(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, void* Fx, void* Fy) {
   using real2 = typename vec2<real>::type;
-  const int P = p->P, logP = p->logP, hp1 = P / 2 + 1;
+  const int P = p->P, hp1 = P / 2 + 1;
+  const FftDims d = p->dims;
   // columns per CTA: as many as shared memory allows for big batches (coalescing), fewer for small
   // problems so that the column kernel still fills the GPU (C3: one 89x89 instance -> 129 CTAs)
   int cols = cols_for<real>(P);
@@ -367,12 +444,12 @@ static int fft_conv_launch(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, vo
   size_t sm_inv = ((size_t)3 * (P + 1) + P) * sizeof(real2);
   const int rt = P >= 512 ? 256 : 128;
   fft_rows_fwd_kernel<real><<<dim3((p->Ny + 1) / 2, p->B), rt, sm_rows, ctx->stream>>>(
-      p->Ny, p->Nx, P, logP, (const real*)rhosum, (real2*)p->ahat, (const real2*)p->tw);
+      p->Ny, p->Nx, d, (const real*)rhosum, (real2*)p->ahat, (const real2*)p->tw);
   const int ct = (P * cols) / 2 >= 2048 ? 512 : ((P * cols) / 2 >= 256 ? 256 : 128);
   fft_cols_kernel<real, 0><<<dim3((hp1 + cols - 1) / cols, p->B), ct, sm_cols, ctx->stream>>>(
-      p->Ny, p->Ny, P, logP, cols, 1.0, (const real2*)p->ahat, (const real2*)p->khat, (real2*)p->g, (const real2*)p->tw, gstride);
+      p->Ny, p->Ny, d, cols, 1.0, (const real2*)p->ahat, (const real2*)p->khat, (real2*)p->g, (const real2*)p->tw, gstride);
   fft_rows_inv_kernel<real><<<dim3((p->Ny + 1) / 2, p->B), rt, sm_inv, ctx->stream>>>(
-      p->Nx, p->Ny, P, logP, (const real2*)p->g, gstride, (real*)Fx, (real*)Fy, (const real2*)p->tw);
+      p->Nx, p->Ny, d, (const real2*)p->g, gstride, (real*)Fx, (real*)Fy, (const real2*)p->tw);
   ctx->launches += 3;
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;
