@@ -171,6 +171,13 @@ int smm_abm_ensemble_dev(smm_ctx* ctx, const smm_params* q, int32_t precision, i
                          void* us_dev, double* sum_us_dev, double* sum_zs_dev, double* sum_ys_dev,
                          int64_t* numbers_dev);
 
+/* Kernel-density estimate of one set of agents on `grid` (ensemble.jl:27-38, sumgaussian :2-8, gaussian
+ * pde.jl:122): us Julia [Nx,Ny,2,L] = (1/n) sum over the agents with medium i and influencer j of the
+ * Gaussian of width kde_sigma centred at the agent.  Also the density part of randominit (pde.jl:124-159).
+ * x Julia [n,2]; follow [n] 0-based; state [n] in {-1,+1}. */
+int smm_kde(smm_ctx* ctx, int32_t n, int32_t L, int32_t precision, const double* x, const int32_t* follow,
+            const int32_t* state, double kde_sigma, const smm_grid* grid, double* us);
+
 /* Large single population kept on the device between calls (config C5: n = 1e7, CSR network).
  * smm_abm_pop_create uploads the initial condition and network once; smm_abm_pop_step advances
  * `nsteps` steps with Philox noise (one fused kernel per step, no host round trip);

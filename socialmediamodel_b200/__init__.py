@@ -8,7 +8,8 @@ include/smm_b200.h); there is no CPU fallback.
 from .setting import (ABMconstruct, PDEconstruct, PDEconstructcoarse, PDEconstructmeso, Struct, parameters,
                       parameterscontrol, parametersstronginf)
 from .abm import ABMsolve, abm_draws, abm_init, abm_solve_raw
-from .ensemble import ABMsolveensemble, PDEsolveensemble, abm_ensemble_raw, ensemble_means, savetimes_abm
+from .ensemble import (ABMsolveensemble, PDEsolveensemble, abm_ensemble_raw, ensemble_means, kde, runensembles,
+                       savetimes_abm)
 from .pde import (ArrayPartition, PDEBatch, PDESolution, PDEsolve, constructinitial, default_dt, f, gaussian, pde_rhs,
                   pde_solve_raw, randominit, sol2uyz, uniforminit)
 from .population import ABMPopulation

@@ -67,6 +67,7 @@ PROTOTYPES = {
                                    _P, _P, _P, _P, _P, _P, _P]),
     "smm_abm_ensemble_dev": (C.c_int, [_P, C.POINTER(smm_params), _I32, _I32, _I32, _I64, _U64, _P, _P, _I32, _P, _D,
                                        C.POINTER(smm_grid), _P, _P, _P, _P, _P]),
+    "smm_kde": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _D, C.POINTER(smm_grid), _P]),
     "smm_abm_pop_create": (C.c_int, [_P, C.POINTER(smm_params), _I32, _U64, _P, _P, _P, _P, _P, _P, _P, C.POINTER(_P)]),
     "smm_abm_pop_step": (C.c_int, [_P, _P, _I32]),
     "smm_abm_pop_step_injected": (C.c_int, [_P, _P, _P, _P, _P]),

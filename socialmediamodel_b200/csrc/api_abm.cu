@@ -607,6 +607,37 @@ extern "C" int smm_abm_ensemble_dev(smm_ctx* ctx, const smm_params* q, int32_t p
   return SMM_OK;
 }
 
+extern "C" int smm_kde(smm_ctx* ctx, int32_t n, int32_t L, int32_t precision, const double* x, const int32_t* follow,
+                       const int32_t* state, double kde_sigma, const smm_grid* grid, double* us) {
+  SMM_REQUIRE(ctx, ctx != nullptr, "smm_kde: ctx is NULL");
+  SMM_REQUIRE(ctx, n >= 1 && L >= 1 && L <= 256 && x && follow && state && us, "smm_kde: bad argument");
+  SMM_REQUIRE(ctx, precision == SMM_PREC_F32 || precision == SMM_PREC_F64, "smm_kde: unknown precision");
+  SMM_REQUIRE(ctx, kde_sigma > 0, "smm_kde: kde_sigma must be > 0");
+  SMM_TRY(check_grid(ctx, grid, "smm_kde"));
+  for (int i = 0; i < n; i++) {
+    SMM_REQUIRE(ctx, follow[i] >= 0 && follow[i] < L, "smm_kde: follow[%d]=%d outside 0..L-1", i, follow[i]);
+    SMM_REQUIRE(ctx, state[i] == 1 || state[i] == -1, "smm_kde: state[%d]=%d is not +-1", i, state[i]);
+  }
+  SMM_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t rs = precision == SMM_PREC_F64 ? 8 : 4, per = (size_t)grid->Nx * grid->Ny * 2 * L;
+  void *dx, *dst32, *dfol, *dus;
+  signed char* dst;
+  SMM_TRY(upload_real(ctx, S_XS, x, (size_t)2 * n, precision, &dx));
+  SMM_TRY(upload(ctx, S_TMP0, state, (size_t)n * 4, &dst32));
+  SMM_TRY(smm_scratch(ctx, S_STATE, n, (void**)&dst));
+  SMM_TRY(smm_launch_convert_i32_to_i8(ctx, (const int32_t*)dst32, dst, n));
+  SMM_TRY(upload(ctx, S_FOLS, follow, (size_t)n * 4, &dfol));
+  SMM_TRY(smm_scratch(ctx, S_US, per * rs, &dus));
+  KdeArgs Kd;
+  Kd.n = n; Kd.L = L; Kd.S = 1; Kd.Nx = grid->Nx; Kd.Ny = grid->Ny;
+  Kd.gx0 = grid->x0; Kd.gy0 = grid->y0; Kd.dx = grid->dx; Kd.dy = grid->dy; Kd.sigma = kde_sigma;
+  Kd.xs = dx; Kd.follows = (const int32_t*)dfol; Kd.state = dst; Kd.nsave = 1; Kd.us = dus;
+  SMM_TRY(smm_launch_kde(ctx, Kd, precision));
+  SMM_TRY(download_real(ctx, dus, per, precision, us));
+  SMM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return SMM_OK;
+}
+
 // ---------------------------------------------------------------------------------------
 // large resident population (C5)
 // ---------------------------------------------------------------------------------------

@@ -79,6 +79,29 @@ def ABMsolveensemble(NT=200, N=10, *, savepoints=4, init="4inf", p=None, q=None,
     return us, zs, ys, (p, q)
 
 
+def kde(x, follow, state, *, p, L, sigma=0.1, precision="f64", ctx=None):
+    """smm_kde: us[Nx,Ny,2,L] = (1/n) sum of Gaussians per (medium, influencer) class (ensemble.jl:27-38)."""
+    ctx = _lib.Context.default() if ctx is None else ctx
+    n = len(follow)
+    xx = _lib.f_array(np.asarray(x, float).reshape((n, 2), order="F"), np.float64)
+    fo = np.ascontiguousarray(follow, np.int32); st = np.ascontiguousarray(state, np.int32)
+    Nx, Ny = p.X.shape
+    us = np.empty((Nx, Ny, 2, L), order="F")
+    g = _lib.make_grid(p)
+    ctx.check(ctx.lib.smm_kde(ctx.h, n, int(L), _lib.PREC[precision], _lib.ptr(xx), _lib.ptr(fo), _lib.ptr(st),
+                              float(sigma), C.byref(g), _lib.ptr(us)), "smm_kde")
+    return us
+
+
+def runensembles(N, *, NT=200, tmax=2.0, savepoints=5, q=None, sigma=0.1, save=True, precision="f32"):
+    """ensemble.jl:88-95 without the plotting call: one PDE solve and N ABM realizations saved at the same
+    number of points.  Returns (us, zs, ys, (p, q), us2, zs2, ys2, (p2, q))."""
+    q = parameters() if q is None else q
+    us, zs, ys, (p, qp) = PDEsolveensemble(tmax, 1, savepoints=savepoints, q=q, save=save, precision=precision)
+    us2, zs2, ys2, (p2, q2) = ABMsolveensemble(NT, N, savepoints=savepoints, q=q, sigma=sigma, save=save, precision=precision)
+    return us, zs, ys, (p, qp), us2, zs2, ys2, (p2, qp)
+
+
 def ensemble_means(us, zs, ys):
     """plotting.jl:361-363."""
     N = us.shape[-1]

@@ -62,15 +62,9 @@ def randominit(pq, rng=None):
     pos = rng.random((n, 2)) * (dom[0, 1] - dom[0, 0]) + dom[0, 0]
     med = rng.integers(0, 2, n)
     inf = np.where(pos[:, 1] > 0, np.where(pos[:, 0] > 0, 0, 1), np.where(pos[:, 0] > 0, 2, 3))
-    rho = np.zeros((p.N_x, p.N_y, 2, L), order="F")
-    xa, ya = p.X[:, 0], p.Y[0, :]
-    for i in range(2):
-        for j in range(L):
-            sel = (med == i) & (inf == j)
-            if sel.any():
-                ex = np.exp(-50.0 * (xa[:, None] - pos[sel, 0][None, :]) ** 2)
-                ey = np.exp(-50.0 * (ya[:, None] - pos[sel, 1][None, :]) ** 2)
-                rho[:, :, i, j] = (ex @ ey.T) / (2 * np.pi * 0.01)
+    # density = KDE (sigma = 0.1, pde.jl:122,136) of the sampled agents on the PDE grid: the GPU kernel K4
+    from .ensemble import kde
+    rho = kde(pos, inf, np.where(med == 1, 1, -1), p=p, L=L, sigma=0.1, precision="f64") * n
     u0 = rho / (rho.sum() * p.dV)
     counts = np.array([[np.sum((inf == j) & (med == i)) for i in range(2)] for j in range(L)], float)
     y0 = np.stack([[pos[inf == j, d].sum() for j in range(L)] for d in range(2)]) / counts.sum(axis=1)[None, :]

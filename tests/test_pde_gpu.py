@@ -192,3 +192,25 @@ def test_rhs_refined_grids_f32(dx, N):
     dur, dzr, dyr = P.rhs(*uzy0.x, oracle_p(p), dict(q))
     assert rel(du, dur) < TOL32, rel(du, dur)
     assert np.abs(dy - dyr).max() < 1e-7 and np.abs(dz - dzr).max() < 1e-7
+
+
+def test_randominit_uses_gpu_kde_and_matches_oracle():
+    """randominit (pde.jl:124-168): density = KDE of sampled agents (GPU kernel K4), y0 = class means."""
+    p = smm.PDEconstructcoarse()
+    q = smm.parameters(n=80)
+    uzy0, ci, cm = smm.randominit((p, q), np.random.default_rng(4))
+    rng = np.random.default_rng(4)
+    pos = rng.random((80, 2)) * (p.domain[0, 1] - p.domain[0, 0]) + p.domain[0, 0]
+    med = rng.integers(0, 2, 80)
+    ur, zr, yr, _, _ = P.randominit_from(oracle_p(p), dict(q), pos, med)
+    assert rel(uzy0.x[0], ur) < 1e-10
+    np.testing.assert_allclose(uzy0.x[2], yr, rtol=1e-12)
+    assert abs(uzy0.x[0].sum() * p.dV - 1) < 1e-12
+    sol, _ = smm.PDEsolve(0.004, init="random", p=p, q=q, rng=np.random.default_rng(4), precision="f64")
+    assert np.isfinite(sol(0.004).x[0]).all()
+
+
+def test_runensembles_shapes():
+    us, zs, ys, (p, q), us2, zs2, ys2, _ = smm.runensembles(3, NT=10, tmax=0.01, savepoints=2, save=False)
+    assert us.shape == (89, 89, 2, 4, 2, 1) and us2.shape == (89, 89, 2, 4, 2, 3)
+    assert np.isfinite(us).all() and np.isfinite(us2).all()
