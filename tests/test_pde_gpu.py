@@ -214,3 +214,17 @@ def test_runensembles_shapes():
     us, zs, ys, (p, q), us2, zs2, ys2, _ = smm.runensembles(3, NT=10, tmax=0.01, savepoints=2, save=False)
     assert us.shape == (89, 89, 2, 4, 2, 1) and us2.shape == (89, 89, 2, 4, 2, 3)
     assert np.isfinite(us).all() and np.isfinite(us2).all()
+
+
+def test_c3_full_horizon_fp32_drift():
+    """C3: PDEsolve on the default 89x89 grid, RK4 dt=1e-3 to tmax=2.0 (2 000 steps).  FP32 state must stay
+    within 1e-5 of the Float64 run at the final time (the Float64 path is oracle-exact, see above)."""
+    p = smm.PDEconstruct()
+    q = smm.parameters()
+    uzy0, q2 = smm.constructinitial("4inf", (p, q))
+    o32 = smm.pde_solve_raw(p, [q2], *uzy0.x, dt=1e-3, nsteps=2000, savesteps=[200, 2000], precision="f32")
+    o64 = smm.pde_solve_raw(p, [q2], *uzy0.x, dt=1e-3, nsteps=2000, savesteps=[200, 2000], precision="f64")
+    for m in range(2):
+        assert rel(o32["us"][..., m, 0], o64["us"][..., m, 0]) < TOL32
+        assert np.abs(o32["ys"][..., m, 0] - o64["ys"][..., m, 0]).max() < 1e-6
+    assert abs(o64["us"][..., 1, 0].sum() * p.dV - 1.0113) < 2e-3     # the scheme is not mass-conserving (SURVEY hard part 7)
