@@ -243,24 +243,38 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
   const size_t plane = (size_t)Nx * Ny;
   const real* U = static_cast<const real*>(A.U) + (size_t)b * NP * plane;
   // ---- stage the tiles (clamped at the domain edge; the clamped values are never used there)
-  // (loads are issued in batches of 6 before their shared-memory stores: the kernel is bound by
-  //  global-load latency, so the number of independent loads in flight per thread is what matters)
+  // Thread (tx,ty) stages tile rows ty (and ty+8 for ty < 2) at columns tx (and tx+32 for tx < 2): the
+  // four global offsets are computed once and reused for every plane, and all loads of a batch of
+  // planes are issued before their shared-memory stores (the kernel is sensitive to global-load
+  // latency, so the number of independent loads in flight per thread is what matters).
   {
-    constexpr int UB = 6;
-    const int total = NP * TH * TW;
-    for (int e0 = tid; e0 < total; e0 += UB * BX * BY) {
-      real v[UB];
+    const int gxa = min(max(bx0 + tx - 1, 0), Nx - 1), gxb = min(bx0 + tx + 31, Nx - 1);
+    const int gya = min(max(by0 + ty - 1, 0), Ny - 1), gyb = min(by0 + ty + 7, Ny - 1);
+    const unsigned oaa = (unsigned)gya * Nx + gxa, oab = (unsigned)gya * Nx + gxb;
+    const unsigned oba = (unsigned)gyb * Nx + gxa, obb = (unsigned)gyb * Nx + gxb;
+    const bool cb = tx < 2, rb = ty < 2;
+    real* t0 = tile + ty * TW + tx;
+    constexpr int PBATCH = 4;
+    for (int p0 = 0; p0 < NP; p0 += PBATCH) {
+      real vaa[PBATCH], vab[PBATCH], vba[PBATCH], vbb[PBATCH];
 #pragma unroll
-      for (int q = 0; q < UB; q++) {
-        const int e = min(e0 + q * BX * BY, total - 1);
-        const int p = e / (TH * TW), r = e - p * (TH * TW);
-        const int yy = r / TW, xx = r - yy * TW;
-        const int gx = min(max(bx0 + xx - 1, 0), Nx - 1), gy = min(max(by0 + yy - 1, 0), Ny - 1);
-        v[q] = U[(size_t)p * plane + (size_t)gy * Nx + gx];
+      for (int q = 0; q < PBATCH; q++) {
+        const real* Up = U + (size_t)min(p0 + q, NP - 1) * plane;
+        vaa[q] = Up[oaa];
+        vab[q] = cb ? Up[oab] : (real)0;
+        vba[q] = rb ? Up[oba] : (real)0;
+        vbb[q] = (cb && rb) ? Up[obb] : (real)0;
       }
 #pragma unroll
-      for (int q = 0; q < UB; q++)
-        if (e0 + q * BX * BY < total) tile[e0 + q * BX * BY] = v[q];
+      for (int q = 0; q < PBATCH; q++) {
+        if (p0 + q < NP) {
+          real* tp = t0 + (p0 + q) * TH * TW;
+          tp[0] = vaa[q];
+          if (cb) tp[32] = vab[q];
+          if (rb) tp[8 * TW] = vba[q];
+          if (cb && rb) tp[8 * TW + 32] = vbb[q];
+        }
+      }
     }
   }
   __syncthreads();  // s_par visible
