@@ -308,3 +308,26 @@ def test_abm_ensemble_chunked_copy_pipeline():
     assert out["numbers"].sum(axis=(0, 1)).tolist() == [R * 24] * (NT + 1)
     pinned = smm.abm_ensemble_raw(NT, R, p=p, q=q, savesteps=st, first_realization=1, seed=3, precision="f32", pinned=True)
     np.testing.assert_array_equal(pinned["us"], out["us"])
+
+
+@pytest.mark.parametrize("name", ["abm_dense_n60.npz", "abm_csr_n80.npz"])
+def test_abm_against_golden_fixtures(name):
+    """Committed golden vectors (tests/golden, oracle-generated): follower histories bit-exact, positions /
+    KDE within the north-star tolerances, in both arithmetic modes."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+    n, NT = int(g["n"]), int(g["NT"])
+    p, q = smm.ABMconstruct(), smm.parameters(n=n)
+    net = (g["rowptr"], g["colidx"]) if "rowptr" in g else None
+    r = {k: g[k] for k in ("x0", "state", "follow0", "inf0", "media0", "xi", "u1", "u2")}
+    init, inj = stack_inputs([r])
+    for precision, rtol in (("f64", RTOL_F64), ("f32", RTOL_F32)):
+        out = smm.abm_solve_raw(NT, p=p, q=q, precision=precision, init_state=init, injected=inj, network=net)
+        same = np.array_equal(out["follows"][:, :, 0].T, g["follows"])
+        assert same or (precision == "f32" and float(g["min_margin"]) < 1e-5)
+        if same:
+            assert relerr(np.transpose(out["xs"][:, :, :, 0], (2, 0, 1)), g["xs"]) < rtol
+        ens = smm.abm_ensemble_raw(NT, 1, p=p, q=q, savesteps=g["savesteps"], precision=precision, init_state=init,
+                                   injected=inj, network=net, want=("us",))
+        if same:
+            assert np.abs(ens["us"][..., 0] - g["us"]).max() / g["us"].max() < max(rtol, 1e-10)

@@ -228,3 +228,20 @@ def test_c3_full_horizon_fp32_drift():
         assert rel(o32["us"][..., m, 0], o64["us"][..., m, 0]) < TOL32
         assert np.abs(o32["ys"][..., m, 0] - o64["ys"][..., m, 0]).max() < 1e-6
     assert abs(o64["us"][..., 1, 0].sum() * p.dV - 1.0113) < 2e-3     # the scheme is not mass-conserving (SURVEY hard part 7)
+
+
+def test_pde_against_golden_fixtures():
+    """Committed golden vectors (tests/golden/pde_coarse.npz, oracle-generated)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pde_coarse.npz"))
+    p, q = smm.PDEconstructcoarse(), smm.parameters()
+    for precision, tol in (("f64", TOL64), ("f32", TOL32)):
+        du, dz, dy = smm.pde_rhs(g["u"], g["z"], g["y"], p=p, q=q, precision=precision)
+        assert rel(du, g["du"]) < tol
+        assert np.abs(dy - g["dy"]).max() < max(tol, 1e-9) and np.abs(dz - g["dz"]).max() < max(tol, 1e-9)
+        q5 = q.merge(L=5, controlled_inf=g["ci5"], controlled_med=g["cm5"])
+        du5, dz5, dy5 = smm.pde_rhs(g["u5"], g["z"], g["y5"], p=p, q=q5, precision=precision)
+        assert rel(du5, g["du5"]) < tol and np.abs(dy5 - g["dy5"]).max() < max(tol, 1e-7)
+        uzy0, q2 = smm.constructinitial("4inf", (p, q))
+        out = smm.pde_solve_raw(p, [q2], *uzy0.x, dt=1e-3, nsteps=10, savesteps=[10], precision=precision)
+        assert rel(out["us"][..., 0, 0], g["u_rk4_10"]) < max(tol, 1e-10)
