@@ -193,7 +193,7 @@ __global__ void kernel_image_kernel(int Nx, int Ny, int P, double hx, double hy,
 
 // rows forward: in[batch][nrows][rowlen] real -> out[batch][nrows][P/2+1] complex.  CTA = one row pair.
 template <typename real>
-__global__ void __launch_bounds__(256) fft_rows_fwd_kernel(int nrows, int rowlen, FftDims d, const real* __restrict__ in,
+__global__ void __launch_bounds__(256) fft_rows_fwd_kernel(int nrows, int rowlen, int rowpitch, FftDims d, const real* __restrict__ in,
                                     typename vec2<real>::type* __restrict__ out,
                                     const typename vec2<real>::type* __restrict__ twg) {
   using real2 = typename vec2<real>::type;
@@ -203,8 +203,8 @@ __global__ void __launch_bounds__(256) fft_rows_fwd_kernel(int nrows, int rowlen
   real2* tw = sh + P;
   const int b = blockIdx.y, ra = blockIdx.x * 2, rb = ra + 1;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const real* rowa = in + ((size_t)b * nrows + ra) * rowlen;
-  const real* rowb = in + ((size_t)b * nrows + rb) * rowlen;
+  const real* rowa = in + ((size_t)b * nrows + ra) * rowpitch;
+  const real* rowb = in + ((size_t)b * nrows + rb) * rowpitch;
   const bool hasb = rb < nrows;
   for (int i = tid; i < P; i += nt) tw[i] = twg[i];
   for (int i = tid; i < P; i += nt) sh[i] = i < rowlen ? mk2(rowa[i], hasb ? rowb[i] : (real)0) : mk2((real)0, (real)0);
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(512) fft_cols_kernel(int nrows, int nkeep, Fft
 
 // rows inverse + division: G[k][b][iy][kx] -> Fx, Fy [b][iy][ix].  CTA = one row pair, 3 FFTs.
 template <typename real>
-__global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, FftDims d, const typename vec2<real>::type* __restrict__ G,
+__global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, int Pw, FftDims d, const typename vec2<real>::type* __restrict__ G,
                                     size_t gstride, real* __restrict__ Fx, real* __restrict__ Fy,
                                     const typename vec2<real>::type* __restrict__ twg) {
   using real2 = typename vec2<real>::type;
@@ -310,12 +310,12 @@ __global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, FftDi
   fft_dit_inv<real>(sh, 3, cs, d, tw);
   for (int ix = tid; ix < Nx; ix += nt) {
     const real2 o0 = sh[ix], ox = sh[cs + ix], oy = sh[2 * cs + ix];
-    const size_t oa = ((size_t)b * Ny + ra) * Nx + ix;
+    const size_t oa = ((size_t)b * Ny + ra) * Pw + ix;
     Fx[oa] = ox.x / o0.x;  // pde.jl:58 force ./ norms
     Fy[oa] = oy.x / o0.x;
     if (hasb) {
-      Fx[oa + Nx] = ox.y / o0.y;
-      Fy[oa + Nx] = oy.y / o0.y;
+      Fx[oa + Pw] = ox.y / o0.y;
+      Fy[oa + Pw] = oy.y / o0.y;
     }
   }
 }
@@ -328,7 +328,7 @@ template <typename real> int cols_for(int P) {
 }  // namespace
 
 struct smm_fft_plan {
-  int Nx, Ny, P, B, precision;
+  int Nx, Ny, Pw, P, B, precision;  // Pw: row pitch of rhosum / Fx / Fy
   FftDims dims;
   void* tw;    // real2 [P], stage-major
   void* khat;  // real2 [3][P/2+1][P]
@@ -357,7 +357,7 @@ static int set_smem(smm_ctx* ctx, int P, int cols) {
   return SMM_OK;
 }
 
-int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, double hx, double hy, int B, int precision, smm_fft_plan** out) {
+int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, int Pw, double hx, double hy, int B, int precision, smm_fft_plan** out) {
   *out = nullptr;
   // smallest P = 2^a or 3*2^a (a >= 5) with P >= 2N-1
   const int need = 2 * (Nx > Ny ? Nx : Ny) - 1;
@@ -374,7 +374,7 @@ int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, double hx, double hy, int 
   const int P = d.P;
   SMM_REQUIRE(ctx, P > 0 && P <= 2048, "FFT convolution: grid %dx%d needs P=%d > 2048", Nx, Ny, P);
   smm_fft_plan* p = new smm_fft_plan();
-  p->Nx = Nx; p->Ny = Ny; p->P = P; p->dims = d; p->B = B; p->precision = precision;
+  p->Nx = Nx; p->Ny = Ny; p->Pw = Pw; p->P = P; p->dims = d; p->B = B; p->precision = precision;
   p->tw = p->khat = p->ahat = p->g = nullptr;
   const size_t c2 = precision == SMM_PREC_F64 ? 16 : 8;
   const int hp1 = P / 2 + 1;
@@ -410,7 +410,7 @@ int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, double hx, double hy, int 
   {
     const int cols = cols_for<double>(P);
     size_t sm_rows = ((size_t)P + P) * 16;
-    fft_rows_fwd_kernel<double><<<dim3(P / 2, 3), 256, sm_rows, ctx->stream>>>(P, P, d, (const double*)tmp[0], (double2*)tmp[2], (const double2*)tmp[1]);
+    fft_rows_fwd_kernel<double><<<dim3(P / 2, 3), 256, sm_rows, ctx->stream>>>(P, P, P, d, (const double*)tmp[0], (double2*)tmp[2], (const double2*)tmp[1]);
     size_t sm_cols1 = ((size_t)cols * (P + 1) + P) * 16;
     double2* kd = precision == SMM_PREC_F64 ? (double2*)p->khat : (double2*)tmp[3];
     fft_cols_kernel<double, 1><<<dim3((hp1 + cols - 1) / cols, 3), 512, sm_cols1, ctx->stream>>>(
@@ -444,12 +444,12 @@ static int fft_conv_launch(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, vo
   size_t sm_inv = ((size_t)3 * (P + 1) + P) * sizeof(real2);
   const int rt = P >= 512 ? 256 : 128;
   fft_rows_fwd_kernel<real><<<dim3((p->Ny + 1) / 2, p->B), rt, sm_rows, ctx->stream>>>(
-      p->Ny, p->Nx, d, (const real*)rhosum, (real2*)p->ahat, (const real2*)p->tw);
+      p->Ny, p->Nx, p->Pw, d, (const real*)rhosum, (real2*)p->ahat, (const real2*)p->tw);
   const int ct = (P * cols) / 2 >= 2048 ? 512 : ((P * cols) / 2 >= 256 ? 256 : 128);
   fft_cols_kernel<real, 0><<<dim3((hp1 + cols - 1) / cols, p->B), ct, sm_cols, ctx->stream>>>(
       p->Ny, p->Ny, d, cols, 1.0, (const real2*)p->ahat, (const real2*)p->khat, (real2*)p->g, (const real2*)p->tw, gstride);
   fft_rows_inv_kernel<real><<<dim3((p->Ny + 1) / 2, p->B), rt, sm_inv, ctx->stream>>>(
-      p->Nx, p->Ny, d, (const real2*)p->g, gstride, (real*)Fx, (real*)Fy, (const real2*)p->tw);
+      p->Nx, p->Ny, p->Pw, d, (const real2*)p->g, gstride, (real*)Fx, (real*)Fy, (const real2*)p->tw);
   ctx->launches += 3;
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;

@@ -45,7 +45,7 @@ enum { ACC_NONE = 0, ACC_INIT = 1, ACC_ADD = 2, ACC_FINAL = 3 };
 enum { FIN_INIT = 0, FIN_STAGE = 1 };
 
 struct StageArgs {
-  int B, L, Nx, Ny;
+  int B, L, Nx, Ny, Pw;  // Pw = row pitch in elements (Nx rounded up to a 16-byte multiple: TMA)
   double gx0, gy0, dx, dy;
   const void* U;      // stage state being differentiated
   const void* un;     // state at the start of the step
@@ -174,12 +174,12 @@ __global__ void __launch_bounds__(BX* BY) pde_moments_kernel(StageArgs A) {
   const int lane = threadIdx.x, warp = threadIdx.y;
   __shared__ double part_w[BY * 2 * LMAX * 3];
   __shared__ double sm[2 * LMAX * 3];
-  const size_t plane = (size_t)Nx * Ny;
+  const size_t plane = (size_t)A.Pw * Ny;
   const real* U = static_cast<const real*>(A.U) + (size_t)b * 2 * L * plane;
   const real X = (real)(A.gx0 + ix * A.dx), Y = (real)(A.gy0 + iy * A.dy);
   real rs = 0;
   for (int pl = 0; pl < 2 * L; pl++) {
-    real v = in ? U[(size_t)pl * plane + (size_t)iy * Nx + ix] : (real)0;
+    real v = in ? U[(size_t)pl * plane + (size_t)iy * A.Pw + ix] : (real)0;
     rs += v;
     real s0 = warp_sum(v), s1 = warp_sum(v * X);
     if (lane == 0) {
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(BX* BY) pde_moments_kernel(StageArgs A) {
       o[0] = (double)s0; o[1] = (double)s1; o[2] = (double)s0 * (double)Y;
     }
   }
-  if (in) static_cast<real*>(A.rhosum_out)[(size_t)b * plane + (size_t)iy * Nx + ix] = rs;
+  if (in) static_cast<real*>(A.rhosum_out)[(size_t)b * plane + (size_t)iy * A.Pw + ix] = rs;
   moments_epilogue(A, b, part_w, sm, FIN_INIT);
 }
 
@@ -240,7 +240,8 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
   }
   if (tid < 2) { s_zx[tid] = (real)A.coef[b].z[tid][0]; s_zy[tid] = (real)A.coef[b].z[tid][1]; }
   if (tid == 0) { s_par[0] = (real)A.inst[b].a; s_par[1] = (real)A.inst[b].b; s_par[2] = (real)A.inst[b].c; s_par[3] = (real)A.inst[b].D; }
-  const size_t plane = (size_t)Nx * Ny;
+  const int Pw = A.Pw;
+  const size_t plane = (size_t)Pw * Ny;
   const real* U = static_cast<const real*>(A.U) + (size_t)b * NP * plane;
   // ---- stage the tiles (clamped at the domain edge; the clamped values are never used there)
   // Thread (tx,ty) stages tile rows ty (and ty+8 for ty < 2) at columns tx (and tx+32 for tx < 2): the
@@ -250,8 +251,8 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
   {
     const int gxa = min(max(bx0 + tx - 1, 0), Nx - 1), gxb = min(bx0 + tx + 31, Nx - 1);
     const int gya = min(max(by0 + ty - 1, 0), Ny - 1), gyb = min(by0 + ty + 7, Ny - 1);
-    const unsigned oaa = (unsigned)gya * Nx + gxa, oab = (unsigned)gya * Nx + gxb;
-    const unsigned oba = (unsigned)gyb * Nx + gxa, obb = (unsigned)gyb * Nx + gxb;
+    const unsigned oaa = (unsigned)gya * Pw + gxa, oab = (unsigned)gya * Pw + gxb;
+    const unsigned oba = (unsigned)gyb * Pw + gxa, obb = (unsigned)gyb * Pw + gxb;
     const bool cb = tx < 2, rb = ty < 2;
     real* t0 = tile + ty * TW + tx;
     constexpr int PBATCH = 4;
@@ -285,12 +286,12 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
     for (int e = tid; e < BY * TW; e += BX * BY) {
       const int yy = e / TW, xx = e - yy * TW;
       const int gx = min(max(bx0 + xx - 1, 0), Nx - 1), gy = min(by0 + yy, Ny - 1);
-      sFx[e] = pa0 * Fx[(size_t)gy * Nx + gx];
+      sFx[e] = pa0 * Fx[(size_t)gy * Pw + gx];
     }
     for (int e = tid; e < TH * BX; e += BX * BY) {
       const int yy = e / BX, xx = e - yy * BX;
       const int gx = min(bx0 + xx, Nx - 1), gy = min(max(by0 + yy - 1, 0), Ny - 1);
-      sFy[e] = pa0 * Fy[(size_t)gy * Nx + gx];
+      sFy[e] = pa0 * Fy[(size_t)gy * Pw + gx];
     }
   }
   __syncthreads();
@@ -322,7 +323,7 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
   const real* un = static_cast<const real*>(A.un) + (size_t)b * NP * plane;
   real* Uout = static_cast<real*>(A.Uout) + (size_t)b * NP * plane;
   real* acc = A.acc ? static_cast<real*>(A.acc) + (size_t)b * NP * plane : nullptr;
-  const size_t o_c = (size_t)cy * Nx + cx;
+  const size_t o_c = (size_t)cy * Pw + cx;
   const real dtA = (real)A.A, dtB = (real)A.Bc, dtC = (real)(A.C * A.dt), dtw = (real)(A.bw * A.dt);
   // step-start state and accumulator of this grid point for all planes, loaded up front (independent
   // loads in flight together; inside the plane loop they would queue behind possibly-aliasing stores)
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
 // = exp(-h sqrt(d^2 + ady^2)) for d in -(Nx-1)..Nx-1 (row-extended so the index is monotone in jx).
 constexpr int CT = 8, NS = 16;
 template <typename real, bool TABLE_IN_SMEM>
-__global__ void __launch_bounds__(CT* CT* NS) pde_conv_kernel(int Nx, int Ny, double h, const real* __restrict__ wext,
+__global__ void __launch_bounds__(CT* CT* NS) pde_conv_kernel(int Nx, int Ny, int Pw, double h, const real* __restrict__ wext,
                                                                const real* __restrict__ rhosum, real* __restrict__ Fx,
                                                                real* __restrict__ Fy) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -424,13 +425,13 @@ __global__ void __launch_bounds__(CT* CT* NS) pde_conv_kernel(int Nx, int Ny, do
     __syncthreads();
   }
   const real* wt = TABLE_IN_SMEM ? wsm : wext;
-  const real* rho = rhosum + (size_t)b * Nx * Ny;
+  const real* rho = rhosum + (size_t)b * Pw * Ny;
   const int cx = min(ix, Nx - 1), cy = min(iy, Ny - 1);
   real a0 = 0, a1 = 0, a2 = 0;
   for (int jy = slice; jy < Ny; jy += NS) {
     const int dyi = jy - cy;
     const real* wrow = wt + (size_t)(dyi < 0 ? -dyi : dyi) * W + (Nx - 1 - cx);
-    const real* rrow = rho + (size_t)jy * Nx;
+    const real* rrow = rho + (size_t)jy * Pw;
     real rowsum = 0, rowx = 0;
     real d = (real)(-cx);
 #pragma unroll 4
@@ -456,8 +457,8 @@ __global__ void __launch_bounds__(CT* CT* NS) pde_conv_kernel(int Nx, int Ny, do
       s2 += red[(s * CT * CT + o) * 3 + 2];
     }
     // pde.jl:58: force ./ norms (the dV factors cancel); K = w * (x' - x) with x' - x = h * d
-    Fx[(size_t)b * Nx * Ny + (size_t)iy * Nx + ix] = (real)h * s1 / s0;
-    Fy[(size_t)b * Nx * Ny + (size_t)iy * Nx + ix] = (real)h * s2 / s0;
+    Fx[(size_t)b * Pw * Ny + (size_t)iy * Pw + ix] = (real)h * s1 / s0;
+    Fy[(size_t)b * Pw * Ny + (size_t)iy * Pw + ix] = (real)h * s2 / s0;
   }
 }
 
@@ -480,15 +481,26 @@ __global__ void broadcast_kernel(real* dst, size_t per_inst, int B) {  // copy i
   }
 }
 
+// dense [rows][Nx] <-> pitched [rows][Pw] (pad columns are left untouched / skipped)
+template <typename Tin, typename Tout>
+__global__ void pitch_copy_kernel(const Tin* __restrict__ in, Tout* __restrict__ out, size_t rows, int Nx, int pin, int pout) {
+  size_t stride = (size_t)gridDim.x * blockDim.x, total = rows * Nx;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+    const size_t r = e / Nx;
+    const int x = (int)(e - r * Nx);
+    out[r * pout + x] = (Tout)in[r * pin + x];
+  }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
 // batch object
 // ---------------------------------------------------------------------------------------------
 struct smm_pde_batch {
-  int B, L, Nx, Ny, precision;
+  int B, L, Nx, Ny, Pw, precision;  // Pw: device row pitch (elements)
   smm_grid grid;
-  size_t plane, per_inst, rs;
+  size_t plane, per_inst, host_per, rs;  // plane/per_inst: device (pitched) element counts; host_per: dense
   void *u, *Ua, *Ub, *acc, *rhosum, *Fx, *Fy, *wext;
   double* partials;
   unsigned* counters;
@@ -516,7 +528,7 @@ static void pde_free(smm_pde_batch* pb) {
 static StageArgs base_args(const smm_pde_batch* pb) {
   StageArgs A;
   memset(&A, 0, sizeof A);
-  A.B = pb->B; A.L = pb->L; A.Nx = pb->Nx; A.Ny = pb->Ny;
+  A.B = pb->B; A.L = pb->L; A.Nx = pb->Nx; A.Ny = pb->Ny; A.Pw = pb->Pw;
   A.gx0 = pb->grid.x0; A.gy0 = pb->grid.y0; A.dx = pb->grid.dx; A.dy = pb->grid.dy;
   A.Fx = pb->Fx; A.Fy = pb->Fy; A.rhosum_out = pb->rhosum;
   A.partials = pb->partials; A.counters = pb->counters; A.coef = pb->coef; A.ode = pb->ode; A.inst = pb->inst;
@@ -540,7 +552,7 @@ static int launch_conv(smm_ctx* ctx, smm_pde_batch* pb) {
   const int threads = CT * CT * NS;
   const double h = pb->grid.dx;
 #define CONV(real, SM)                                                                                      \
-  pde_conv_kernel<real, SM><<<grid, threads, pb->conv_smem, ctx->stream>>>(pb->Nx, pb->Ny, h, (const real*)pb->wext, \
+  pde_conv_kernel<real, SM><<<grid, threads, pb->conv_smem, ctx->stream>>>(pb->Nx, pb->Ny, pb->Pw, h, (const real*)pb->wext, \
                                                                           (const real*)pb->rhosum, (real*)pb->Fx, (real*)pb->Fy)
   if (pb->precision == SMM_PREC_F64) { if (pb->table_in_smem) CONV(double, true); else CONV(double, false); }
   else { if (pb->table_in_smem) CONV(float, true); else CONV(float, false); }
@@ -666,8 +678,10 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
   pb->fft = nullptr;
   pb->no_graph = false;
   pb->rs = precision == SMM_PREC_F64 ? 8 : 4;
-  pb->plane = (size_t)grid->Nx * grid->Ny;
+  pb->Pw = (grid->Nx + 3) & ~3;  // 16-byte row pitch in both precisions (TMA global strides)
+  pb->plane = (size_t)pb->Pw * grid->Ny;
   pb->per_inst = pb->plane * 2 * L;
+  pb->host_per = (size_t)grid->Nx * grid->Ny * 2 * L;
   pb->nbx = (grid->Nx + BX - 1) / BX; pb->nby = (grid->Ny + BY - 1) / BY;
   const size_t state_bytes = (size_t)B * pb->per_inst * pb->rs, field_bytes = (size_t)B * pb->plane * pb->rs;
   const size_t wcount = (size_t)grid->Ny * (2 * grid->Nx - 1);
@@ -677,6 +691,12 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
   PB_CUDA(cudaMalloc(&pb->Ub, state_bytes)); PB_CUDA(cudaMalloc(&pb->acc, state_bytes));
   PB_CUDA(cudaMalloc(&pb->rhosum, field_bytes)); PB_CUDA(cudaMalloc(&pb->Fx, field_bytes)); PB_CUDA(cudaMalloc(&pb->Fy, field_bytes));
   PB_CUDA(cudaMalloc(&pb->wext, wcount * pb->rs));
+  {  // pad columns must hold zeros (they are read by halo loads, never written)
+    void* st[] = {pb->u, pb->Ua, pb->Ub, pb->acc};
+    for (void* p : st) PB_CUDA(cudaMemsetAsync(p, 0, state_bytes, ctx->stream));
+    void* fl[] = {pb->rhosum, pb->Fx, pb->Fy};
+    for (void* p : fl) PB_CUDA(cudaMemsetAsync(p, 0, field_bytes, ctx->stream));
+  }
   PB_CUDA(cudaMalloc((void**)&pb->partials, (size_t)B * pb->nbx * pb->nby * 2 * L * 3 * 8));
   PB_CUDA(cudaMalloc((void**)&pb->counters, (size_t)B * 4));
   PB_CUDA(cudaMalloc((void**)&pb->coef, (size_t)B * sizeof(PdeCoef)));
@@ -705,15 +725,22 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
     const char* ev = getenv("SMM_PDE_CONV");
     const int need = 2 * std::max(grid->Nx, grid->Ny) - 1;
     if (!(ev && strcmp(ev, "direct") == 0) && need <= 2048)
-      PB_TRY(smm_fft_plan_create(ctx, grid->Nx, grid->Ny, grid->dx, grid->dy, B, precision, &pb->fft));
+      PB_TRY(smm_fft_plan_create(ctx, grid->Nx, grid->Ny, pb->Pw, grid->dx, grid->dy, B, precision, &pb->fft));
   }
   // initial state: u (converted to `real`), coef.y/z
   const int ninit = shared_init ? 1 : B;
   {
     void* tmp;
-    PB_TRY(smm_scratch(ctx, S_STAGE, (size_t)ninit * pb->per_inst * 8, &tmp));
-    PB_CUDA(cudaMemcpyAsync(tmp, u0, (size_t)ninit * pb->per_inst * 8, cudaMemcpyHostToDevice, ctx->stream));
-    PB_TRY(smm_launch_convert_f64_to_real(ctx, (const double*)tmp, pb->u, (size_t)ninit * pb->per_inst, precision));
+    PB_TRY(smm_scratch(ctx, S_STAGE, (size_t)ninit * pb->host_per * 8, &tmp));
+    PB_CUDA(cudaMemcpyAsync(tmp, u0, (size_t)ninit * pb->host_per * 8, cudaMemcpyHostToDevice, ctx->stream));
+    {
+      const size_t rows = (size_t)ninit * 2 * L * grid->Ny;
+      const unsigned g = (unsigned)std::min<size_t>((rows * grid->Nx + 255) / 256, (size_t)ctx->sm_count * 16);
+      if (precision == SMM_PREC_F64) pitch_copy_kernel<double, double><<<g, 256, 0, ctx->stream>>>((const double*)tmp, (double*)pb->u, rows, grid->Nx, grid->Nx, pb->Pw);
+      else pitch_copy_kernel<double, float><<<g, 256, 0, ctx->stream>>>((const double*)tmp, (float*)pb->u, rows, grid->Nx, grid->Nx, pb->Pw);
+      ctx->launches++;
+      PB_CUDA(cudaGetLastError());
+    }
     if (shared_init && B > 1) {
       if (precision == SMM_PREC_F64) broadcast_kernel<double><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>((double*)pb->u, pb->per_inst, B);
       else broadcast_kernel<float><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>((float*)pb->u, pb->per_inst, B);
@@ -804,15 +831,15 @@ static int batch_read_ode(smm_ctx* ctx, smm_pde_batch* pb, double* z, double* y,
 }
 
 static int download_state(smm_ctx* ctx, smm_pde_batch* pb, const void* dev, double* host) {
-  const size_t count = (size_t)pb->B * pb->per_inst;
-  const void* src = dev;
-  if (pb->precision != SMM_PREC_F64) {
-    void* tmp;
-    SMM_TRY(smm_scratch(ctx, S_STAGE, count * 8, &tmp));
-    SMM_TRY(smm_launch_convert_real_to_f64(ctx, dev, (double*)tmp, count, pb->precision));
-    src = tmp;
-  }
-  SMM_CUDA(ctx, cudaMemcpyAsync(host, src, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t count = (size_t)pb->B * pb->host_per, rows = (size_t)pb->B * 2 * pb->L * pb->Ny;
+  void* tmp;
+  SMM_TRY(smm_scratch(ctx, S_STAGE, count * 8, &tmp));
+  const unsigned g = (unsigned)std::min<size_t>((count + 255) / 256, (size_t)ctx->sm_count * 16);
+  if (pb->precision == SMM_PREC_F64) pitch_copy_kernel<double, double><<<g, 256, 0, ctx->stream>>>((const double*)dev, (double*)tmp, rows, pb->Nx, pb->Pw, pb->Nx);
+  else pitch_copy_kernel<float, double><<<g, 256, 0, ctx->stream>>>((const float*)dev, (double*)tmp, rows, pb->Nx, pb->Pw, pb->Nx);
+  ctx->launches++;
+  SMM_CUDA(ctx, cudaGetLastError());
+  SMM_CUDA(ctx, cudaMemcpyAsync(host, tmp, count * 8, cudaMemcpyDeviceToHost, ctx->stream));
   return SMM_OK;
 }
 
@@ -827,7 +854,16 @@ extern "C" int smm_pde_batch_read(smm_ctx* ctx, smm_pde_batch* pb, double* u, do
 extern "C" int smm_pde_batch_sum_dev(smm_ctx* ctx, smm_pde_batch* pb, double* sum_u_dev, double* sum_z_dev, double* sum_y_dev) {
   SMM_REQUIRE(ctx, ctx && pb, "smm_pde_batch_sum_dev: NULL argument");
   SMM_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (sum_u_dev) SMM_TRY(smm_launch_ensemble_sum(ctx, pb->u, pb->precision, pb->B, pb->per_inst, sum_u_dev));
+  if (sum_u_dev) {  // sum over the instances in the pitched layout, then drop the pad columns
+    void* tmp;
+    SMM_TRY(smm_scratch(ctx, S_TMP5, pb->per_inst * 8, &tmp));
+    SMM_TRY(smm_launch_ensemble_sum(ctx, pb->u, pb->precision, pb->B, pb->per_inst, (double*)tmp));
+    const size_t rows = (size_t)2 * pb->L * pb->Ny;
+    const unsigned g = (unsigned)std::min<size_t>((rows * pb->Nx + 255) / 256, (size_t)ctx->sm_count * 16);
+    pitch_copy_kernel<double, double><<<g, 256, 0, ctx->stream>>>((const double*)tmp, sum_u_dev, rows, pb->Nx, pb->Pw, pb->Nx);
+    ctx->launches++;
+    SMM_CUDA(ctx, cudaGetLastError());
+  }
   if (sum_z_dev || sum_y_dev) {
     // the ODE unknowns live in PdeCoef (strided); gather on the host (tiny) and upload the sums
     std::vector<double> z((size_t)pb->B * 4), y((size_t)pb->B * 2 * pb->L);
@@ -890,7 +926,7 @@ extern "C" int smm_pde_solve(smm_ctx* ctx, const smm_grid* grid, const smm_param
   smm_pde_batch* pb = nullptr;
   SMM_TRY(smm_pde_batch_create(ctx, grid, q, B, L, precision, controlled_inf, controlled_med, u0, z0, y0, 0, &pb));
   int rc = SMM_OK;
-  const size_t per = pb->per_inst;
+  const size_t per = pb->host_per;
   std::vector<double> ubuf, zbuf((size_t)B * 4), ybuf((size_t)B * 2 * L);
   if (us || sum_us) ubuf.resize((size_t)B * per);
   int done = 0;

@@ -100,6 +100,6 @@ int smm_launch_convert_u8_to_i32(smm_ctx* ctx, const unsigned char* in, int32_t*
 
 // FFT-based Toeplitz correlation for the PDE interaction force (fft_conv.cu)
 struct smm_fft_plan;
-int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, double hx, double hy, int B, int precision, smm_fft_plan** out);
+int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, int Pw, double hx, double hy, int B, int precision, smm_fft_plan** out);
 int smm_fft_conv(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, void* Fx, void* Fy);
 void smm_fft_plan_destroy(smm_fft_plan* p);
