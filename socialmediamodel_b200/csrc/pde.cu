@@ -12,6 +12,7 @@
 //                         influencer/media ODE right-hand sides (:239-265), the rate factors
 //                         (pde.jl:35-47) and advances the ODE unknowns (Float64).
 // Layout in HBM: u[b][j][i][iy][ix] (= Julia u[Nx,Ny,2,L,B], x fastest), rhosum/Fx/Fy[b][iy][ix].
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 #include <string.h>
 
@@ -45,6 +46,9 @@ enum { ACC_NONE = 0, ACC_INIT = 1, ACC_ADD = 2, ACC_FINAL = 3 };
 enum { FIN_INIT = 0, FIN_STAGE = 1 };
 
 struct StageArgs {
+  // TMA descriptors of the stage state U (3-D: x, y, plane*instance) and of Fx / Fy (3-D: x, y, instance)
+  CUtensorMap tmU, tmFx, tmFy;
+  int use_tma;
   int B, L, Nx, Ny, Pw;  // Pw = row pitch in elements (Nx rounded up to a 16-byte multiple: TMA)
   double gx0, gy0, dx, dy;
   const void* U;      // stage state being differentiated
@@ -215,9 +219,40 @@ __device__ void moments_ticket(const StageArgs& A, int b, double* sm, int mode) 
 // (~11 independent loads in flight per thread), then every thread evaluates its grid point for all
 // planes from shared memory.  LT = compile-time L (loops unroll, centres stay in registers);
 // LT = 0 is the runtime-L fallback.
-constexpr int TW = BX + 2, TH = BY + 2;
+constexpr int TW = BX + 8, TH = BY + 2;  // tile row = 40 elements starting at x = bx0-4: a TMA box must start
+                                         // on a 16-byte boundary in global memory and be a 16-byte multiple wide
+constexpr int XO = 4;                    // tile column of the CTA's first grid point
+
+// ---- TMA / mbarrier primitives (sm_90+; SASS: UTMALDG, SYNCS) -------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__host__ __device__ inline size_t align128(size_t b) { return (b + 127) & ~(size_t)127; }
+
 template <typename real, int LT>
-__global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_kernel(StageArgs A) {
+__global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_kernel(const __grid_constant__ StageArgs A) {
   const int L = LT ? LT : A.L;
   const int NP = 2 * L;
   const int Nx = A.Nx, Ny = A.Ny, b = blockIdx.z;
@@ -226,11 +261,13 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
   const int ix = bx0 + tx, iy = by0 + ty;
   const int tid = ty * BX + tx;
   const bool in = ix < Nx && iy < Ny;
-  extern __shared__ __align__(16) unsigned char smem_stage[];
-  real* tile = reinterpret_cast<real*>(smem_stage);   // [NP][TH][TW]
-  real* sFx = tile + (size_t)NP * TH * TW;             // [BY][TW]   a * Fx with x halo
-  real* sFy = sFx + BY * TW;                           // [TH][BX]   a * Fy with y halo
-  real* mom = sFy + TH * BX;                           // [BY][NP][32]
+  extern __shared__ __align__(128) unsigned char smem_stage[];
+  // every TMA destination starts on a 128-byte boundary
+  real* tile = reinterpret_cast<real*>(smem_stage);                                             // [NP][TH][TW]
+  real* sFx = reinterpret_cast<real*>(smem_stage + align128(sizeof(real) * NP * TH * TW));       // [BY][TW]  Fx with x halo
+  real* sFy = reinterpret_cast<real*>(reinterpret_cast<unsigned char*>(sFx) + align128(sizeof(real) * BY * TW));  // [TH][BX]
+  real* mom = reinterpret_cast<real*>(reinterpret_cast<unsigned char*>(sFy) + align128(sizeof(real) * TH * BX));  // [BY][NP][32]
+  __shared__ __align__(8) unsigned long long tma_bar;
   __shared__ double sm[2 * LMAX * 3];
   __shared__ real s_yx[LMAX], s_yy[LMAX], s_R[2][LMAX], s_zx[2], s_zy[2];
   __shared__ real s_par[4];
@@ -244,6 +281,20 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
   const size_t plane = (size_t)Pw * Ny;
   const real* U = static_cast<const real*>(A.U) + (size_t)b * NP * plane;
   // ---- stage the tiles (clamped at the domain edge; the clamped values are never used there)
+  if (A.use_tma) {
+    // One elected thread issues three bulk tensor copies (TMA): the 2L x 10 x 36 density box with its
+    // one-cell halo and the two force boxes.  Out-of-range coordinates (the domain edge) are filled
+    // with zeros by the hardware; those halo values are never used (one-sided boundary formulas).
+    if (tid == 0) mbar_init(&tma_bar, 1);
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(&tma_bar, (unsigned)(sizeof(real) * (NP * TH * TW + BY * TW + TH * BX)));
+      tma_load_3d(tile, &A.tmU, bx0 - XO, by0 - 1, b * NP, &tma_bar);
+      tma_load_3d(sFx, &A.tmFx, bx0 - XO, by0, b, &tma_bar);
+      tma_load_3d(sFy, &A.tmFy, bx0, by0 - 1, b, &tma_bar);
+    }
+    mbar_wait(&tma_bar, 0);
+  } else {
   // Thread (tx,ty) stages tile rows ty (and ty+8 for ty < 2) at columns tx (and tx+32 for tx < 2): the
   // four global offsets are computed once and reused for every plane, and all loads of a batch of
   // planes are issued before their shared-memory stores (the kernel is sensitive to global-load
@@ -254,7 +305,7 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
     const unsigned oaa = (unsigned)gya * Pw + gxa, oab = (unsigned)gya * Pw + gxb;
     const unsigned oba = (unsigned)gyb * Pw + gxa, obb = (unsigned)gyb * Pw + gxb;
     const bool cb = tx < 2, rb = ty < 2;
-    real* t0 = tile + ty * TW + tx;
+    real* t0 = tile + ty * TW + tx + XO - 1;
     constexpr int PBATCH = 4;
     for (int p0 = 0; p0 < NP; p0 += PBATCH) {
       real vaa[PBATCH], vab[PBATCH], vba[PBATCH], vbb[PBATCH];
@@ -280,21 +331,22 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
   }
   __syncthreads();  // s_par visible
   {
-    const real pa0 = s_par[0];
     const real* Fx = static_cast<const real*>(A.Fx) + (size_t)b * plane;
     const real* Fy = static_cast<const real*>(A.Fy) + (size_t)b * plane;
-    for (int e = tid; e < BY * TW; e += BX * BY) {
-      const int yy = e / TW, xx = e - yy * TW;
+    for (int e = tid; e < BY * (BX + 2); e += BX * BY) {
+      const int yy = e / (BX + 2), xx = e - yy * (BX + 2);
       const int gx = min(max(bx0 + xx - 1, 0), Nx - 1), gy = min(by0 + yy, Ny - 1);
-      sFx[e] = pa0 * Fx[(size_t)gy * Pw + gx];
+      sFx[yy * TW + xx + XO - 1] = Fx[(size_t)gy * Pw + gx];
     }
     for (int e = tid; e < TH * BX; e += BX * BY) {
       const int yy = e / BX, xx = e - yy * BX;
       const int gx = min(bx0 + xx, Nx - 1), gy = min(max(by0 + yy - 1, 0), Ny - 1);
-      sFy[e] = pa0 * Fy[(size_t)gy * Pw + gx];
+      sFy[e] = Fy[(size_t)gy * Pw + gx];
     }
   }
   __syncthreads();
+  }
+  const real pa = s_par[0];
   const real pb = s_par[1], pc = s_par[2], D = s_par[3];
   const real h = (real)A.dx, ih = (real)(1.0 / A.dx), ih2 = (real)(1.0 / (A.dx * A.dx));
   const real Ddx = (real)((double)D / A.dx), Ddy = (real)((double)D / A.dy);  // pde.jl:231-234 (Q12)
@@ -302,10 +354,10 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
   const real X = (real)(A.gx0 + cx * A.dx), Y = (real)(A.gy0 + cy * A.dy);
   const real bc = pb + pc;
   // plane-independent parts of the velocity a F + b (y_j - x) + c (z_i - x)   (pde.jl:214)
-  const real vxc0 = sFx[ty * TW + tx + 1] - bc * X, vxm0 = sFx[ty * TW + tx] - bc * (X - h), vxp0 = sFx[ty * TW + tx + 2] - bc * (X + h);
-  const real vyc0 = sFy[(ty + 1) * BX + tx] - bc * Y, vym0 = sFy[ty * BX + tx] - bc * (Y - h), vyp0 = sFy[(ty + 2) * BX + tx] - bc * (Y + h);
+  const real vxc0 = pa * sFx[ty * TW + tx + XO] - bc * X, vxm0 = pa * sFx[ty * TW + tx + XO - 1] - bc * (X - h), vxp0 = pa * sFx[ty * TW + tx + XO + 1] - bc * (X + h);
+  const real vyc0 = pa * sFy[(ty + 1) * BX + tx] - bc * Y, vym0 = pa * sFy[ty * BX + tx] - bc * (Y - h), vyp0 = pa * sFy[(ty + 2) * BX + tx] - bc * (Y + h);
   const bool x_lo = cx == 0, x_hi = cx == Nx - 1, y_lo = cy == 0, y_hi = cy == Ny - 1;
-  const real* tc = tile + (ty + 1) * TW + tx + 1;  // centre of plane 0
+  const real* tc = tile + (ty + 1) * TW + tx + XO;  // centre of plane 0
 
   // per medium: sum of densities and of rates at this grid point (pde.jl:220-225)
   real rsum[2] = {0, 0}, gsum[2] = {0, 0};
@@ -513,6 +565,8 @@ struct smm_pde_batch {
   std::map<std::pair<int, double>, cudaGraphExec_t> graphs;
   int64_t steps_taken;
   smm_fft_plan* fft;  // null = direct Toeplitz kernel
+  CUtensorMap tm_u, tm_ua, tm_ub, tm_fx, tm_fy;  // TMA descriptors (stage kernel tile loads)
+  bool use_tma;
   bool no_graph;      // stream capture unavailable on the caller's stream: launch kernels directly
 };
 
@@ -528,6 +582,8 @@ static void pde_free(smm_pde_batch* pb) {
 static StageArgs base_args(const smm_pde_batch* pb) {
   StageArgs A;
   memset(&A, 0, sizeof A);
+  A.use_tma = pb->use_tma ? 1 : 0;
+  A.tmFx = pb->tm_fx; A.tmFy = pb->tm_fy;
   A.B = pb->B; A.L = pb->L; A.Nx = pb->Nx; A.Ny = pb->Ny; A.Pw = pb->Pw;
   A.gx0 = pb->grid.x0; A.gy0 = pb->grid.y0; A.dx = pb->grid.dx; A.dy = pb->grid.dy;
   A.Fx = pb->Fx; A.Fy = pb->Fy; A.rhosum_out = pb->rhosum;
@@ -562,7 +618,9 @@ static int launch_conv(smm_ctx* ctx, smm_pde_batch* pb) {
   return SMM_OK;
 }
 
-static size_t stage_smem(int L, size_t rs) { return rs * ((size_t)2 * L * TH * TW + BY * TW + TH * BX + (size_t)BY * 2 * L * 32); }
+static size_t stage_smem(int L, size_t rs) {
+  return align128(rs * 2 * L * TH * TW) + align128(rs * BY * TW) + align128(rs * TH * BX) + rs * (size_t)BY * 2 * L * 32;
+}
 
 template <typename real, int LT>
 static int launch_stage_t(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
@@ -617,6 +675,7 @@ static int enqueue_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, int scheme) 
     SMM_TRY(launch_conv(ctx, pb));
     StageArgs A = base_args(pb);
     A.U = st[s].U; A.un = pb->u; A.Uout = st[s].out; A.acc = pb->acc;
+    A.tmU = st[s].U == pb->u ? pb->tm_u : (st[s].U == pb->Ua ? pb->tm_ua : pb->tm_ub);
     A.dt = dt; A.A = st[s].A; A.Bc = st[s].B; A.C = st[s].C; A.bw = st[s].bw; A.acc_mode = st[s].acc;
     A.last_stage = s == ns - 1; A.do_moments = 1;
     SMM_TRY(launch_stage(ctx, pb, A));
@@ -642,6 +701,37 @@ static int fill_inst(smm_ctx* ctx, const smm_params* q, int B, int L, const doub
     for (int i = 0; i < 2; i++) I.cmed[i] = cmed ? (int)cmed[(size_t)b * 2 + i] : 0;
   }
   return SMM_OK;
+}
+
+// ---- TMA descriptors ---------------------------------------------------------------------------
+typedef CUresult (*smm_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static smm_encode_tiled_fn get_encode_tiled() {
+  static smm_encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (smm_encode_tiled_fn)f;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+// 3-D map over a pitched field [nz][Ny][Pw] whose valid x extent is Nx; box = {bx, by, bz}
+static bool make_map3(CUtensorMap* tm, void* base, int precision, int Nx, int Ny, int Pw, size_t nz, int bx, int by, int bz) {
+  smm_encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return false;
+  const size_t rs = precision == SMM_PREC_F64 ? 8 : 4;
+  cuuint64_t dims[3] = {(cuuint64_t)Nx, (cuuint64_t)Ny, (cuuint64_t)nz};
+  cuuint64_t strides[2] = {(cuuint64_t)Pw * rs, (cuuint64_t)Pw * Ny * rs};
+  cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, precision == SMM_PREC_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
 }
 
 #define PB_CUDA(expr)                                                                                   \
@@ -677,6 +767,7 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
   pb->steps_taken = 0;
   pb->fft = nullptr;
   pb->no_graph = false;
+  pb->use_tma = false;
   pb->rs = precision == SMM_PREC_F64 ? 8 : 4;
   pb->Pw = (grid->Nx + 3) & ~3;  // 16-byte row pitch in both precisions (TMA global strides)
   pb->plane = (size_t)pb->Pw * grid->Ny;
@@ -719,6 +810,19 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
   if (pb->conv_smem > 48 * 1024) {
     if (precision == SMM_PREC_F64) PB_CUDA(cudaFuncSetAttribute(pde_conv_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb->conv_smem));
     else PB_CUDA(cudaFuncSetAttribute(pde_conv_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb->conv_smem));
+  }
+  {  // TMA descriptors for the stage kernel's tile loads (SMM_PDE_TMA=0 falls back to LDG staging)
+    const char* ev = getenv("SMM_PDE_TMA");
+    pb->use_tma = !(ev && ev[0] == '0') && 2 * L <= 256;
+    if (pb->use_tma) {
+      const size_t nz = (size_t)2 * L * B;
+      bool ok = make_map3(&pb->tm_u, pb->u, precision, grid->Nx, grid->Ny, pb->Pw, nz, TW, TH, 2 * L) &&
+                make_map3(&pb->tm_ua, pb->Ua, precision, grid->Nx, grid->Ny, pb->Pw, nz, TW, TH, 2 * L) &&
+                make_map3(&pb->tm_ub, pb->Ub, precision, grid->Nx, grid->Ny, pb->Pw, nz, TW, TH, 2 * L) &&
+                make_map3(&pb->tm_fx, pb->Fx, precision, grid->Nx, grid->Ny, pb->Pw, (size_t)B, TW, BY, 1) &&
+                make_map3(&pb->tm_fy, pb->Fy, precision, grid->Nx, grid->Ny, pb->Pw, (size_t)B, BX, TH, 1);
+      if (!ok) pb->use_tma = false;
+    }
   }
   // interaction force: FFT correlation (default), or the direct O(N^2) kernel when SMM_PDE_CONV=direct
   {
@@ -899,6 +1003,7 @@ extern "C" int smm_pde_rhs(smm_ctx* ctx, const smm_grid* grid, const smm_params*
     smm_toc(ctx, SMM_K_CONV);
     StageArgs A = base_args(pb);
     A.U = pb->u; A.un = pb->u; A.Uout = pb->Ua; A.acc = nullptr;
+    A.tmU = pb->tm_u;
     A.dt = 1.0; A.A = 0; A.Bc = 0; A.C = 1.0; A.bw = 0; A.acc_mode = ACC_NONE; A.last_stage = 0; A.do_moments = 0;
     smm_tic(ctx, SMM_K_STENCIL);
     if ((rc = launch_stage(ctx, pb, A)) != SMM_OK) break;
