@@ -37,7 +37,7 @@ def run_pde_c3(ctx, steps=400, dt=1e-3):
     cells = p.N_x * p.N_y * 2 * 4
     return dict(workload="C3 PDEsolve 89x89x2x4, uniforminit, RK4 dt=1e-3, one instance, CUDA graph per step",
                 metric="pde_cell_steps_per_s", value=cells / (us_step * 1e-6), us_per_step=us_step,
-                kernels_per_step=8, mass=float(u.sum() * p.dV), finite=bool(np.isfinite(u).all()),
+                kernels_per_step=16, mass=float(u.sum() * p.dV), finite=bool(np.isfinite(u).all()),
                 note="63 368 cells: launch/latency-bound, not HBM-bound (SURVEY 8d)")
 
 
@@ -59,22 +59,21 @@ def run_pde_sweep(ctx, dx=0.025, B=64, steps=10, dt=None):
     cells = p.N_x * p.N_y * 2 * 4 * B
     peaks = _peaks()
     ach = cells * 76 / (ms_step * 1e-3) / 1e9          # 19 B per cell per RK stage
-    N = p.N_x * p.N_y
-    conv_fma = 3.0 * N * N * B * 4                       # direct Toeplitz: 3 N FMA per grid point per RHS
     return dict(workload=f"C4 sample: {B} PDE instances {p.N_x}x{p.N_y}x2x4, parameter lattice, RK4 dt={dt:.2e}",
                 metric="pde_cell_steps_per_s", value=cells / (ms_step * 1e-3), ms_per_step=ms_step,
                 finite=bool(np.isfinite(y).all()),
-                roofline=dict(kernel="pde_stage_kernel<float> + pde_conv_kernel<float>", bound="hbm", achieved=ach,
+                roofline=dict(kernel="pde_stage_kernel<float,4> + fft_{rows_fwd,cols,rows_inv}<float>", bound="hbm", achieved=ach,
                               peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"], traffic=None,
                               bytes_per_cell_step=76, peak_source=peaks["source"],
-                              conv_tfma_per_s=conv_fma / (ms_step * 1e-3) / 1e12,
-                              note="step time includes the direct Toeplitz convolution (FP32-pipe-bound, 37.2 TFMA/s peak)"))
+                              note="whole RK4 step: 4 x (3 FFT kernels for the interaction force + fused stage kernel); "
+                                   "76 B/cell-step counts the stencil/RK traffic only (SURVEY 8d)"))
 
 
 def run_pde_workloads(ctx):
     out = {}
     for name, fn in (("pde_C3", lambda: run_pde_c3(ctx)),
-                     ("pde_sweep_177", lambda: run_pde_sweep(ctx, dx=0.025, B=16, steps=4))):
+                     ("pde_sweep_177", lambda: run_pde_sweep(ctx, dx=0.025, B=16, steps=4)),
+                     ("pde_C4_shard_353", lambda: run_pde_sweep(ctx, dx=0.0125, B=64, steps=3))):
         try:
             out[name] = fn()
         except Exception as e:

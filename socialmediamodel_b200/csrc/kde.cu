@@ -163,8 +163,23 @@ int smm_launch_ensemble_sum(smm_ctx* ctx, const void* us, int precision, int R, 
   return SMM_OK;
 }
 
+// few outputs, many realizations (ys / zs sums): one CTA per output element, fixed-order tree reduction
+__global__ void small_sum_kernel(const double* __restrict__ v, int R, int per_real, double* __restrict__ out) {
+  __shared__ double sh[256];
+  const int e = blockIdx.x;
+  double acc = 0.0;
+  for (int r = threadIdx.x; r < R; r += 256) acc += v[(size_t)r * per_real + e];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[e] = sh[0];
+}
+
 int smm_launch_small_sum(smm_ctx* ctx, const double* v, int R, int per_real, double* out) {
-  ensemble_sum_kernel<double><<<(per_real + 255) / 256, 256, 0, ctx->stream>>>(v, R, (size_t)per_real, out, 0);
+  small_sum_kernel<<<per_real, 256, 0, ctx->stream>>>(v, R, per_real, out);
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;
