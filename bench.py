@@ -287,6 +287,29 @@ def run_abm_pop(args, ctx, n=10_000_000, L=64, k=16, steps=20, warmup=3):
                               peak_source=peaks["source"]))
 
 
+def run_abm_c1(ctx):
+    """C1: ABMsolve() -- one realization, default paper parameters (n=250, L=4, M=2, NT=100), full history
+    returned through the reference-shaped API; the oracle port of the same call timed beside it."""
+    import socialmediamodel_b200 as smm
+    from oracle import abm_oracle as A
+    smm.ABMsolve(100, chosenseed=0, ctx=ctx)
+    t0 = time.perf_counter()
+    reps = 20
+    for k in range(reps):
+        xs, stateinfs, infs, meds, state, _ = smm.ABMsolve(100, chosenseed=k, ctx=ctx)
+    gpu_ms = (time.perf_counter() - t0) / reps * 1e3
+    rng = np.random.default_rng(0)
+    x0 = rng.uniform(-2.2, 2.2, (250, 2)); st = np.where(rng.random(250) > 0.5, 1, -1)
+    f0, i0, m0 = A.abm_init(x0)
+    t0 = time.perf_counter()
+    A.abm_solve(100, x0, st, f0, i0, m0, rng.standard_normal((100, 250, 2)), rng.random((100, 250)), rng.random((100, 250)),
+                A.default_p(), A.default_q())
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    return dict(workload="C1 ABMsolve(): 1 realization, n=250, L=4, M=2, NT=100, full history (host API, Float64 out)",
+                metric="abm_agent_steps_per_s", value=250 * 100 / (gpu_ms * 1e-3), ms_per_call=gpu_ms,
+                cpu_port_ms_per_call=cpu_ms, note="single CTA: latency-bound by design; ensembles are the throughput path")
+
+
 # ------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle (port of the reference algorithm) on host cores
 # ------------------------------------------------------------------------------------------
@@ -367,7 +390,7 @@ def main():
     res, ctx = run_abm_ensemble(args, rank, world, local)
     if rank == 0 and world == 1 and not args.no_extra:
         extra = {}
-        for name, fn in (("abm_population_C5", lambda: run_abm_pop(args, ctx)),):
+        for name, fn in (("abm_C1", lambda: run_abm_c1(ctx)), ("abm_population_C5", lambda: run_abm_pop(args, ctx))):
             try:
                 extra[name] = fn()
             except Exception as e:  # a secondary workload must not lose the headline line

@@ -1,5 +1,8 @@
 """FP32 vs Float64 trajectory drift of the PDE path over long horizons (hard part 5 of SURVEY section 7)."""
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 

@@ -1,5 +1,8 @@
 """Small fixed workloads for ncu captures: python tools_profile.py {pde_c3|pde_sweep|pop|kde}"""
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 
