@@ -16,6 +16,9 @@ import numpy as np
 from .abm_oracle import default_q, julia_range  # noqa: F401  (re-exported)
 
 
+AT_TARGET = 1e-12  # distance below which a controlled influencer/medium counts as arrived
+
+
 def julia_round(v):
     """Julia ``round`` = ties-to-even (setting.jl:51-52, pde.jl:97-99); np.round agrees."""
     return int(np.round(v))
@@ -236,12 +239,13 @@ def rhs(u, z, y, p, q, controlled_inf=None, controlled_med=None, force="toeplitz
             tgt = np.ravel(q["controltarget1"] if ci == 1 else q["controltarget2"])
             spd = q["controlspeed1"] if ci == 1 else q["controlspeed2"]
             nrm = np.linalg.norm(tgt - y[:, j])
-            dyv[:, j] = spd * (tgt - y[:, j]) / nrm if nrm > 0 else 0.0
+            # pde.jl:244,250 test `> 0`; AT_TARGET guards the rounding-decided case at arrival (see pde.cu)
+            dyv[:, j] = spd * (tgt - y[:, j]) / nrm if nrm > AT_TARGET else 0.0
     for i in range(2):                                             # pde.jl:256-265
         if controlled_med[i] == 1:
             tgt = np.ravel(q["controltarget1"])
             nrm = np.linalg.norm(tgt - z[:, i])
-            dz[:, i] = q["controlspeed1"] * (tgt - z[:, i]) / nrm if nrm > 0 else 0.0
+            dz[:, i] = q["controlspeed1"] * (tgt - z[:, i]) / nrm if nrm > AT_TARGET else 0.0
         else:
             ri = u[:, :, i, :].sum(axis=2)
             mean = 1 / m_i[i] * dV * np.array([(ri * X).sum(), (ri * Y).sum()])

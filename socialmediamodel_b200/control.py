@@ -1,0 +1,147 @@
+"""Control layer of the reference as a caller of the GPU right-hand side (src/controlstrategies.jl:5-132;
+SURVEY section 8(f) "next" #1): prep, PDEsolvefixedtargetsfast, PDEsolvefixedtargets.
+
+The optimiser (NLopt COBYLA/MLSL, controlstrategies.jl:137-209) is out of scope; what it evaluates -- the
+objective (follower share integrated over time, L2 norm of the control speed) for given targets -- is here,
+and ``fixedtargets_objectives`` evaluates many candidate strategies at once as ONE device-resident batch
+(the ensemble axis of smm_pde_solve), which is what a multistart search needs.
+
+Time integration: the reference uses the adaptive default solver with dtmin (controlstrategies.jl:10,96); here
+the fixed-step RK4 graph with a step that divides ``savedt``.  Reference quirks kept: with
+countercontrol="no" the added influencer carries flag 3 and therefore moves towards controltarget2 at
+controlspeed2 (pde.jl:249-255), not towards ``targets`` (controlstrategies.jl:16,92).
+"""
+import numpy as np
+
+from .pde import ArrayPartition, PDESolution, constructinitial, default_dt, pde_solve_raw
+from .setting import PDEconstruct, PDEconstructcoarse, parameterscontrol, parametersstronginf
+
+
+def _segment_steps(T, savedt, dt):
+    nsave = int(round(T / savedt))
+    assert abs(nsave * savedt - T) < 1e-9 * max(1.0, T), "segment length must be a multiple of savedt"
+    per = max(1, int(np.ceil(savedt / dt - 1e-9)))
+    return nsave, per, savedt / per
+
+
+def _solve_segments(p, qs, u0, z0, y0, T, savedt, dt, precision, ctx):
+    """integrate B instances over [0,T], saving every savedt (both ends, like saveat=0:savedt:T)."""
+    nsave, per, h = _segment_steps(T, savedt, dt)
+    savesteps = (np.arange(nsave + 1) * per).astype(np.int32)
+    out = pde_solve_raw(p, qs, u0, z0, y0, dt=h, nsteps=nsave * per, savesteps=savesteps, precision=precision, ctx=ctx)
+    return out, savesteps * h
+
+
+def prep(tequil=5.0, *, p=None, q=None, r=None, init="uniform", savedt=0.05, dtmin=0.001, countercontrol="no",
+         returnsol=False, dt=None, precision="f32", ctx=None):
+    """controlstrategies.jl:5-63: equilibrate for tequil, then append the controlled influencer(s)."""
+    p = PDEconstruct() if p is None else p
+    q = parametersstronginf() if q is None else q
+    r = parameterscontrol() if r is None else r
+    uzy0, q1 = constructinitial(init, (p, q))
+    dt = default_dt(p, q1) if dt is None else dt
+    out, ts = _solve_segments(p, [q1], *uzy0.x, tequil, savedt, dt, precision, ctx)
+    sol1 = PDESolution(ts, [ArrayPartition(out["us"][..., m, 0], out["zs"][..., m, 0], out["ys"][..., m, 0]) for m in range(len(ts))])
+    u, z, y = sol1.u[-1].x
+    Lold = q1.L
+    ci = list(np.asarray(q1.controlled_inf, float))
+    if countercontrol == "no":
+        q2 = q1.merge(L=Lold + 1, controlled_inf=np.array(ci + [3.0]))
+    elif countercontrol == "inf":
+        q2 = q1.merge(L=Lold + 2, controlled_inf=np.array(ci + [1.0, 3.0]))
+    elif countercontrol == "med":
+        q2 = q1.merge(L=Lold + 1, controlled_inf=np.array(ci + [3.0]), controlled_med=np.array([0.0, 1.0]))
+    else:
+        raise ValueError(f"unknown countercontrol {countercontrol!r}")
+    L = q2.L
+    u2 = np.zeros((p.N_x, p.N_y, 2, L), order="F")
+    u2[:, :, :, :Lold] = u
+    if r.start == "influencer":
+        startlocation = y[:, 0].reshape(1, 2).copy()
+    elif r.start == "zero":
+        startlocation = np.zeros((1, 2))
+    elif r.start == "mean":   # mean opinion of the agents of medium 2 (controlstrategies.jl:36)
+        w = u2[:, :, 1, :].sum(axis=2)
+        startlocation = (np.array([(w * p.X).sum(), (w * p.Y).sum()]) / u2[:, :, 1, :].sum()).reshape(1, 2)
+    else:
+        raise ValueError(f"unknown start {r.start!r}")
+    y2 = np.zeros((2, L), order="F")
+    y2[:, :Lold] = y
+    y2[:, Lold:] = startlocation.reshape(2, 1)
+    startlocationmed = z[:, 1].reshape(1, 2).copy() if countercontrol == "med" else None
+    uzy = ArrayPartition(u2, np.asfortranarray(z), y2)
+    if not returnsol:
+        return uzy, startlocation, (p, q2), startlocationmed
+    return uzy, startlocation, (p, q2), startlocationmed, sol1, (p, q1)
+
+
+def fixedtargets_objectives(ts, targets_list, startlocation, pq, r, uzy0, *, savedt=0.05, dtmin=0.001, countercontrol="no",
+                            stubborntarget=None, startlocationmed=None, returnsol=False, dt=None, precision="f32", ctx=None):
+    """PDEsolvefixedtargetsfast (controlstrategies.jl:67-115) for K candidate strategies at once: targets_list[k]
+    is a (2, n_targets) array.  Returns followersum[K], speedpenalty[K] (and the per-candidate sols/Ps)."""
+    p, q = pq
+    K = len(targets_list)
+    ts = np.ravel(np.asarray(ts, float))
+    L = q.L
+    if countercontrol != "no":
+        stub = np.asarray(stubborntarget, float).reshape(1, 2)
+        q = q.merge(controltarget2=stub, controlspeed2=float(np.linalg.norm(stub - startlocation) / ts[-1]))
+    start = [np.asarray(startlocationmed if countercontrol == "med" else startlocation, float).reshape(1, 2)] * K
+    targets_list = [np.asarray(t, float).reshape(2, -1) for t in targets_list]
+    n_targets = targets_list[0].shape[1]
+    dt = default_dt(p, q) if dt is None else dt
+    followersum = np.zeros(K); speedpen = np.zeros(K)
+    u = np.stack([uzy0.x[0]] * K, axis=-1); z = np.stack([uzy0.x[1]] * K, axis=-1); y = np.stack([uzy0.x[2]] * K, axis=-1)
+    sols = [[] for _ in range(K)]; Ps = [[] for _ in range(K)]
+    for n in range(n_targets):
+        Dt = ts[n + 1] - ts[n]
+        qs = []
+        for k in range(K):
+            target = targets_list[k][:, n].reshape(1, 2)
+            speed = float(np.linalg.norm(target - start[k]) / Dt)
+            qs.append(q.merge(controltarget1=target, controlspeed1=speed))
+            speedpen[k] += speed ** 2 * Dt
+            start[k] = target
+        out, tsave = _solve_segments(p, qs, u, z, y, Dt, savedt, dt, precision, ctx)
+        us = out["us"]                                                       # [Nx,Ny,2,L,nsave,K]
+        share = us[:, :, :, L - 1].sum(axis=(0, 1, 2)) / us.sum(axis=(0, 1, 2, 3))   # [nsave, K]
+        followersum += share.sum(axis=0) * savedt                            # controlstrategies.jl:98
+        u, z, y = us[..., -1, :], out["zs"][..., -1, :], out["ys"][..., -1, :]
+        if returnsol:
+            for k in range(K):
+                sols[k].append(PDESolution(tsave, [ArrayPartition(us[..., m, k], out["zs"][..., m, k], out["ys"][..., m, k])
+                                                   for m in range(len(tsave))]))
+                Ps[k].append((p, qs[k]))
+    speedpen = np.sqrt(speedpen)
+    return (followersum, speedpen, sols, Ps) if returnsol else (followersum, speedpen)
+
+
+def PDEsolvefixedtargetsfast(ts, targets, startlocation, pq, r, uzy0, *, savedt=0.05, atol=1e-6, rtol=1e-3, dtmin=0.001,
+                             countercontrol="no", stubborntarget=None, startlocationmed=None, returnsol=False, dt=None,
+                             precision="f32", ctx=None):
+    """controlstrategies.jl:67-115 (atol/rtol accepted and ignored: fixed-step integration)."""
+    res = fixedtargets_objectives(ts, [targets], startlocation, pq, r, uzy0, savedt=savedt, dtmin=dtmin,
+                                  countercontrol=countercontrol, stubborntarget=stubborntarget,
+                                  startlocationmed=startlocationmed, returnsol=returnsol, dt=dt, precision=precision, ctx=ctx)
+    if returnsol:
+        return float(res[0][0]), float(res[1][0]), res[2][0], res[3][0]
+    return float(res[0][0]), float(res[1][0])
+
+
+def PDEsolvefixedtargets(targets, *, p=None, q=None, r=None, init="uniform", countercontrol="no", stubborntarget=(1.5, 1.5),
+                         savedt=0.05, dt=None, precision="f32", ctx=None):
+    """controlstrategies.jl:120-132."""
+    p = PDEconstructcoarse() if p is None else p
+    q = parametersstronginf() if q is None else q
+    r = parameterscontrol(ntarg=1, start="zero") if r is None else r
+    ntarg, Tmax, tequil = r.ntarg, r.Tmax, r.tequil
+    ts = np.concatenate([[0.0], Tmax / ntarg * np.arange(1, ntarg + 1)])
+    targets = np.asarray(targets, float).reshape((2, ntarg), order="F")
+    uzy0, startlocation, (p, q2), slm, sol1, (p, q1) = prep(tequil, p=p, q=q, r=r, init=init, savedt=savedt,
+                                                            countercontrol=countercontrol, returnsol=True, dt=dt,
+                                                            precision=precision, ctx=ctx)
+    fs, sp, sols, Ps = PDEsolvefixedtargetsfast(ts, targets, startlocation, (p, q2), r, uzy0, savedt=savedt,
+                                                countercontrol=countercontrol,
+                                                stubborntarget=np.asarray(stubborntarget, float).reshape(1, 2),
+                                                startlocationmed=slm, returnsol=True, dt=dt, precision=precision, ctx=ctx)
+    return fs, sp, [sol1] + sols, [(p, q1)] + Ps

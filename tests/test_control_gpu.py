@@ -1,0 +1,64 @@
+"""The control layer as a caller of the GPU right-hand side (controlstrategies.jl:5-132):
+parity of prep / PDEsolvefixedtargetsfast / PDEsolvefixedtargets against the oracle restatement running the
+same fixed-step RK4, for the three countercontrol modes, and batched evaluation of candidate strategies."""
+import numpy as np
+import pytest
+
+import socialmediamodel_b200 as smm
+from oracle import abm_oracle as A
+from oracle import control_oracle as CO
+from oracle import pde_oracle as P
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("cc,start", [("no", "zero"), ("inf", "influencer"), ("med", "mean")])
+def test_fixed_targets_parity(cc, start):
+    p = smm.PDEconstructcoarse()
+    po = P.pde_construct_coarse()
+    q = smm.parametersstronginf()
+    qo = A.default_q(eta=1.0)
+    r = smm.parameterscontrol(ntarg=2, start=start, Tmax=0.04, tequil=0.02)
+    targets = np.array([[0.3, 0.3], [-0.5, 0.8]]).T                      # (2, ntarg)
+    fs, sp, sols, Ps = smm.PDEsolvefixedtargets(targets.reshape(-1, order="F"), p=p, q=q, r=r, countercontrol=cc,
+                                                stubborntarget=[1.5, 1.5], savedt=0.01, dt=1e-3, precision="f64")
+    uzy0, sl, q2, ci2, cm2, slm = CO.prep(0.02, po, qo, start=start, savedt=0.01, dt=1e-3, countercontrol=cc)
+    ts = np.array([0.0, 0.02, 0.04])
+    fr, pr, (ur, zr, yr) = CO.fixedtargets(ts, targets, sl, po, q2, ci2, cm2, uzy0, savedt=0.01, dt=1e-3, countercontrol=cc,
+                                           stubborntarget=np.array([1.5, 1.5]), startlocationmed=slm)
+    assert abs(fs - fr) < 1e-10 * max(1.0, abs(fr)) + 1e-12
+    assert abs(sp - pr) < 1e-12
+    uf, zf, yf = sols[-1](0.02).x
+    assert np.abs(uf - ur).max() / np.abs(ur).max() < 1e-10
+    np.testing.assert_allclose(yf, yr, atol=1e-11)
+    np.testing.assert_allclose(zf, zr, atol=1e-11)
+    assert len(sols) == 3 and Ps[1][1].L == (6 if cc == "inf" else 5)
+    # the controlled entities move to their targets (pde.jl:243-261) -- up to one RK4 step of travel: the last
+    # stage of the arriving step lands exactly on the target, where the reference defines the velocity as 0
+    step_travel = np.linalg.norm(targets[:, 1] - targets[:, 0]) / 0.02 * 1e-3
+    if cc == "inf":
+        assert np.linalg.norm(yf[:, 4] - targets[:, 1]) < step_travel             # flag 1 -> the last target
+    if cc == "med":
+        assert np.linalg.norm(zf[:, 1] - targets[:, 1]) < step_travel             # controlled medium
+    # FP32 run of the same evaluation stays within the north-star tolerance
+    fs32, sp32, sols32, _ = smm.PDEsolvefixedtargets(targets.reshape(-1, order="F"), p=p, q=q, r=r, countercontrol=cc,
+                                                     stubborntarget=[1.5, 1.5], savedt=0.01, dt=1e-3, precision="f32")
+    assert abs(fs32 - fr) < 1e-5 * max(abs(fr), 1e-3) + 1e-9
+    assert np.abs(sols32[-1](0.02).x[0] - ur).max() / np.abs(ur).max() < 1e-5
+
+
+def test_batched_candidate_strategies_equal_single_evaluations():
+    """K candidate target sets evaluated as one device batch == K separate evaluations."""
+    p = smm.PDEconstructcoarse()
+    q = smm.parametersstronginf()
+    r = smm.parameterscontrol(ntarg=2, start="zero", Tmax=0.04, tequil=0.02)
+    uzy0, sl, (p, q2), slm = smm.prep(0.02, p=p, q=q, r=r, savedt=0.01, dt=1e-3, countercontrol="inf", precision="f64")
+    ts = [0.0, 0.02, 0.04]
+    cands = [np.array([[0.3, 0.3], [-0.5, 0.8]]).T, np.array([[1.0, -1.0], [0.0, 0.0]]).T, np.array([[-1.5, 1.5], [1.5, 1.5]]).T]
+    fb, pb = smm.fixedtargets_objectives(ts, cands, sl, (p, q2), r, uzy0, savedt=0.01, dt=1e-3, countercontrol="inf",
+                                         stubborntarget=[1.5, 1.5], precision="f64")
+    for k, c in enumerate(cands):
+        f1, p1 = smm.PDEsolvefixedtargetsfast(ts, c, sl, (p, q2), r, uzy0, savedt=0.01, dt=1e-3, countercontrol="inf",
+                                              stubborntarget=[1.5, 1.5], precision="f64")
+        assert abs(fb[k] - f1) < 1e-13 and abs(pb[k] - p1) < 1e-13
+    assert len(set(np.round(fb, 12))) == 3                                 # different strategies, different objectives
