@@ -205,7 +205,10 @@ def run_abm_ensemble(args, rank, world, local):
     barrier(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
     e2e_value = world * R * NT * n * e2e_steps / e2e_s
-    d2h = out_us.nbytes + zs.nbytes + ys.nbytes + s_us.nbytes + s_zs.nbytes + s_ys.nbytes
+    # the per-realization densities cross PCIe as FP32 and are widened into the Float64 host array by the
+    # library's host threads (csrc/host_widen.cpp); everything else is copied as Float64
+    widen = os.environ.get("SMM_HOST_WIDEN", "1") != "0"
+    d2h = (out_us.nbytes // 2 if widen else out_us.nbytes) + zs.nbytes + ys.nbytes + s_us.nbytes + s_zs.nbytes + s_ys.nbytes
     h2d = C.sizeof(_lib.smm_params) + C.sizeof(_lib.smm_grid) + savesteps.nbytes
     mean_check = float(s_us.sum() * p.dV / (R * sp))
     ctx.free_pinned(out_us)
@@ -233,7 +236,10 @@ def run_abm_ensemble(args, rank, world, local):
                            l2="flushed between timed passes (256 MiB write); working set is shared memory"),
                e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                         ms_per_step=e2e_s / e2e_steps * 1e3, steps=e2e_steps,
-                        api="smm_abm_ensemble (host buffers; us/zs/ys + ensemble sums copied back as Float64)"),
+                        host_bytes_written_per_step=out_us.nbytes + zs.nbytes + ys.nbytes + s_us.nbytes + s_zs.nbytes + s_ys.nbytes,
+                        api="smm_abm_ensemble (host buffers; us/zs/ys + ensemble sums returned as Float64; "
+                            "us crosses PCIe as FP32 and is widened by host threads)" if widen else
+                            "smm_abm_ensemble (host buffers; us/zs/ys + ensemble sums copied back as Float64)"),
                gpu_launches=launches, clocks=clocks, roofline=roofline, roofline_kde=roofline_kde,
                wall_ms_per_step=t_wall / args.steps * 1e3, ensemble_mass_check=mean_check)
     return res, ctx

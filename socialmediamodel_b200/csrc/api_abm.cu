@@ -5,7 +5,9 @@
 
 #include <algorithm>
 
+#include <vector>
 #include "smm_internal.h"
+#include "host_widen.h"
 
 std::string g_smm_last_error;
 
@@ -76,6 +78,9 @@ extern "C" int smm_ctx_destroy(smm_ctx* ctx) {
     if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
   }
   for (int i = 0; i < 2; i++) { if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]); if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); }
+  for (int i = 0; i < 2; i++) if (ctx->ev_h[i]) cudaEventDestroy(ctx->ev_h[i]);
+  if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
+  smm_hostpool_destroy(ctx->hostpool);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -502,9 +507,55 @@ extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t preci
   }
   if (numbers) SMM_TRY(smm_scratch(ctx, S_NUMBERS, (size_t)(NT + 1) * L * M * 8, &d_numbers));
   if (sum_us && nsave) SMM_TRY(smm_scratch(ctx, S_SUMUS, per_real * 8, &d_sum_us));
+  // FP32 mode: the chunks cross PCIe as FP32 (half the bytes) into a pinned ring and host threads widen
+  // them into `us` (host_widen.cpp); each chunk is copied in kSub units so that DMA and widening overlap.
+  const char* hw_env = getenv("SMM_HOST_WIDEN");
+  const bool host_widen = nchunks > 1 && precision == SMM_PREC_F32 && !(hw_env && hw_env[0] == '0');
+  int kSub = 2;
+  if (const char* e = getenv("SMM_HOST_WIDEN_SUB")) kSub = std::max(1, atoi(e));
+  const size_t unit_real = ((size_t)Rc0 + kSub - 1) / kSub;  // realizations per copy unit
+  if (host_widen) {
+    if (!ctx->hostpool) ctx->hostpool = smm_hostpool_create(0);
+    for (int i = 0; i < 2; i++)
+      if (!ctx->ev_h[i]) SMM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_h[i], cudaEventDisableTiming));
+    const size_t need = 2 * unit_real * per_real * 4;
+    if (ctx->h_ring_bytes < need) {
+      if (ctx->h_ring) { SMM_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream)); SMM_CUDA(ctx, cudaFreeHost(ctx->h_ring)); ctx->h_ring = nullptr; ctx->h_ring_bytes = 0; }
+      SMM_CUDA(ctx, cudaHostAlloc(&ctx->h_ring, need, cudaHostAllocDefault));
+      ctx->h_ring_bytes = need;
+    }
+  }
   struct Pending { int chunk; size_t r0, rc; };
   Pending pending = {-1, 0, 0};
   void* stage[2] = {nullptr, nullptr};
+  // copy units of the host-widen pipeline: unit g covers realizations [g_r0, g_r0 + g_rc) of chunk g / kSub
+  struct Unit { int chunk; size_t r0, rc; bool last_of_chunk; };
+  std::vector<Unit> units;
+  size_t issued = 0, widened = 0;
+  auto issue_unit = [&](size_t g) -> int {
+    const Unit& u = units[g];
+    const int sl = u.chunk & 1, hs = (int)(g & 1);
+    float* h = (float*)ctx->h_ring + (size_t)hs * unit_real * per_real;
+    const float* d = (const float*)stage[sl] + (u.r0 - (size_t)u.chunk * Rc0) * per_real;
+    SMM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[sl], 0));
+    SMM_CUDA(ctx, cudaMemcpyAsync(h, d, u.rc * per_real * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    SMM_CUDA(ctx, cudaEventRecord(ctx->ev_h[hs], ctx->copy_stream));
+    if (u.last_of_chunk) SMM_CUDA(ctx, cudaEventRecord(ctx->ev_copied[sl], ctx->copy_stream));
+    return SMM_OK;
+  };
+  // widen every unit below `drain_end`; copies may run ahead into units below `issuable_end`
+  auto pump = [&](size_t drain_end, size_t issuable_end) -> int {
+    while (widened < drain_end) {
+      while (issued < std::min(issuable_end, widened + 2)) SMM_TRY(issue_unit(issued++));
+      const int hs = (int)(widened & 1);
+      SMM_CUDA(ctx, cudaEventSynchronize(ctx->ev_h[hs]));
+      const Unit& u = units[widened];
+      smm_hostpool_widen(ctx->hostpool, (const float*)ctx->h_ring + (size_t)hs * unit_real * per_real,
+                         us + u.r0 * per_real, u.rc * per_real);
+      widened++;
+    }
+    return SMM_OK;
+  };
   auto issue_copy = [&](const Pending& pc) -> int {  // D2H of a converted chunk on the copy stream
     const int sl = pc.chunk & 1;
     SMM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[sl], 0));
@@ -543,6 +594,17 @@ extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t preci
     if (us && nsave) {
       if (nchunks == 1) {
         SMM_TRY(download_real(ctx, E.d_us, rc * per_real, precision, us));
+      } else if (host_widen) {
+        const int sl = c & 1;
+        SMM_TRY(smm_scratch(ctx, sl ? S_STAGE_B : S_STAGE_A, (size_t)Rc0 * per_real * 4, &stage[sl]));
+        if (c >= 2) SMM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[sl], 0));  // staging slot free again
+        SMM_CUDA(ctx, cudaMemcpyAsync(stage[sl], E.d_us, rc * per_real * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        SMM_CUDA(ctx, cudaEventRecord(ctx->ev_ready[sl], ctx->stream));
+        const size_t drain_end = units.size();  // everything of the chunks before this one
+        for (size_t o = 0; o < rc; o += unit_real)
+          units.push_back({c, r0 + o, std::min(unit_real, rc - o), o + unit_real >= rc});
+        // this chunk's kernels are queued: drain the previous chunk while they run
+        SMM_TRY(pump(drain_end, units.size()));
       } else {
         const int sl = c & 1;
         SMM_TRY(smm_scratch(ctx, sl ? S_STAGE_B : S_STAGE_A, (size_t)Rc0 * per_real * 8, &stage[sl]));
@@ -557,6 +619,7 @@ extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t preci
     }
   }
   if (pending.chunk >= 0) SMM_TRY(issue_copy(pending));
+  if (host_widen) SMM_TRY(pump(units.size(), units.size()));
   void* p;
   if (sum_us && nsave) SMM_TRY(download(ctx, d_sum_us, per_real * 8, sum_us));
   if (sum_zs && nsave) {

@@ -31,6 +31,11 @@ struct smm_ctx {
   size_t pinned_bytes = 0;
   cudaStream_t copy_stream = nullptr;  // device->host copies overlapped with compute (chunked ensembles)
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+  // FP32 outputs widened to Float64 by host threads (host_widen.cpp): pinned ring + its events
+  struct smm_hostpool* hostpool = nullptr;
+  void* h_ring = nullptr;
+  size_t h_ring_bytes = 0;
+  cudaEvent_t ev_h[2] = {nullptr, nullptr};
 };
 
 extern std::string g_smm_last_error;

@@ -308,6 +308,16 @@ def test_abm_ensemble_chunked_copy_pipeline():
     assert out["numbers"].sum(axis=(0, 1)).tolist() == [R * 24] * (NT + 1)
     pinned = smm.abm_ensemble_raw(NT, R, p=p, q=q, savesteps=st, first_realization=1, seed=3, precision="f32", pinned=True)
     np.testing.assert_array_equal(pinned["us"], out["us"])
+    # the same through the older pipeline (Float64 conversion on the device, twice the PCIe bytes)
+    import os
+    os.environ["SMM_HOST_WIDEN"] = "0"
+    try:
+        dev = smm.abm_ensemble_raw(NT, R, p=p, q=q, savesteps=st, first_realization=1, seed=3, precision="f32")
+    finally:
+        del os.environ["SMM_HOST_WIDEN"]
+    np.testing.assert_array_equal(dev["us"], out["us"])
+    f64 = smm.abm_ensemble_raw(NT, R, p=p, q=q, savesteps=st, first_realization=1, seed=3, precision="f64", want=("us",))
+    assert np.abs(f64["us"] - out["us"]).max() <= 1e-5 * f64["us"].max()
 
 
 @pytest.mark.parametrize("name", ["abm_dense_n60.npz", "abm_csr_n80.npz"])
