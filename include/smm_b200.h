@@ -230,6 +230,38 @@ int smm_pde_batch_read(smm_ctx* ctx, smm_pde_batch* pb, double* u, double* z, do
 int smm_pde_batch_sum_dev(smm_ctx* ctx, smm_pde_batch* pb, double* sum_u_dev, double* sum_z_dev, double* sum_y_dev);
 int smm_pde_batch_destroy(smm_ctx* ctx, smm_pde_batch* pb);
 
+/* Adaptive time integration with per-instance step-size control — the semantics of the reference's
+ * DifferentialEquations.solve calls (pde.jl:291; controlstrategies.jl:10,96: abstol, reltol, dtmin,
+ * force_dtmin, saveat) on an explicit embedded Runge-Kutta 3(2) pair (the 3-stage 3rd-order
+ * Bogacki-Shampine scheme c = (0, 1/2, 3/4), b = (2/9, 1/3, 4/9), with the 2nd-order midpoint solution
+ * b* = (0, 1, 0) as error estimator).  Every instance carries its own clock and step size on the device:
+ * err = dt * sum_i (b_i - b*_i) k_i, norm = sqrt(mean((err / (abstol + reltol * max(|u_n|, |u_n+1|)))^2))
+ * over all density values and ODE unknowns, accept if norm <= 1, next dt = dt * clamp(0.9 norm^(-1/3), 0.2, 5);
+ * steps are shortened to land exactly on the requested output times. */
+typedef struct {
+  double abstol, reltol;   /* DifferentialEquations defaults: 1e-6, 1e-3 */
+  double dt0;              /* first trial step; <= 0: 0.1 dx^2 / D */
+  double dtmin;            /* smallest step (0 = none) */
+  double dtmax;            /* largest step (<= 0 = none) */
+  int32_t force_dtmin;     /* != 0: a step of size dtmin is accepted whatever its error (force_dtmin = true);
+                              0: the call fails with SMM_ERR_UNSUPPORTED when the error test fails at dtmin */
+  int32_t max_attempts;    /* per call and instance (<= 0: 1 000 000) */
+} smm_adapt;
+
+/* Advance every instance of the batch from the batch clock (0 at creation; smm_pde_batch_step advances it by
+ * nsteps * dt) to t_end.  Optional outputs per instance [B]: accepted / rejected step counts of this call and
+ * the step size the controller proposes next. */
+int smm_pde_batch_advance(smm_ctx* ctx, smm_pde_batch* pb, double t_end, const smm_adapt* opt,
+                          int64_t* naccept, int64_t* nreject, double* dt_next);
+
+/* PDEsolve with the adaptive integrator: states recorded at savetimes[nsave] (ascending, >= 0; 0 = the
+ * initial state, save_start = true).  Outputs as in smm_pde_solve; naccept / nreject [B] may be NULL. */
+int smm_pde_solve_adaptive(smm_ctx* ctx, const smm_grid* grid, const smm_params* q, int32_t B, int32_t L,
+                           int32_t precision, const double* controlled_inf, const double* controlled_med,
+                           const double* u0, const double* z0, const double* y0, const smm_adapt* opt,
+                           int32_t nsave, const double* savetimes, double* us, double* zs, double* ys,
+                           double* sum_us, double* sum_zs, double* sum_ys, int64_t* naccept, int64_t* nreject);
+
 #ifdef __cplusplus
 }
 #endif

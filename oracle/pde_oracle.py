@@ -306,3 +306,62 @@ def adaptive_solve(u0, z0, y0, tmax, p, q, ci=None, cm=None, rtol=1e-8, atol=1e-
     sol = solve_ivp(fun, (0, tmax), v0, method="DOP853", rtol=rtol, atol=atol)
     v = sol.y[:, -1]
     return v[:nu].reshape(shp), v[nu:nu + 4].reshape(2, 2), v[nu + 4:].reshape(2, shp[3])
+
+
+# ---- adaptive embedded 3(2) pair: the controller of csrc/pde.cu restated ------------------
+def bs3_adaptive(u0, z0, y0, savetimes, p, q, ci=None, cm=None, abstol=1e-6, reltol=1e-3, dt0=0.0, dtmin=0.0,
+                 dtmax=0.0, force_dtmin=False, force="toeplitz", max_attempts=10 ** 6):
+    """Adaptive integration with the semantics of the reference's solve calls (pde.jl:291;
+    controlstrategies.jl:10,96: abstol, reltol, dtmin, force_dtmin, saveat) on the explicit 3-stage
+    Bogacki-Shampine scheme c=(0,1/2,3/4), b=(2/9,1/3,4/9) with the midpoint solution b*=(0,1,0) as error
+    estimator: norm = sqrt(mean((err/(abstol+reltol*max(|u_n|,|u_n+1|)))^2)) over all density values and ODE
+    unknowns, accept if norm<=1, next dt = dt*clamp(0.9 norm^(-1/3), 0.2, 5), steps clipped to land on the
+    save times.  (DifferentialEquations.jl itself is absent from the reference tree; only its call-site
+    keywords are restated.)  Returns (list of (u,z,y) at savetimes, log of (t, dt, norm, accepted))."""
+    u, z, y = u0.copy(), z0.copy(), y0.copy()
+    D = 0.5 * float(q["sigma"]) ** 2
+    dt_prop = dt0 if dt0 > 0 else (0.1 * min(p["dx"], p["dy"]) ** 2 / D if D > 0 else 1e-3)
+    t, out, log, attempts = 0.0, [], [], 0
+    ntot = u.size + z.size + y.size
+    for tend in savetimes:
+        if dtmax > 0:
+            dt_prop = min(dt_prop, dtmax)
+        dt_prop = max(dt_prop, dtmin)
+        while tend - t > 1e-13 * max(1.0, abs(tend)):
+            rem = tend - t
+            clipped = dt_prop >= rem
+            dt = rem if clipped else dt_prop
+            k1 = rhs(u, z, y, p, q, ci, cm, force=force)
+            k2 = rhs(u + 0.5 * dt * k1[0], z + 0.5 * dt * k1[1], y + 0.5 * dt * k1[2], p, q, ci, cm, force=force)
+            k3 = rhs(u + 0.75 * dt * k2[0], z + 0.75 * dt * k2[1], y + 0.75 * dt * k2[2], p, q, ci, cm, force=force)
+            new = [w + dt * (2 / 9 * a + 1 / 3 * b + 4 / 9 * c) for w, a, b, c in zip((u, z, y), k1, k2, k3)]
+            err = [dt * (2 / 9 * a + (1 / 3 - 1.0) * b + 4 / 9 * c) for a, b, c in zip(k1, k2, k3)]
+            tot = sum(float(np.sum((e / (abstol + reltol * np.maximum(np.abs(w), np.abs(n)))) ** 2))
+                      for e, w, n in zip(err, (u, z, y), new))
+            norm = np.sqrt(tot / ntot)
+            at_min = dt <= dtmin * (1 + 1e-12)
+            accept = bool(norm <= 1.0) or (force_dtmin and at_min)
+            if norm != norm:
+                fac = 0.2
+            elif norm > 0:
+                fac = min(5.0, max(0.2, 0.9 * norm ** (-1.0 / 3.0)))
+            else:
+                fac = 5.0
+            log.append((t, dt, norm, accept))
+            if accept:
+                t = tend if clipped else t + dt
+                u, z, y = new
+                dt_prop = max(dt_prop, dt * fac) if clipped else dt * fac
+            else:
+                dt_prop = dt * min(fac, 0.9)
+                if at_min and not force_dtmin:
+                    raise RuntimeError("error test failed at dt = dtmin")
+            if dtmax > 0:
+                dt_prop = min(dt_prop, dtmax)
+            dt_prop = max(dt_prop, dtmin)
+            attempts += 1
+            if attempts > max_attempts:
+                raise RuntimeError("too many attempts")
+        t = tend
+        out.append((u.copy(), z.copy(), y.copy()))
+    return out, log

@@ -11,7 +11,7 @@ from .abm import ABMsolve, abm_draws, abm_init, abm_solve_raw
 from .ensemble import (ABMsolveensemble, PDEsolveensemble, abm_ensemble_raw, ensemble_means, kde, runensembles,
                        savetimes_abm)
 from .pde import (ArrayPartition, PDEBatch, PDESolution, PDEsolve, constructinitial, default_dt, f, gaussian, pde_rhs,
-                  pde_solve_raw, randominit, sol2uyz, uniforminit)
+                  pde_solve_adaptive_raw, pde_solve_raw, randominit, sol2uyz, uniforminit)
 from .control import PDEsolvefixedtargets, PDEsolvefixedtargetsfast, fixedtargets_objectives, prep
 from .population import ABMPopulation
 from ._lib import Context, SmmError

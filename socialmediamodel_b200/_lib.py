@@ -42,6 +42,17 @@ class smm_grid(C.Structure):
                 ("dx", C.c_double), ("dy", C.c_double)]
 
 
+class smm_adapt(C.Structure):
+    _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("dt0", C.c_double), ("dtmin", C.c_double),
+                ("dtmax", C.c_double), ("force_dtmin", C.c_int32), ("max_attempts", C.c_int32)]
+
+
+def make_adapt(abstol=1e-6, reltol=1e-3, dt0=0.0, dtmin=0.0, dtmax=0.0, force_dtmin=False, max_attempts=0):
+    """Step-control options of the adaptive integrator; the defaults are DifferentialEquations.jl's."""
+    return smm_adapt(float(abstol), float(reltol), float(dt0), float(dtmin), float(dtmax), int(bool(force_dtmin)),
+                     int(max_attempts))
+
+
 _P = C.c_void_p
 _I32, _I64, _U64, _D = C.c_int32, C.c_int64, C.c_uint64, C.c_double
 
@@ -84,6 +95,9 @@ PROTOTYPES = {
     "smm_pde_batch_read": (C.c_int, [_P, _P, _P, _P, _P]),
     "smm_pde_batch_sum_dev": (C.c_int, [_P, _P, _P, _P, _P]),
     "smm_pde_batch_destroy": (C.c_int, [_P, _P]),
+    "smm_pde_batch_advance": (C.c_int, [_P, _P, _D, C.POINTER(smm_adapt), _P, _P, _P]),
+    "smm_pde_solve_adaptive": (C.c_int, [_P, C.POINTER(smm_grid), C.POINTER(smm_params), _I32, _I32, _I32, _P, _P,
+                                         _P, _P, _P, C.POINTER(smm_adapt), _I32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -40,10 +40,25 @@ struct PdeCoef {  // per-instance stage data: written by the finalising CTA, rea
 
 struct PdeOde {  // RK bookkeeping of the ODE unknowns
   double yn[LMAX][2], zn[2][2], yacc[LMAX][2], zacc[2][2];
+  double yerr[LMAX][2], zerr[2][2];  // embedded error estimate (adaptive stepping)
+};
+
+// Per-instance step controller of the adaptive integrator (embedded 3(2) pair, see enqueue_adaptive_attempt).
+// Written only by the CTA that finalises the instance in the last stage kernel of an attempt (and by the
+// host between calls); read by every CTA of the following kernels.
+struct PdeCtl {
+  double t, tend, dt_prop, dt_try, dtmin, dtmax, abstol, reltol, errnorm, ntot;
+  long long naccept, nreject;
+  int cur;         // which of the two ping-pong buffers (u, Ua) holds the current state
+  int done;        // reached tend (or failed): all kernels skip the instance
+  int need_init;   // last attempt rejected: density sum / moments of the current state must be rebuilt
+  int clipped;     // dt_try was shortened to land on tend
+  int force_dtmin, fail;
 };
 
 enum { ACC_NONE = 0, ACC_INIT = 1, ACC_ADD = 2, ACC_FINAL = 3 };
 enum { FIN_INIT = 0, FIN_STAGE = 1 };
+enum { ROLE_FIXED = 0, ROLE_CUR = 1, ROLE_OTHER = 2 };  // adaptive mode: buffer chosen per instance by PdeCtl::cur
 
 struct StageArgs {
   // TMA descriptors of the stage state U (3-D: x, y, plane*instance) and of Fx / Fy (3-D: x, y, instance)
@@ -65,6 +80,16 @@ struct StageArgs {
   const PdeInst* inst;
   double dt, A, Bc, C, bw;
   int acc_mode, last_stage, do_moments;
+  // adaptive stepping (ctl != nullptr): dt comes from ctl[b].dt_try, the ping-pong buffers P[0]/P[1] are
+  // selected per instance, and a second accumulator carries the embedded error estimate
+  PdeCtl* ctl;
+  void* P[2];
+  CUtensorMap tmP[2];
+  int u_role, out_role;
+  void* err;         // error accumulator (state-sized)
+  double* errpart;   // [B][nblk] per-CTA sums of (err / scale)^2
+  double ew;         // error weight of this stage (b_i - b*_i)
+  int err_mode;      // ACC_INIT / ACC_ADD / ACC_FINAL
 };
 
 __device__ __forceinline__ float fast_exp_neg_dist(float dx, float dy) { return w_of_r2(fmaf(dx, dx, dy * dy)); }
@@ -74,12 +99,17 @@ __device__ __forceinline__ double r_fun(double x) { return x > 0.1 ? x : 0.1; } 
 
 // Reduce the per-CTA partial moments of an instance (fixed order: deterministic), advance the ODE
 // unknowns by the stage formula, and produce the coefficients of the next right-hand side.
+__device__ void adaptive_controller(const StageArgs& A, int b, int nblk, const double* s_err);
+
 __device__ void finalize_instance(const StageArgs& A, int b, int nblk, int mode, double* sm /* [2L][3] */) {
   const int L = A.L, tid = threadIdx.y * blockDim.x + threadIdx.x;
   const double dV = A.dx * A.dy;
   PdeCoef& cf = A.coef[b];
   PdeOde& od = A.ode[b];
   const PdeInst& in = A.inst[b];
+  const bool adaptive = A.ctl != nullptr;
+  const double dt = adaptive ? A.ctl[b].dt_try : A.dt;
+  __shared__ double s_err[LMAX + 2];  // adaptive: scaled squared error of each ODE unknown pair
   if (tid < 2 * L * 3) {
     double s = 0.0;
     const double* p = A.partials + ((size_t)b * nblk) * (2 * L * 3) + tid;
@@ -94,20 +124,32 @@ __device__ void finalize_instance(const StageArgs& A, int b, int nblk, int mode,
     double* dys = is_inf ? cf.dy[e] : cf.dz[e];
     double* yn = is_inf ? od.yn[e] : od.zn[e];
     double* ya = is_inf ? od.yacc[e] : od.zacc[e];
-    double ynew[2];
+    double* ye = is_inf ? od.yerr[e] : od.zerr[e];
+    double ynew[2], esum = 0.0;
     for (int d = 0; d < 2; d++) {
       if (mode == FIN_INIT) {
         ynew[d] = ys[d];
         yn[d] = ys[d];
       } else {
-        double out = A.A * yn[d] + A.Bc * ys[d] + A.C * A.dt * dys[d];
-        if (A.acc_mode == ACC_INIT) ya[d] = yn[d] + A.dt * A.bw * dys[d];
-        else if (A.acc_mode == ACC_ADD) ya[d] += A.dt * A.bw * dys[d];
-        else if (A.acc_mode == ACC_FINAL) out = ya[d] + A.dt * A.bw * dys[d];
+        double out = A.A * yn[d] + A.Bc * ys[d] + A.C * dt * dys[d];
+        if (A.acc_mode == ACC_INIT) ya[d] = yn[d] + dt * A.bw * dys[d];
+        else if (A.acc_mode == ACC_ADD) ya[d] += dt * A.bw * dys[d];
+        else if (A.acc_mode == ACC_FINAL) out = ya[d] + dt * A.bw * dys[d];
+        if (adaptive) {
+          double ev = A.ew * dt * dys[d];
+          if (A.err_mode == ACC_INIT) ye[d] = ev;
+          else if (A.err_mode == ACC_ADD) ye[d] += ev;
+          else {
+            ev += ye[d];
+            const double sc = A.ctl[b].abstol + A.ctl[b].reltol * fmax(fabs(yn[d]), fabs(out));
+            esum += (ev / sc) * (ev / sc);
+          }
+        }
         ynew[d] = out;
-        if (A.last_stage) yn[d] = out;
+        if (A.last_stage && !adaptive) yn[d] = out;  // adaptive: committed by the controller on acceptance
       }
     }
+    if (adaptive) s_err[tid] = esum;
     // right-hand side of the ODE at the new stage state
     double m = 0.0, mx = 0.0, my = 0.0;
     if (is_inf) {  // sums over the media i of plane (e, i)
@@ -143,6 +185,63 @@ __device__ void finalize_instance(const StageArgs& A, int b, int nblk, int mode,
       cf.R[1][e] = in.eta * r_fun((m1 - m0) / (m1 + m0));
     }
   }
+  if (adaptive && mode == FIN_STAGE && A.last_stage) {
+    __syncthreads();
+    adaptive_controller(A, b, nblk, s_err);
+  }
+}
+
+// Step-size control of one instance after the last stage of an attempt (run by the finalising CTA).
+// err = dt * sum_i (b_i - b*_i) k_i of the 3(2) pair; norm = sqrt(mean((err / (abstol + reltol*max(|u_n|,|u_n+1|)))^2))
+// over all density values and ODE unknowns (the DifferentialEquations.jl norm, call sites pde.jl:291,
+// controlstrategies.jl:10,96: abstol / reltol / dtmin / force_dtmin).  Accept if norm <= 1; the next step is
+// dt * clamp(0.9 norm^(-1/3), 0.2, 5).  The per-CTA partial sums are added in a fixed order (deterministic).
+__device__ void adaptive_controller(const StageArgs& A, int b, int nblk, const double* s_err) {
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+  __shared__ double red[BX * BY];
+  double s = 0.0;
+  for (int k = tid; k < nblk; k += nthr) s += A.errpart[(size_t)b * nblk + k];
+  red[tid] = s;
+  __syncthreads();
+  for (int w = nthr / 2; w > 0; w >>= 1) {
+    if (tid < w) red[tid] += red[tid + w];
+    __syncthreads();
+  }
+  if (tid != 0) return;
+  PdeCtl& c = A.ctl[b];
+  PdeCoef& cf = A.coef[b];
+  PdeOde& od = A.ode[b];
+  double tot = red[0];
+  for (int e = 0; e < A.L + 2; e++) tot += s_err[e];
+  const double norm = sqrt(tot / c.ntot);
+  c.errnorm = norm;
+  const bool at_min = c.dt_try <= c.dtmin * (1.0 + 1e-12);  // also a step shortened below dtmin to land on tend
+  const bool accept = (norm <= 1.0) || (c.force_dtmin && at_min);
+  double fac = 5.0;
+  if (!(norm == norm)) fac = 0.2;  // NaN
+  else if (norm > 0.0) fac = fmin(5.0, fmax(0.2, 0.9 / cbrt(norm)));
+  if (accept) {
+    c.t = c.clipped ? c.tend : c.t + c.dt_try;
+    c.cur ^= 1;
+    c.need_init = 0;
+    c.naccept++;
+    c.dt_prop = c.clipped ? fmax(c.dt_prop, c.dt_try * fac) : c.dt_try * fac;
+    for (int e = 0; e < A.L; e++) { od.yn[e][0] = cf.y[e][0]; od.yn[e][1] = cf.y[e][1]; }
+    for (int e = 0; e < 2; e++) { od.zn[e][0] = cf.z[e][0]; od.zn[e][1] = cf.z[e][1]; }
+  } else {
+    c.need_init = 1;
+    c.nreject++;
+    c.dt_prop = c.dt_try * fmin(fac, 0.9);
+    for (int e = 0; e < A.L; e++) { cf.y[e][0] = od.yn[e][0]; cf.y[e][1] = od.yn[e][1]; }
+    for (int e = 0; e < 2; e++) { cf.z[e][0] = od.zn[e][0]; cf.z[e][1] = od.zn[e][1]; }
+    if (at_min && !c.force_dtmin) { c.fail = 1; c.done = 1; }  // "dt <= dtmin": the reference aborts here
+  }
+  if (c.dtmax > 0.0) c.dt_prop = fmin(c.dt_prop, c.dtmax);
+  c.dt_prop = fmax(c.dt_prop, c.dtmin);
+  const double rem = c.tend - c.t;
+  if (rem <= 1e-13 * fmax(1.0, fabs(c.tend))) { c.t = c.tend; c.done = 1; }
+  else if (c.dt_prop >= rem) { c.dt_try = rem; c.clipped = 1; }
+  else { c.dt_try = c.dt_prop; c.clipped = 0; }
 }
 
 // CTA-level: write this CTA's partial moments, detect the last CTA of the instance, finalise.
@@ -183,7 +282,13 @@ __global__ void __launch_bounds__(BX* BY) pde_moments_kernel(StageArgs A) {
   __shared__ double part_w[BY * 2 * LMAX * 3];
   __shared__ double sm[2 * LMAX * 3];
   const size_t plane = (size_t)A.Pw * Ny;
-  const real* U = static_cast<const real*>(A.U) + (size_t)b * 2 * L * plane;
+  const void* Ubase = A.U;
+  if (A.ctl) {  // adaptive: only after a rejected attempt, on the instance's current buffer
+    const PdeCtl& c = A.ctl[b];
+    if (c.done || !c.need_init) return;
+    Ubase = c.cur ? A.P[1] : A.P[0];
+  }
+  const real* U = static_cast<const real*>(Ubase) + (size_t)b * 2 * L * plane;
   const real X = (real)(A.gx0 + ix * A.dx), Y = (real)(A.gy0 + iy * A.dy);
   real rs = 0;
   for (int pl = 0; pl < 2 * L; pl++) {
@@ -255,7 +360,7 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, in
 }
 __host__ __device__ inline size_t align128(size_t b) { return (b + 127) & ~(size_t)127; }
 
-template <typename real, int LT>
+template <typename real, int LT, bool AD>
 __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_kernel(const __grid_constant__ StageArgs A) {
   const int L = LT ? LT : A.L;
   const int NP = 2 * L;
@@ -283,7 +388,21 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
   if (tid == 0) { s_par[0] = (real)A.inst[b].a; s_par[1] = (real)A.inst[b].b; s_par[2] = (real)A.inst[b].c; s_par[3] = (real)A.inst[b].D; }
   const int Pw = A.Pw;
   const size_t plane = (size_t)Pw * Ny;
-  const real* U = static_cast<const real*>(A.U) + (size_t)b * NP * plane;
+  double dt_b = A.dt;
+  const void *Uin = A.U, *un_base = A.un;
+  void* out_base = A.Uout;
+  const CUtensorMap* tmU = &A.tmU;
+  if constexpr (AD) {  // per-instance step size and ping-pong buffers (PdeCtl)
+    const PdeCtl& c = A.ctl[b];
+    if (c.done) return;
+    dt_b = c.dt_try;
+    const int cur = c.cur;
+    un_base = cur ? A.P[1] : A.P[0];
+    if (A.u_role == ROLE_CUR) { Uin = un_base; tmU = cur ? &A.tmP[1] : &A.tmP[0]; }
+    else if (A.u_role == ROLE_OTHER) { Uin = cur ? A.P[0] : A.P[1]; tmU = cur ? &A.tmP[0] : &A.tmP[1]; }
+    if (A.out_role == ROLE_OTHER) out_base = cur ? A.P[0] : A.P[1];
+  }
+  const real* U = static_cast<const real*>(Uin) + (size_t)b * NP * plane;
   // ---- stage the tiles (clamped at the domain edge; the clamped values are never used there)
   if (A.use_tma) {
     // One elected thread issues three bulk tensor copies (TMA): the 2L x 10 x 36 density box with its
@@ -293,7 +412,7 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
     __syncthreads();
     if (tid == 0) {
       mbar_expect_tx(&tma_bar, (unsigned)(sizeof(real) * (NP * TH * TW + BY * TW + TH * BX)));
-      tma_load_3d(tile, &A.tmU, bx0 - XO, by0 - 1, b * NP, &tma_bar);
+      tma_load_3d(tile, tmU, bx0 - XO, by0 - 1, b * NP, &tma_bar);
       tma_load_3d(sFx, &A.tmFx, bx0 - XO, by0, b, &tma_bar);
       tma_load_3d(sFy, &A.tmFy, bx0, by0 - 1, b, &tma_bar);
     }
@@ -376,22 +495,28 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
       gsum[i] += Ej * s_R[i][j];
     }
   }
-  const real* un = static_cast<const real*>(A.un) + (size_t)b * NP * plane;
-  real* Uout = static_cast<real*>(A.Uout) + (size_t)b * NP * plane;
+  const real* un = static_cast<const real*>(un_base) + (size_t)b * NP * plane;
+  real* Uout = static_cast<real*>(out_base) + (size_t)b * NP * plane;
   real* acc = A.acc ? static_cast<real*>(A.acc) + (size_t)b * NP * plane : nullptr;
+  real* errb = AD ? static_cast<real*>(A.err) + (size_t)b * NP * plane : nullptr;
   const size_t o_c = (size_t)cy * Pw + cx;
-  const real dtA = (real)A.A, dtB = (real)A.Bc, dtC = (real)(A.C * A.dt), dtw = (real)(A.bw * A.dt);
+  const real dtA = (real)A.A, dtB = (real)A.Bc, dtC = (real)(A.C * dt_b), dtw = (real)(A.bw * dt_b);
+  const real dte = AD ? (real)(A.ew * dt_b) : (real)0;
+  const real e_atol = AD ? (real)A.ctl[b].abstol : (real)0, e_rtol = AD ? (real)A.ctl[b].reltol : (real)0;
+  const bool need_err = AD && A.err_mode != ACC_INIT;
+  real esq = 0;
   // step-start state and accumulator of this grid point for all planes, loaded up front (independent
   // loads in flight together; inside the plane loop they would queue behind possibly-aliasing stores)
   constexpr int NPT = LT ? 2 * LT : 1;
-  real unv[NPT], accv[NPT];
-  const bool need_un = dtA != (real)0 || A.acc_mode == ACC_INIT;
+  real unv[NPT], accv[NPT], errv[AD ? NPT : 1];
+  const bool need_un = dtA != (real)0 || A.acc_mode == ACC_INIT || (AD && A.err_mode == ACC_FINAL);
   const bool need_acc = A.acc_mode == ACC_ADD || A.acc_mode == ACC_FINAL;
   if (LT) {
 #pragma unroll
     for (int p = 0; p < NPT; p++) {
       unv[p] = need_un ? un[(size_t)p * plane + o_c] : (real)0;
       accv[p] = need_acc ? acc[(size_t)p * plane + o_c] : (real)0;
+      if (AD) errv[AD ? p : 0] = need_err ? errb[(size_t)p * plane + o_c] : (real)0;
     }
   }
   real rs_out = 0;
@@ -426,6 +551,15 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
       if (A.acc_mode == ACC_INIT) { if (in) acc[po] = unp + dtw * k; }
       else if (A.acc_mode == ACC_ADD) { if (in) acc[po] = accp + dtw * k; }
       else if (A.acc_mode == ACC_FINAL) out = accp + dtw * k;
+      if constexpr (AD) {  // embedded error estimate: err += (b_i - b*_i) dt k_i; scaled norm at the last stage
+        real ev = dte * k;
+        if (need_err) ev += LT ? errv[LT ? p : 0] : errb[po];
+        if (A.err_mode != ACC_FINAL) { if (in) errb[po] = ev; }
+        else if (in) {
+          const real q = ev / (e_atol + e_rtol * fmax(fabs(unp), fabs(out)));
+          esq += q * q;
+        }
+      }
       if (in) Uout[po] = out;
       const real v = in ? out : (real)0;
       rs_out += v;
@@ -434,7 +568,22 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
   }
   if (!A.do_moments) return;
   if (in) static_cast<real*>(A.rhosum_out)[(size_t)b * plane + o_c] = rs_out;
+  __shared__ double s_esq[BY];
+  if constexpr (AD) {
+    if (A.err_mode == ACC_FINAL) {
+      const real w = warp_sum(esq);
+      if (tx == 0) s_esq[ty] = (double)w;
+    }
+  }
   __syncthreads();
+  if constexpr (AD) {
+    if (A.err_mode == ACC_FINAL && tid == 0) {
+      double t = 0.0;
+      for (int w = 0; w < BY; w++) t += s_esq[w];
+      A.errpart[(size_t)b * (gridDim.x * gridDim.y) + blockIdx.y * gridDim.x + blockIdx.x] = t;
+      __threadfence();
+    }
+  }
   // block-level moments: warp `w` reduces plane w, w + 8, ..: column sums over the 8 rows in fixed
   // order, then one shuffle tree over the 32 columns (deterministic)
   {
@@ -572,12 +721,21 @@ struct smm_pde_batch {
   CUtensorMap tm_u, tm_ua, tm_ub, tm_fx, tm_fy;  // TMA descriptors (stage kernel tile loads)
   bool use_tma;
   bool no_graph;      // stream capture unavailable on the caller's stream: launch kernels directly
+  // adaptive integrator (allocated by the first smm_pde_batch_advance)
+  double time;        // batch clock
+  void* err;
+  double* errpart;
+  PdeCtl* ctl;
+  std::vector<PdeCtl> h_ctl;
+  cudaGraphExec_t adapt_graph;
 };
 
 static void pde_free(smm_pde_batch* pb) {
   if (!pb) return;
-  void* ptrs[] = {pb->u, pb->Ua, pb->Ub, pb->acc, pb->rhosum, pb->Fx, pb->Fy, pb->wext, pb->partials, pb->counters, pb->coef, pb->ode, pb->inst};
+  void* ptrs[] = {pb->u, pb->Ua, pb->Ub, pb->acc, pb->rhosum, pb->Fx, pb->Fy, pb->wext, pb->partials, pb->counters, pb->coef, pb->ode, pb->inst,
+                  pb->err, pb->errpart, pb->ctl};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (pb->adapt_graph) cudaGraphExecDestroy(pb->adapt_graph);
   for (auto& g : pb->graphs) cudaGraphExecDestroy(g.second);
   smm_fft_plan_destroy(pb->fft);
   delete pb;
@@ -626,25 +784,31 @@ static size_t stage_smem(int L, size_t rs) {
   return align128(rs * 2 * L * TH * TW) + align128(rs * BY * TW) + align128(rs * TH * BX) + rs * (size_t)BY * 2 * L * 32;
 }
 
-template <typename real, int LT>
+template <typename real, int LT, bool AD>
 static int launch_stage_t(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
   dim3 grid(pb->nbx, pb->nby, pb->B), block(BX, BY);
   const size_t sm = stage_smem(pb->L, sizeof(real));
-  if (sm > 48 * 1024) SMM_CUDA(ctx, cudaFuncSetAttribute(pde_stage_kernel<real, LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  pde_stage_kernel<real, LT><<<grid, block, sm, ctx->stream>>>(A);
+  // static + dynamic shared memory can exceed 48 KB even when the dynamic part alone does not: always opt in
+  SMM_CUDA(ctx, cudaFuncSetAttribute(pde_stage_kernel<real, LT, AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 48 * 1024)));
+  pde_stage_kernel<real, LT, AD><<<grid, block, sm, ctx->stream>>>(A);
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;
 }
 
-static int launch_stage(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
+template <bool AD>
+static int launch_stage_ad(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
   const bool f64 = pb->precision == SMM_PREC_F64;
   switch (pb->L) {
-    case 4: return f64 ? launch_stage_t<double, 4>(ctx, pb, A) : launch_stage_t<float, 4>(ctx, pb, A);
-    case 5: return f64 ? launch_stage_t<double, 5>(ctx, pb, A) : launch_stage_t<float, 5>(ctx, pb, A);
-    case 6: return f64 ? launch_stage_t<double, 6>(ctx, pb, A) : launch_stage_t<float, 6>(ctx, pb, A);
-    default: return f64 ? launch_stage_t<double, 0>(ctx, pb, A) : launch_stage_t<float, 0>(ctx, pb, A);
+    case 4: return f64 ? launch_stage_t<double, 4, AD>(ctx, pb, A) : launch_stage_t<float, 4, AD>(ctx, pb, A);
+    case 5: return f64 ? launch_stage_t<double, 5, AD>(ctx, pb, A) : launch_stage_t<float, 5, AD>(ctx, pb, A);
+    case 6: return f64 ? launch_stage_t<double, 6, AD>(ctx, pb, A) : launch_stage_t<float, 6, AD>(ctx, pb, A);
+    default: return f64 ? launch_stage_t<double, 0, AD>(ctx, pb, A) : launch_stage_t<float, 0, AD>(ctx, pb, A);
   }
+}
+
+static int launch_stage(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
+  return A.ctl ? launch_stage_ad<true>(ctx, pb, A) : launch_stage_ad<false>(ctx, pb, A);
 }
 
 // one RK step = nstages x (conv, stage).  Buffer roles: u = step start / result, Ua/Ub stage states.
@@ -769,6 +933,7 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
   pb->u = pb->Ua = pb->Ub = pb->acc = pb->rhosum = pb->Fx = pb->Fy = pb->wext = nullptr;
   pb->partials = nullptr; pb->counters = nullptr; pb->coef = nullptr; pb->ode = nullptr; pb->inst = nullptr;
   pb->steps_taken = 0;
+  pb->time = 0.0; pb->err = nullptr; pb->errpart = nullptr; pb->ctl = nullptr; pb->adapt_graph = nullptr;
   pb->fft = nullptr;
   pb->no_graph = false;
   pb->use_tma = false;
@@ -907,6 +1072,7 @@ extern "C" int smm_pde_batch_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, in
     for (int s = 0; s < nsteps; s++) SMM_TRY(enqueue_step(ctx, pb, dt, scheme));
     smm_toc(ctx, SMM_K_STENCIL);
     pb->steps_taken += nsteps;
+    pb->time += dt * nsteps;
     return SMM_OK;
   }
   const int per_step = (scheme == SMM_RK_EULER ? 1 : scheme == SMM_RK_HEUN ? 2 : scheme == SMM_RK_SSPRK3 ? 3 : 4) * 2;
@@ -915,6 +1081,168 @@ extern "C" int smm_pde_batch_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, in
   smm_toc(ctx, SMM_K_STENCIL);
   ctx->launches += (int64_t)per_step * nsteps;
   pb->steps_taken += nsteps;
+  pb->time += dt * nsteps;
+  return SMM_OK;
+}
+
+// ---- adaptive integrator -------------------------------------------------------------------------
+template <typename real>
+__global__ void adapt_commit_kernel(real* P0, const real* P1, const PdeCtl* ctl, size_t per_inst) {
+  const int b = blockIdx.y;
+  if (!ctl[b].cur) return;  // current state already in the primary buffer
+  real* d = P0 + (size_t)b * per_inst;
+  const real* s = P1 + (size_t)b * per_inst;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_inst; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+static StageArgs adaptive_args(const smm_pde_batch* pb) {
+  StageArgs A = base_args(pb);
+  A.ctl = pb->ctl; A.P[0] = pb->u; A.P[1] = pb->Ua; A.tmP[0] = pb->tm_u; A.tmP[1] = pb->tm_ua;
+  A.err = pb->err; A.errpart = pb->errpart; A.acc = pb->acc;
+  return A;
+}
+
+// One step attempt of every unfinished instance: [moments of the current state where the previous attempt
+// was rejected] + 3 x (interaction force, fused stage).  Stage states: Y2 = u + dt/2 k1 -> other ping-pong
+// buffer, Y3 = u + 3dt/4 k2 -> Ub, u_new = u + dt (2/9 k1 + 1/3 k2 + 4/9 k3) -> other ping-pong buffer; the
+// last stage also leaves the error norm, and its finalising CTA accepts (flips the buffers) or rejects.
+static int enqueue_adaptive_attempt(smm_ctx* ctx, smm_pde_batch* pb) {
+  {
+    StageArgs A = adaptive_args(pb);
+    A.U = pb->u;
+    dim3 grid(pb->nbx, pb->nby, pb->B), block(BX, BY);
+    if (pb->precision == SMM_PREC_F64) pde_moments_kernel<double><<<grid, block, 0, ctx->stream>>>(A);
+    else pde_moments_kernel<float><<<grid, block, 0, ctx->stream>>>(A);
+    ctx->launches++;
+    SMM_CUDA(ctx, cudaGetLastError());
+  }
+  struct St { int u_role, out_role; double A, C, bw, ew; int acc; };
+  const St st[3] = {{ROLE_CUR, ROLE_OTHER, 1, 0.5, 2.0 / 9, 2.0 / 9, ACC_INIT},
+                    {ROLE_OTHER, ROLE_FIXED, 1, 0.75, 1.0 / 3, 1.0 / 3 - 1.0, ACC_ADD},
+                    {ROLE_FIXED, ROLE_OTHER, 0, 0, 4.0 / 9, 4.0 / 9, ACC_FINAL}};
+  for (int s = 0; s < 3; s++) {
+    SMM_TRY(launch_conv(ctx, pb));
+    StageArgs A = adaptive_args(pb);
+    A.u_role = st[s].u_role; A.out_role = st[s].out_role;
+    A.U = pb->Ub; A.tmU = pb->tm_ub; A.Uout = pb->Ub; A.un = pb->u;  // the ROLE_FIXED buffer
+    A.dt = 0; A.A = st[s].A; A.Bc = 0; A.C = st[s].C; A.bw = st[s].bw; A.ew = st[s].ew;
+    A.acc_mode = st[s].acc; A.err_mode = st[s].acc;
+    A.last_stage = s == 2; A.do_moments = 1;
+    SMM_TRY(launch_stage(ctx, pb, A));
+  }
+  return SMM_OK;
+}
+
+extern "C" int smm_pde_batch_advance(smm_ctx* ctx, smm_pde_batch* pb, double t_end, const smm_adapt* opt,
+                                     int64_t* naccept, int64_t* nreject, double* dt_next) {
+  SMM_REQUIRE(ctx, ctx && pb && opt, "smm_pde_batch_advance: NULL argument");
+  SMM_REQUIRE(ctx, opt->abstol > 0 && opt->reltol >= 0, "smm_pde_batch_advance: need abstol > 0 and reltol >= 0");
+  SMM_REQUIRE(ctx, opt->dtmin >= 0, "smm_pde_batch_advance: dtmin must be >= 0");
+  SMM_REQUIRE(ctx, t_end >= pb->time, "smm_pde_batch_advance: t_end=%g lies before the batch clock %g", t_end, pb->time);
+  SMM_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int B = pb->B, nblk = pb->nbx * pb->nby;
+  const size_t state_bytes = (size_t)B * pb->per_inst * pb->rs;
+  if (!pb->ctl) {
+    SMM_CUDA(ctx, cudaMalloc(&pb->err, state_bytes));
+    SMM_CUDA(ctx, cudaMemsetAsync(pb->err, 0, state_bytes, ctx->stream));
+    SMM_CUDA(ctx, cudaMalloc((void**)&pb->errpart, (size_t)B * nblk * 8));
+    SMM_CUDA(ctx, cudaMalloc((void**)&pb->ctl, (size_t)B * sizeof(PdeCtl)));
+    pb->h_ctl.assign(B, PdeCtl());
+    std::vector<PdeInst> inst(B);
+    SMM_CUDA(ctx, cudaMemcpyAsync(inst.data(), pb->inst, (size_t)B * sizeof(PdeInst), cudaMemcpyDeviceToHost, ctx->stream));
+    SMM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < B; b++) {
+      PdeCtl& c = pb->h_ctl[b];
+      memset(&c, 0, sizeof c);
+      const double h2 = std::min(pb->grid.dx, pb->grid.dy) * std::min(pb->grid.dx, pb->grid.dy);
+      c.dt_prop = opt->dt0 > 0 ? opt->dt0 : (inst[b].D > 0 ? 0.1 * h2 / inst[b].D : 1e-3);
+      c.ntot = (double)pb->host_per + 2.0 * (pb->L + 2);
+    }
+  }
+  const int64_t max_attempts = opt->max_attempts > 0 ? opt->max_attempts : 1000000;
+  std::vector<long long> acc0(B), rej0(B);
+  for (int b = 0; b < B; b++) {
+    PdeCtl& c = pb->h_ctl[b];
+    c.t = pb->time; c.tend = t_end;
+    c.abstol = opt->abstol; c.reltol = opt->reltol; c.dtmin = opt->dtmin; c.dtmax = opt->dtmax;
+    c.force_dtmin = opt->force_dtmin != 0; c.fail = 0; c.cur = 0; c.need_init = 0;
+    if (c.dtmax > 0) c.dt_prop = std::min(c.dt_prop, c.dtmax);
+    c.dt_prop = std::max(c.dt_prop, c.dtmin);
+    const double rem = t_end - c.t;
+    c.done = rem <= 1e-13 * std::max(1.0, std::fabs(t_end));
+    if (c.dt_prop >= rem) { c.dt_try = rem; c.clipped = 1; } else { c.dt_try = c.dt_prop; c.clipped = 0; }
+    acc0[b] = c.naccept; rej0[b] = c.nreject;
+  }
+  SMM_CUDA(ctx, cudaMemcpyAsync(pb->ctl, pb->h_ctl.data(), (size_t)B * sizeof(PdeCtl), cudaMemcpyHostToDevice, ctx->stream));
+  // the kernel chain of one attempt is captured once (no step size is baked in) and replayed
+  bool use_graph = !pb->no_graph;
+  if (use_graph && !pb->adapt_graph) {
+    cudaGraph_t graph;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      pb->no_graph = true;
+      use_graph = false;
+    } else {
+      int64_t l0 = ctx->launches;
+      int rc = enqueue_adaptive_attempt(ctx, pb);
+      ctx->launches = l0;
+      cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+      if (rc != SMM_OK) { if (e == cudaSuccess) cudaGraphDestroy(graph); return rc; }
+      SMM_CUDA(ctx, e);
+      SMM_CUDA(ctx, cudaGraphInstantiate(&pb->adapt_graph, graph, 0));
+      cudaGraphDestroy(graph);
+    }
+  }
+  int64_t attempts = 0;
+  bool failed = false;
+  smm_tic(ctx, SMM_K_STENCIL);
+  for (;;) {
+    // attempts until the next look at the controllers: the slowest instance's remaining time / step
+    double est = 0;
+    bool all_done = true;
+    for (int b = 0; b < B; b++) {
+      const PdeCtl& c = pb->h_ctl[b];
+      if (c.fail) failed = true;
+      if (c.done) continue;
+      all_done = false;
+      est = std::max(est, (c.tend - c.t) / std::max(c.dt_prop, 1e-300));
+    }
+    if (all_done || failed || attempts >= max_attempts) break;
+    const int burst = (int)std::min<double>(64.0, std::max(1.0, std::ceil(est)));
+    for (int k = 0; k < burst; k++) {
+      if (use_graph) { SMM_CUDA(ctx, cudaGraphLaunch(pb->adapt_graph, ctx->stream)); ctx->launches += 7; }
+      else SMM_TRY(enqueue_adaptive_attempt(ctx, pb));
+    }
+    attempts += burst;
+    SMM_CUDA(ctx, cudaMemcpyAsync(pb->h_ctl.data(), pb->ctl, (size_t)B * sizeof(PdeCtl), cudaMemcpyDeviceToHost, ctx->stream));
+    SMM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  smm_toc(ctx, SMM_K_STENCIL);
+  {  // bring every instance's current state back into the primary buffer
+    dim3 grid((unsigned)std::min<size_t>((pb->per_inst + 255) / 256, 64), B);
+    if (pb->precision == SMM_PREC_F64) adapt_commit_kernel<double><<<grid, 256, 0, ctx->stream>>>((double*)pb->u, (const double*)pb->Ua, pb->ctl, pb->per_inst);
+    else adapt_commit_kernel<float><<<grid, 256, 0, ctx->stream>>>((float*)pb->u, (const float*)pb->Ua, pb->ctl, pb->per_inst);
+    ctx->launches++;
+    SMM_CUDA(ctx, cudaGetLastError());
+    SMM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  for (int b = 0; b < B; b++) {
+    const PdeCtl& c = pb->h_ctl[b];
+    if (naccept) naccept[b] = c.naccept - acc0[b];
+    if (nreject) nreject[b] = c.nreject - rej0[b];
+    if (dt_next) dt_next[b] = c.dt_prop;
+  }
+  if (failed) {
+    for (int b = 0; b < B; b++)
+      if (pb->h_ctl[b].fail)
+        return smm_fail(ctx, SMM_ERR_UNSUPPORTED, "smm_pde_batch_advance: instance %d: error test failed at dt = dtmin = %g (t = %g, norm = %g); "
+                        "set force_dtmin or lower dtmin", b, opt->dtmin, pb->h_ctl[b].t, pb->h_ctl[b].errnorm);
+  }
+  for (int b = 0; b < B; b++)
+    if (!pb->h_ctl[b].done)
+      return smm_fail(ctx, SMM_ERR_UNSUPPORTED, "smm_pde_batch_advance: instance %d did not reach t_end=%g within %lld attempts (t = %g, dt = %g, norm = %g)",
+                      b, t_end, (long long)max_attempts, pb->h_ctl[b].t, pb->h_ctl[b].dt_prop, pb->h_ctl[b].errnorm);
+  pb->time = t_end;
   return SMM_OK;
 }
 
@@ -1020,6 +1348,28 @@ extern "C" int smm_pde_rhs(smm_ctx* ctx, const smm_grid* grid, const smm_params*
   return rc;
 }
 
+// Read the batch state and scatter it into slot m of the Julia layouts us[Nx,Ny,2,L,nsave,B], zs[2,2,nsave,B],
+// ys[2,L,nsave,B] and the per-save-point sums over the instances.
+static int record_snapshot(smm_ctx* ctx, smm_pde_batch* pb, int m, int nsave, double* us, double* zs, double* ys, double* sum_us,
+                           double* sum_zs, double* sum_ys, std::vector<double>& ubuf, std::vector<double>& zbuf, std::vector<double>& ybuf) {
+  const int B = pb->B, L = pb->L;
+  const size_t per = pb->host_per;
+  SMM_TRY(smm_pde_batch_read(ctx, pb, ubuf.empty() ? nullptr : ubuf.data(), zbuf.data(), ybuf.data()));
+  SMM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int b = 0; b < B; b++) {
+    if (us) memcpy(us + ((size_t)b * nsave + m) * per, ubuf.data() + (size_t)b * per, per * 8);
+    if (zs) memcpy(zs + ((size_t)b * nsave + m) * 4, zbuf.data() + (size_t)b * 4, 4 * 8);
+    if (ys) memcpy(ys + ((size_t)b * nsave + m) * 2 * L, ybuf.data() + (size_t)b * 2 * L, (size_t)2 * L * 8);
+  }
+  if (sum_us) {
+    double* o = sum_us + (size_t)m * per;
+    for (size_t e = 0; e < per; e++) { double s = 0; for (int b = 0; b < B; b++) s += ubuf[(size_t)b * per + e]; o[e] = s; }
+  }
+  if (sum_zs) for (int e = 0; e < 4; e++) { double s = 0; for (int b = 0; b < B; b++) s += zbuf[(size_t)b * 4 + e]; sum_zs[(size_t)m * 4 + e] = s; }
+  if (sum_ys) for (int e = 0; e < 2 * L; e++) { double s = 0; for (int b = 0; b < B; b++) s += ybuf[(size_t)b * 2 * L + e]; sum_ys[(size_t)m * 2 * L + e] = s; }
+  return SMM_OK;
+}
+
 extern "C" int smm_pde_solve(smm_ctx* ctx, const smm_grid* grid, const smm_params* q, int32_t B, int32_t L,
                              int32_t precision, const double* controlled_inf, const double* controlled_med,
                              const double* u0, const double* z0, const double* y0, double dt, int32_t nsteps,
@@ -1044,20 +1394,37 @@ extern "C" int smm_pde_solve(smm_ctx* ctx, const smm_grid* grid, const smm_param
     if ((rc = smm_pde_batch_step(ctx, pb, dt, target - done, scheme)) != SMM_OK) break;
     done = target;
     if (m == nsave) break;
-    if ((rc = smm_pde_batch_read(ctx, pb, ubuf.empty() ? nullptr : ubuf.data(), zbuf.data(), ybuf.data())) != SMM_OK) break;
-    SMM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    // scatter into the Julia layouts us[Nx,Ny,2,L,nsave,B], zs[2,2,nsave,B], ys[2,L,nsave,B]
-    for (int b = 0; b < B; b++) {
-      if (us) memcpy(us + ((size_t)b * nsave + m) * per, ubuf.data() + (size_t)b * per, per * 8);
-      if (zs) memcpy(zs + ((size_t)b * nsave + m) * 4, zbuf.data() + (size_t)b * 4, 4 * 8);
-      if (ys) memcpy(ys + ((size_t)b * nsave + m) * 2 * L, ybuf.data() + (size_t)b * 2 * L, (size_t)2 * L * 8);
-    }
-    if (sum_us) {
-      double* o = sum_us + (size_t)m * per;
-      for (size_t e = 0; e < per; e++) { double s = 0; for (int b = 0; b < B; b++) s += ubuf[(size_t)b * per + e]; o[e] = s; }
-    }
-    if (sum_zs) for (int e = 0; e < 4; e++) { double s = 0; for (int b = 0; b < B; b++) s += zbuf[(size_t)b * 4 + e]; sum_zs[(size_t)m * 4 + e] = s; }
-    if (sum_ys) for (int e = 0; e < 2 * L; e++) { double s = 0; for (int b = 0; b < B; b++) s += ybuf[(size_t)b * 2 * L + e]; sum_ys[(size_t)m * 2 * L + e] = s; }
+    if ((rc = record_snapshot(ctx, pb, m, nsave, us, zs, ys, sum_us, sum_zs, sum_ys, ubuf, zbuf, ybuf)) != SMM_OK) break;
+  }
+  if (rc == SMM_OK) { cudaStreamSynchronize(ctx->stream); smm_collect_times(ctx); }
+  pde_free(pb);
+  return rc;
+}
+
+extern "C" int smm_pde_solve_adaptive(smm_ctx* ctx, const smm_grid* grid, const smm_params* q, int32_t B, int32_t L,
+                                      int32_t precision, const double* controlled_inf, const double* controlled_med,
+                                      const double* u0, const double* z0, const double* y0, const smm_adapt* opt,
+                                      int32_t nsave, const double* savetimes, double* us, double* zs, double* ys,
+                                      double* sum_us, double* sum_zs, double* sum_ys, int64_t* naccept, int64_t* nreject) {
+  SMM_REQUIRE(ctx, ctx != nullptr, "smm_pde_solve_adaptive: ctx is NULL");
+  SMM_REQUIRE(ctx, opt != nullptr, "smm_pde_solve_adaptive: options missing");
+  SMM_REQUIRE(ctx, nsave >= 1 && savetimes, "smm_pde_solve_adaptive: need at least one save time");
+  for (int m = 0; m < nsave; m++) {
+    SMM_REQUIRE(ctx, savetimes[m] >= 0, "smm_pde_solve_adaptive: savetimes[%d]=%g is negative", m, savetimes[m]);
+    SMM_REQUIRE(ctx, m == 0 || savetimes[m] > savetimes[m - 1], "smm_pde_solve_adaptive: savetimes must be strictly ascending");
+  }
+  smm_pde_batch* pb = nullptr;
+  SMM_TRY(smm_pde_batch_create(ctx, grid, q, B, L, precision, controlled_inf, controlled_med, u0, z0, y0, 0, &pb));
+  int rc = SMM_OK;
+  std::vector<double> ubuf, zbuf((size_t)B * 4), ybuf((size_t)B * 2 * L);
+  if (us || sum_us) ubuf.resize((size_t)B * pb->host_per);
+  std::vector<int64_t> na(B), nr(B);
+  if (naccept) memset(naccept, 0, (size_t)B * 8);
+  if (nreject) memset(nreject, 0, (size_t)B * 8);
+  for (int m = 0; m < nsave && rc == SMM_OK; m++) {
+    if ((rc = smm_pde_batch_advance(ctx, pb, savetimes[m], opt, na.data(), nr.data(), nullptr)) != SMM_OK) break;
+    for (int b = 0; b < B; b++) { if (naccept) naccept[b] += na[b]; if (nreject) nreject[b] += nr[b]; }
+    if ((rc = record_snapshot(ctx, pb, m, nsave, us, zs, ys, sum_us, sum_zs, sum_ys, ubuf, zbuf, ybuf)) != SMM_OK) break;
   }
   if (rc == SMM_OK) { cudaStreamSynchronize(ctx->stream); smm_collect_times(ctx); }
   pde_free(pb);

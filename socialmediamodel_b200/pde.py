@@ -161,6 +161,17 @@ class PDEBatch:
         self.ctx.check(self.ctx.lib.smm_pde_batch_step(self.ctx.h, self.h, float(dt), int(nsteps), _lib.SCHEME[scheme]),
                        "smm_pde_batch_step")
 
+    def advance(self, t_end, *, abstol=1e-6, reltol=1e-3, dt0=0.0, dtmin=0.0, dtmax=0.0, force_dtmin=False,
+                max_attempts=0):
+        """Adaptive integration of every instance to the absolute time ``t_end`` (smm_pde_batch_advance; the
+        tolerances / dtmin / force_dtmin keywords of the reference's solve calls, controlstrategies.jl:10,96).
+        Returns (accepted, rejected, next_dt) per instance."""
+        opt = _lib.make_adapt(abstol, reltol, dt0, dtmin, dtmax, force_dtmin, max_attempts)
+        na = np.zeros(self.B, np.int64); nr = np.zeros(self.B, np.int64); dn = np.zeros(self.B)
+        self.ctx.check(self.ctx.lib.smm_pde_batch_advance(self.ctx.h, self.h, float(t_end), C.byref(opt), _lib.ptr(na),
+                                                          _lib.ptr(nr), _lib.ptr(dn)), "smm_pde_batch_advance")
+        return na, nr, dn
+
     def read(self, want_u=True):
         Nx, Ny, L, B = self.p.N_x, self.p.N_y, self.L, self.B
         u = np.empty((Nx, Ny, 2, L, B), order="F") if want_u else None
@@ -236,14 +247,60 @@ def pde_solve_raw(p, qs, u0, z0, y0, *, dt, nsteps, savesteps, scheme="rk4", pre
     return out
 
 
+def pde_solve_adaptive_raw(p, qs, u0, z0, y0, *, savetimes, abstol=1e-6, reltol=1e-3, dt0=0.0, dtmin=0.0, dtmax=0.0,
+                           force_dtmin=False, max_attempts=0, precision="f32", want_sums=False, ctx=None):
+    """smm_pde_solve_adaptive: like pde_solve_raw, with states recorded at the times ``savetimes`` and
+    per-instance accepted / rejected step counts in ``naccept`` / ``nreject``."""
+    ctx = _lib.Context.default() if ctx is None else ctx
+    qs = list(qs)
+    B, L = len(qs), int(qs[0].L)
+    Nx, Ny = p.N_x, p.N_y
+    savetimes = np.ascontiguousarray(savetimes, np.float64)
+    ns = len(savetimes)
+    uu = _lib.f_array(np.asarray(u0, float).reshape((Nx, Ny, 2, L, B), order="F"), np.float64)
+    zz = _lib.f_array(np.asarray(z0, float).reshape((2, 2, B), order="F"), np.float64)
+    yy = _lib.f_array(np.asarray(y0, float).reshape((2, L, B), order="F"), np.float64)
+    us = np.empty((Nx, Ny, 2, L, ns, B), order="F"); zs = np.empty((2, 2, ns, B), order="F"); ys = np.empty((2, L, ns, B), order="F")
+    su = np.empty((Nx, Ny, 2, L, ns), order="F") if want_sums else None
+    sz = np.empty((2, 2, ns), order="F") if want_sums else None
+    sy = np.empty((2, L, ns), order="F") if want_sums else None
+    na = np.zeros(B, np.int64); nr = np.zeros(B, np.int64)
+    ci, cm = _controls(qs, L)
+    g = _lib.make_grid(p)
+    pa = _params_array(qs, p)
+    opt = _lib.make_adapt(abstol, reltol, dt0, dtmin, dtmax, force_dtmin, max_attempts)
+    rc = ctx.lib.smm_pde_solve_adaptive(ctx.h, C.byref(g), pa, B, L, _lib.PREC[precision], _lib.ptr(ci), _lib.ptr(cm),
+                                        _lib.ptr(uu), _lib.ptr(zz), _lib.ptr(yy), C.byref(opt), ns, _lib.ptr(savetimes),
+                                        _lib.ptr(us), _lib.ptr(zs), _lib.ptr(ys), _lib.ptr(su), _lib.ptr(sz), _lib.ptr(sy),
+                                        _lib.ptr(na), _lib.ptr(nr))
+    ctx.check(rc, "smm_pde_solve_adaptive")
+    out = dict(us=us, zs=zs, ys=ys, naccept=na, nreject=nr, t=savetimes)
+    if want_sums:
+        out.update(sum_us=su, sum_zs=sz, sum_ys=sy)
+    return out
+
+
 def PDEsolve(tmax=0.1, *, alg=None, init="4inf", p=None, q=None, dt=None, scheme="rk4", precision="f32",
-             nsaves=101, rng=None, ctx=None):
-    """pde.jl:285-294.  ``alg`` is accepted for signature compatibility; integration is the fixed-step
-    ``scheme`` with step ``dt`` (default: default_dt).  Returns (sol, (p, q)) with q augmented by
-    controlled_inf / controlled_med as in the reference (pde.jl:178)."""
+             nsaves=101, rng=None, ctx=None, adaptive=False, abstol=1e-6, reltol=1e-3, dtmin=0.0, force_dtmin=False,
+             saveat=None):
+    """pde.jl:285-294.  Returns (sol, (p, q)) with q augmented by controlled_inf / controlled_med as in the
+    reference (pde.jl:178).  Integration: by default the fixed-step ``scheme`` with step ``dt`` (default:
+    default_dt); with ``adaptive=True`` (or ``alg="BS3"``) the embedded 3(2) pair with per-instance step control
+    and the reference's ``abstol`` / ``reltol`` / ``dtmin`` / ``force_dtmin`` / ``saveat`` keywords
+    (controlstrategies.jl:10).  Any other ``alg`` is accepted for signature compatibility and ignored."""
     p = PDEconstruct() if p is None else p
     q = parameters() if q is None else q
     uzy0, q = constructinitial(init, (p, q), rng)
+    if adaptive or (isinstance(alg, str) and alg.upper() in ("BS3", "ADAPTIVE")):
+        times = np.linspace(0.0, tmax, nsaves) if saveat is None else np.asarray(saveat, float)
+        u0, z0, y0 = uzy0.x
+        out = pde_solve_adaptive_raw(p, [q], u0, z0, y0, savetimes=times, abstol=abstol, reltol=reltol, dtmin=dtmin,
+                                     force_dtmin=force_dtmin, precision=precision, ctx=ctx)
+        states = [ArrayPartition(out["us"][:, :, :, :, m, 0], out["zs"][:, :, m, 0], out["ys"][:, :, m, 0])
+                  for m in range(len(times))]
+        sol = PDESolution(times, states)
+        sol.naccept, sol.nreject = int(out["naccept"][0]), int(out["nreject"][0])
+        return sol, (p, q)
     dt = default_dt(p, q) if dt is None else dt
     nsteps = max(1, int(np.ceil(tmax / dt - 1e-9)))
     dt = tmax / nsteps
