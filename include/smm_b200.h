@@ -236,7 +236,8 @@ int smm_pde_batch_destroy(smm_ctx* ctx, smm_pde_batch* pb);
  * Bogacki-Shampine scheme c = (0, 1/2, 3/4), b = (2/9, 1/3, 4/9), with the 2nd-order midpoint solution
  * b* = (0, 1, 0) as error estimator).  Every instance carries its own clock and step size on the device:
  * err = dt * sum_i (b_i - b*_i) k_i, norm = sqrt(mean((err / (abstol + reltol * max(|u_n|, |u_n+1|)))^2))
- * over all density values and ODE unknowns, accept if norm <= 1, next dt = dt * clamp(0.9 norm^(-1/3), 0.2, 5);
+ * over all density values and ODE unknowns, accept if norm <= 1, next dt = dt * clamp(fac, 0.2, 5) with fac = 0.9 norm^(-7/30) prev^(2/15) after an accepted
+ * step (PI control) and 0.9 norm^(-1/3) after a rejected one, no growth right after a rejection;
  * steps are shortened to land exactly on the requested output times. */
 typedef struct {
   double abstol, reltol;   /* DifferentialEquations defaults: 1e-6, 1e-3 */

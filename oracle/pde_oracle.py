@@ -315,13 +315,14 @@ def bs3_adaptive(u0, z0, y0, savetimes, p, q, ci=None, cm=None, abstol=1e-6, rel
     controlstrategies.jl:10,96: abstol, reltol, dtmin, force_dtmin, saveat) on the explicit 3-stage
     Bogacki-Shampine scheme c=(0,1/2,3/4), b=(2/9,1/3,4/9) with the midpoint solution b*=(0,1,0) as error
     estimator: norm = sqrt(mean((err/(abstol+reltol*max(|u_n|,|u_n+1|)))^2)) over all density values and ODE
-    unknowns, accept if norm<=1, next dt = dt*clamp(0.9 norm^(-1/3), 0.2, 5), steps clipped to land on the
+    unknowns, accept if norm<=1, next dt = dt*clamp(fac, 0.2, 5) with fac = 0.9 norm^(-7/30) prev^(2/15) after an accepted step (PI control, prev = norm
+    of the previous accepted step) and 0.9 norm^(-1/3) after a rejected one (no growth right after a rejection), steps clipped to land on the
     save times.  (DifferentialEquations.jl itself is absent from the reference tree; only its call-site
     keywords are restated.)  Returns (list of (u,z,y) at savetimes, log of (t, dt, norm, accepted))."""
     u, z, y = u0.copy(), z0.copy(), y0.copy()
     D = 0.5 * float(q["sigma"]) ** 2
     dt_prop = dt0 if dt0 > 0 else (0.1 * min(p["dx"], p["dy"]) ** 2 / D if D > 0 else 1e-3)
-    t, out, log, attempts = 0.0, [], [], 0
+    t, out, log, attempts, rejected_last, errprev = 0.0, [], [], 0, False, 1e-4
     ntot = u.size + z.size + y.size
     for tend in savetimes:
         if dtmax > 0:
@@ -344,11 +345,19 @@ def bs3_adaptive(u0, z0, y0, savetimes, p, q, ci=None, cm=None, abstol=1e-6, rel
             if norm != norm:
                 fac = 0.2
             elif norm > 0:
-                fac = min(5.0, max(0.2, 0.9 * norm ** (-1.0 / 3.0)))
+                if accept:   # PI control on accepted steps (beta1 = 7/30, beta2 = 2/15), I control on rejected ones
+                    fac = 0.9 * norm ** (-7.0 / 30.0) * errprev ** (2.0 / 15.0)
+                else:
+                    fac = 0.9 * norm ** (-1.0 / 3.0)
+                fac = min(5.0, max(0.2, fac))
             else:
                 fac = 5.0
+            if rejected_last:
+                fac = min(fac, 1.0)      # no growth right after a rejection
+            rejected_last = not accept
             log.append((t, dt, norm, accept))
             if accept:
+                errprev = max(norm, 1e-4)
                 t = tend if clipped else t + dt
                 u, z, y = new
                 dt_prop = max(dt_prop, dt * fac) if clipped else dt * fac

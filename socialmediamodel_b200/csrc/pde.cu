@@ -47,7 +47,7 @@ struct PdeOde {  // RK bookkeeping of the ODE unknowns
 // Written only by the CTA that finalises the instance in the last stage kernel of an attempt (and by the
 // host between calls); read by every CTA of the following kernels.
 struct PdeCtl {
-  double t, tend, dt_prop, dt_try, dtmin, dtmax, abstol, reltol, errnorm, ntot;
+  double t, tend, dt_prop, dt_try, dtmin, dtmax, abstol, reltol, errnorm, errprev, ntot;
   long long naccept, nreject;
   int cur;         // which of the two ping-pong buffers (u, Ua) holds the current state
   int done;        // reached tend (or failed): all kernels skip the instance
@@ -195,7 +195,7 @@ __device__ void finalize_instance(const StageArgs& A, int b, int nblk, int mode,
 // err = dt * sum_i (b_i - b*_i) k_i of the 3(2) pair; norm = sqrt(mean((err / (abstol + reltol*max(|u_n|,|u_n+1|)))^2))
 // over all density values and ODE unknowns (the DifferentialEquations.jl norm, call sites pde.jl:291,
 // controlstrategies.jl:10,96: abstol / reltol / dtmin / force_dtmin).  Accept if norm <= 1; the next step is
-// dt * clamp(0.9 norm^(-1/3), 0.2, 5).  The per-CTA partial sums are added in a fixed order (deterministic).
+// dt * clamp(fac, 0.2, 5) with the PI / I factors below.  The per-CTA partial sums are added in a fixed order (deterministic).
 __device__ void adaptive_controller(const StageArgs& A, int b, int nblk, const double* s_err) {
   const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
   __shared__ double red[BX * BY];
@@ -219,8 +219,16 @@ __device__ void adaptive_controller(const StageArgs& A, int b, int nblk, const d
   const bool accept = (norm <= 1.0) || (c.force_dtmin && at_min);
   double fac = 5.0;
   if (!(norm == norm)) fac = 0.2;  // NaN
-  else if (norm > 0.0) fac = fmin(5.0, fmax(0.2, 0.9 / cbrt(norm)));
+  else if (norm > 0.0) {
+    // accepted steps: PI control (Gustafsson; the exponents OrdinaryDiffEq uses for a 3rd-order method,
+    // beta1 = 7/30, beta2 = 2/15) — an explicit scheme on this diffusion problem runs at its stability
+    // limit, where the plain I-controller cycles between growth and rejection; rejected steps: I control
+    fac = accept ? 0.9 * pow(norm, -7.0 / 30.0) * pow(c.errprev, 2.0 / 15.0) : 0.9 / cbrt(norm);
+    fac = fmin(5.0, fmax(0.2, fac));
+  }
+  if (c.need_init) fac = fmin(fac, 1.0);  // no growth right after a rejection
   if (accept) {
+    c.errprev = fmax(norm, 1e-4);
     c.t = c.clipped ? c.tend : c.t + c.dt_try;
     c.cur ^= 1;
     c.need_init = 0;
@@ -1157,6 +1165,7 @@ extern "C" int smm_pde_batch_advance(smm_ctx* ctx, smm_pde_batch* pb, double t_e
       const double h2 = std::min(pb->grid.dx, pb->grid.dy) * std::min(pb->grid.dx, pb->grid.dy);
       c.dt_prop = opt->dt0 > 0 ? opt->dt0 : (inst[b].D > 0 ? 0.1 * h2 / inst[b].D : 1e-3);
       c.ntot = (double)pb->host_per + 2.0 * (pb->L + 2);
+      c.errprev = 1e-4;
     }
   }
   const int64_t max_attempts = opt->max_attempts > 0 ? opt->max_attempts : 1000000;
