@@ -6,14 +6,17 @@ objective (follower share integrated over time, L2 norm of the control speed) fo
 and ``fixedtargets_objectives`` evaluates many candidate strategies at once as ONE device-resident batch
 (the ensemble axis of smm_pde_solve), which is what a multistart search needs.
 
-Time integration: the reference uses the adaptive default solver with dtmin (controlstrategies.jl:10,96); here
-the fixed-step RK4 graph with a step that divides ``savedt``.  Reference quirks kept: with
+Time integration: the reference uses the adaptive default solver with abstol / reltol / dtmin / force_dtmin and
+saveat = 0:savedt:T (controlstrategies.jl:10,96).  ``integrator="adaptive"`` maps those keywords onto the
+device-side embedded 3(2) integrator (smm_pde_solve_adaptive; every candidate of a batch has its own step
+control); the default ``integrator="fixed"`` is the fixed-step RK4 graph with a step that divides ``savedt``
+(bitwise reproducible against the oracle).  Reference quirks kept: with
 countercontrol="no" the added influencer carries flag 3 and therefore moves towards controltarget2 at
 controlspeed2 (pde.jl:249-255), not towards ``targets`` (controlstrategies.jl:16,92).
 """
 import numpy as np
 
-from .pde import ArrayPartition, PDESolution, constructinitial, default_dt, pde_solve_raw
+from .pde import ArrayPartition, PDESolution, constructinitial, default_dt, pde_solve_adaptive_raw, pde_solve_raw
 from .setting import PDEconstruct, PDEconstructcoarse, parameterscontrol, parametersstronginf
 
 
@@ -24,23 +27,37 @@ def _segment_steps(T, savedt, dt):
     return nsave, per, savedt / per
 
 
-def _solve_segments(p, qs, u0, z0, y0, T, savedt, dt, precision, ctx):
-    """integrate B instances over [0,T], saving every savedt (both ends, like saveat=0:savedt:T)."""
+def _solve_segments(p, qs, u0, z0, y0, T, savedt, dt, precision, ctx, adapt=None):
+    """integrate B instances over [0,T], saving every savedt (both ends, like saveat=0:savedt:T).
+    adapt = None: fixed step; else dict(atol, rtol, dtmin) for the adaptive integrator (force_dtmin = true)."""
     nsave, per, h = _segment_steps(T, savedt, dt)
+    if adapt is not None:
+        times = np.arange(nsave + 1) * savedt
+        out = pde_solve_adaptive_raw(p, qs, u0, z0, y0, savetimes=times, abstol=adapt["atol"], reltol=adapt["rtol"],
+                                     dtmin=adapt["dtmin"], force_dtmin=True, precision=precision, ctx=ctx)
+        return out, times
     savesteps = (np.arange(nsave + 1) * per).astype(np.int32)
     out = pde_solve_raw(p, qs, u0, z0, y0, dt=h, nsteps=nsave * per, savesteps=savesteps, precision=precision, ctx=ctx)
     return out, savesteps * h
 
 
-def prep(tequil=5.0, *, p=None, q=None, r=None, init="uniform", savedt=0.05, dtmin=0.001, countercontrol="no",
-         returnsol=False, dt=None, precision="f32", ctx=None):
+def _adapt(integrator, atol, rtol, dtmin):
+    if integrator == "fixed":
+        return None
+    if integrator != "adaptive":
+        raise ValueError(f"unknown integrator {integrator!r}")
+    return dict(atol=atol, rtol=rtol, dtmin=dtmin)
+
+
+def prep(tequil=5.0, *, p=None, q=None, r=None, init="uniform", savedt=0.05, atol=1e-6, rtol=1e-3, dtmin=0.001,
+         countercontrol="no", returnsol=False, dt=None, precision="f32", ctx=None, integrator="fixed"):
     """controlstrategies.jl:5-63: equilibrate for tequil, then append the controlled influencer(s)."""
     p = PDEconstruct() if p is None else p
     q = parametersstronginf() if q is None else q
     r = parameterscontrol() if r is None else r
     uzy0, q1 = constructinitial(init, (p, q))
     dt = default_dt(p, q1) if dt is None else dt
-    out, ts = _solve_segments(p, [q1], *uzy0.x, tequil, savedt, dt, precision, ctx)
+    out, ts = _solve_segments(p, [q1], *uzy0.x, tequil, savedt, dt, precision, ctx, _adapt(integrator, atol, rtol, dtmin))
     sol1 = PDESolution(ts, [ArrayPartition(out["us"][..., m, 0], out["zs"][..., m, 0], out["ys"][..., m, 0]) for m in range(len(ts))])
     u, z, y = sol1.u[-1].x
     Lold = q1.L
@@ -75,8 +92,9 @@ def prep(tequil=5.0, *, p=None, q=None, r=None, init="uniform", savedt=0.05, dtm
     return uzy, startlocation, (p, q2), startlocationmed, sol1, (p, q1)
 
 
-def fixedtargets_objectives(ts, targets_list, startlocation, pq, r, uzy0, *, savedt=0.05, dtmin=0.001, countercontrol="no",
-                            stubborntarget=None, startlocationmed=None, returnsol=False, dt=None, precision="f32", ctx=None):
+def fixedtargets_objectives(ts, targets_list, startlocation, pq, r, uzy0, *, savedt=0.05, atol=1e-6, rtol=1e-3, dtmin=0.001,
+                            countercontrol="no", stubborntarget=None, startlocationmed=None, returnsol=False, dt=None,
+                            precision="f32", ctx=None, integrator="fixed"):
     """PDEsolvefixedtargetsfast (controlstrategies.jl:67-115) for K candidate strategies at once: targets_list[k]
     is a (2, n_targets) array.  Returns followersum[K], speedpenalty[K] (and the per-candidate sols/Ps)."""
     p, q = pq
@@ -102,7 +120,7 @@ def fixedtargets_objectives(ts, targets_list, startlocation, pq, r, uzy0, *, sav
             qs.append(q.merge(controltarget1=target, controlspeed1=speed))
             speedpen[k] += speed ** 2 * Dt
             start[k] = target
-        out, tsave = _solve_segments(p, qs, u, z, y, Dt, savedt, dt, precision, ctx)
+        out, tsave = _solve_segments(p, qs, u, z, y, Dt, savedt, dt, precision, ctx, _adapt(integrator, atol, rtol, dtmin))
         us = out["us"]                                                       # [Nx,Ny,2,L,nsave,K]
         share = us[:, :, :, L - 1].sum(axis=(0, 1, 2)) / us.sum(axis=(0, 1, 2, 3))   # [nsave, K]
         followersum += share.sum(axis=0) * savedt                            # controlstrategies.jl:98
@@ -118,30 +136,33 @@ def fixedtargets_objectives(ts, targets_list, startlocation, pq, r, uzy0, *, sav
 
 def PDEsolvefixedtargetsfast(ts, targets, startlocation, pq, r, uzy0, *, savedt=0.05, atol=1e-6, rtol=1e-3, dtmin=0.001,
                              countercontrol="no", stubborntarget=None, startlocationmed=None, returnsol=False, dt=None,
-                             precision="f32", ctx=None):
-    """controlstrategies.jl:67-115 (atol/rtol accepted and ignored: fixed-step integration)."""
-    res = fixedtargets_objectives(ts, [targets], startlocation, pq, r, uzy0, savedt=savedt, dtmin=dtmin,
+                             precision="f32", ctx=None, integrator="fixed"):
+    """controlstrategies.jl:67-115 (atol / rtol / dtmin are used by integrator="adaptive")."""
+    res = fixedtargets_objectives(ts, [targets], startlocation, pq, r, uzy0, savedt=savedt, atol=atol, rtol=rtol, dtmin=dtmin,
                                   countercontrol=countercontrol, stubborntarget=stubborntarget,
-                                  startlocationmed=startlocationmed, returnsol=returnsol, dt=dt, precision=precision, ctx=ctx)
+                                  startlocationmed=startlocationmed, returnsol=returnsol, dt=dt, precision=precision, ctx=ctx,
+                                  integrator=integrator)
     if returnsol:
         return float(res[0][0]), float(res[1][0]), res[2][0], res[3][0]
     return float(res[0][0]), float(res[1][0])
 
 
 def PDEsolvefixedtargets(targets, *, p=None, q=None, r=None, init="uniform", countercontrol="no", stubborntarget=(1.5, 1.5),
-                         savedt=0.05, dt=None, precision="f32", ctx=None):
+                         savedt=0.05, dt=None, precision="f32", ctx=None, integrator="fixed"):
     """controlstrategies.jl:120-132."""
     p = PDEconstructcoarse() if p is None else p
     q = parametersstronginf() if q is None else q
     r = parameterscontrol(ntarg=1, start="zero") if r is None else r
     ntarg, Tmax, tequil = r.ntarg, r.Tmax, r.tequil
+    dtmin = r.get("dtmin", 0.001)
     ts = np.concatenate([[0.0], Tmax / ntarg * np.arange(1, ntarg + 1)])
     targets = np.asarray(targets, float).reshape((2, ntarg), order="F")
     uzy0, startlocation, (p, q2), slm, sol1, (p, q1) = prep(tequil, p=p, q=q, r=r, init=init, savedt=savedt,
                                                             countercontrol=countercontrol, returnsol=True, dt=dt,
-                                                            precision=precision, ctx=ctx)
+                                                            precision=precision, ctx=ctx, integrator=integrator, dtmin=dtmin)
     fs, sp, sols, Ps = PDEsolvefixedtargetsfast(ts, targets, startlocation, (p, q2), r, uzy0, savedt=savedt,
                                                 countercontrol=countercontrol,
                                                 stubborntarget=np.asarray(stubborntarget, float).reshape(1, 2),
-                                                startlocationmed=slm, returnsol=True, dt=dt, precision=precision, ctx=ctx)
+                                                startlocationmed=slm, returnsol=True, dt=dt, precision=precision, ctx=ctx,
+                                                integrator=integrator, dtmin=dtmin)
     return fs, sp, [sol1] + sols, [(p, q1)] + Ps

@@ -190,4 +190,29 @@ function PDEsolveensemble(tmax = 0.1, N = 10; savepoints = 4, alg = nothing, ini
     return us, zs, ys, P
 end
 
+# ---- adaptive integration (smm_pde_solve_adaptive): the keywords of the reference's solve calls
+#      (pde.jl:291; controlstrategies.jl:10,96) on the device-side embedded 3(2) pair ----------------------
+struct SmmAdapt
+    abstol::Float64; reltol::Float64; dt0::Float64; dtmin::Float64; dtmax::Float64
+    force_dtmin::Int32; max_attempts::Int32
+end
+
+function PDEsolveadaptive(tmax = 0.1; init = "4inf", p = PDEconstruct(), q = parameters(), saveat = LinRange(0, tmax, 101),
+                          abstol = 1e-6, reltol = 1e-3, dtmin = 0.0, force_dtmin = false, precision = PREC_F32)
+    uzy0, qa = constructinitial(init, (p, q)); L = qa.L
+    times = collect(Float64, saveat); ns = length(times)
+    us = zeros(p.N_x, p.N_y, 2, L, ns, 1); zs = zeros(2, 2, ns, 1); ys = zeros(2, L, ns, 1)
+    nacc = zeros(Int64, 1); nrej = zeros(Int64, 1)
+    opt = SmmAdapt(abstol, reltol, 0.0, dtmin, 0.0, force_dtmin ? 1 : 0, 0)
+    check(ccall((:smm_pde_solve_adaptive, LIB), Cint,
+                (Ptr{Cvoid}, Ref{SmmGrid}, Ptr{SmmParams}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{SmmAdapt}, Int32, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}),
+                ctx(), grid(p), [params(qa, p)], 1, L, precision, Float64.(collect(qa.controlled_inf)),
+                Float64.(collect(qa.controlled_med)), uzy0.x[1], uzy0.x[2], uzy0.x[3], opt, ns, times,
+                us, zs, ys, C_NULL, C_NULL, C_NULL, nacc, nrej), "smm_pde_solve_adaptive")
+    states = [ArrayPartition(us[:, :, :, :, m, 1], zs[:, :, m, 1], ys[:, :, m, 1]) for m in 1:ns]
+    return FixedStepSolution(times, states), (p, qa)
+end
+
 end # module

@@ -62,3 +62,33 @@ def test_batched_candidate_strategies_equal_single_evaluations():
                                               stubborntarget=[1.5, 1.5], precision="f64")
         assert abs(fb[k] - f1) < 1e-13 and abs(pb[k] - p1) < 1e-13
     assert len(set(np.round(fb, 12))) == 3                                 # different strategies, different objectives
+
+
+@pytest.mark.parametrize("cc", ["no", "inf", "med"])
+def test_adaptive_integrator_with_reference_keywords(cc):
+    """integrator="adaptive": the reference's atol / rtol / dtmin / force_dtmin semantics
+    (controlstrategies.jl:10,96) on the device-side embedded pair.  The objective agrees with the fixed-step
+    evaluation within the requested tolerance, and a batch of candidates with its single evaluations."""
+    p = smm.PDEconstructcoarse()
+    q = smm.parametersstronginf()
+    r = smm.parameterscontrol(ntarg=2, start="zero", Tmax=0.1, tequil=0.05, dtmin=1e-4)
+    targets = np.array([[0.3, 0.3], [-0.5, 0.8]]).T
+    kw = dict(p=p, q=q, r=r, countercontrol=cc, stubborntarget=[1.5, 1.5], savedt=0.01)
+    ff, sf, solf, _ = smm.PDEsolvefixedtargets(targets.reshape(-1, order="F"), dt=2.5e-4, precision="f64", **kw)
+    for precision in ("f64", "f32"):
+        fa, sa, sola, _ = smm.PDEsolvefixedtargets(targets.reshape(-1, order="F"), precision=precision, integrator="adaptive", **kw)
+        assert abs(sa - sf) < 1e-4          # "med": the start location is the equilibrated medium position
+        assert abs(fa - ff) < 5e-3 * abs(ff) + 1e-6, (fa, ff)
+        ua, uf = sola[-1](0.05).x[0], solf[-1](0.05).x[0]
+        assert np.abs(ua - uf).max() / np.abs(uf).max() < 1e-2
+        assert np.abs(sola[-1](0.05).x[2] - solf[-1](0.05).x[2]).max() < 1e-2
+    uzy0, sl, (p2, q2), slm = smm.prep(0.05, p=p, q=q, r=r, savedt=0.01, countercontrol=cc, precision="f64", integrator="adaptive",
+                                       dtmin=1e-4)
+    ts = [0.0, 0.05, 0.1]
+    cands = [targets, np.array([[1.0, -1.0], [0.0, 0.0]]).T]
+    fb, pb = smm.fixedtargets_objectives(ts, cands, sl, (p2, q2), r, uzy0, savedt=0.01, countercontrol=cc, dtmin=1e-4,
+                                         stubborntarget=[1.5, 1.5], startlocationmed=slm, precision="f64", integrator="adaptive")
+    for k, c in enumerate(cands):
+        f1, p1 = smm.PDEsolvefixedtargetsfast(ts, c, sl, (p2, q2), r, uzy0, savedt=0.01, countercontrol=cc, dtmin=1e-4,
+                                              stubborntarget=[1.5, 1.5], startlocationmed=slm, precision="f64", integrator="adaptive")
+        assert abs(fb[k] - f1) < 1e-9 and abs(pb[k] - p1) < 1e-13

@@ -177,3 +177,27 @@ def test_rk4_converged_against_adaptive(coarse):
     s = np.abs(ua).max()
     assert np.abs(u1 - u2).max() / s < 1e-5
     assert np.abs(u2 - ua).max() / s < 1e-6
+
+
+def test_bs3_adaptive_controller(coarse):
+    """The embedded 3(2) pair and its controller (what csrc/pde.cu runs on the device): lands on the save
+    times, error follows the tolerance against the SciPy DOP853 solve, forced dtmin steps terminate (a step
+    shortened below dtmin to reach the save time is accepted too), an unforced failure at dtmin raises."""
+    p, q, (u0, z0, y0, ci, cm) = coarse
+    T = 0.04
+    ua, za, ya = P.adaptive_solve(u0, z0, y0, T, p, q, ci, cm)
+    s = np.abs(ua).max()
+    errs, work = [], []
+    for rtol in (1e-2, 1e-4):
+        states, log = P.bs3_adaptive(u0, z0, y0, [0.0, T / 2, T], p, q, ci, cm, abstol=1e-3 * rtol, reltol=rtol)
+        np.testing.assert_array_equal(states[0][0], u0)                    # save_start
+        errs.append(np.abs(states[-1][0] - ua).max() / s)
+        work.append(len(log))
+        ts = [t for t, dt, n, acc in log if acc]
+        assert any(abs(t + dt - T / 2) < 1e-15 for t, dt, n, acc in log if acc)     # clipped onto the save time
+        assert all(n <= 1.0 for t, dt, n, acc in log if acc) and all(n > 1.0 for t, dt, n, acc in log if not acc)
+    assert errs[1] < errs[0] < 5e-2 and errs[1] < 1e-3 and work[1] > work[0]
+    states, log = P.bs3_adaptive(u0, z0, y0, [T], p, q, ci, cm, dtmin=4e-3, dt0=4e-3, force_dtmin=True)
+    assert len(log) == 10 and all(acc for *_, acc in log)
+    with pytest.raises(RuntimeError, match="dtmin"):
+        P.bs3_adaptive(u0, z0, y0, [T], p, q, ci, cm, dtmin=4e-3, dt0=4e-3, force_dtmin=False)
