@@ -12,7 +12,7 @@ from .ensemble import (ABMsolveensemble, PDEsolveensemble, abm_ensemble_raw, ens
                        savetimes_abm)
 from .pde import (ArrayPartition, PDEBatch, PDESolution, PDEsolve, constructinitial, default_dt, f, gaussian, pde_rhs,
                   pde_solve_adaptive_raw, pde_solve_raw, randominit, sol2uyz, uniforminit)
-from .control import PDEsolvefixedtargets, PDEsolvefixedtargetsfast, fixedtargets_objectives, prep
+from .control import PDEsolvefixedtargets, PDEsolvefixedtargetsfast, PDEsolveopt, fixedtargets_objectives, prep
 from .population import ABMPopulation
 from ._lib import Context, SmmError
 

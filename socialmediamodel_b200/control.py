@@ -166,3 +166,93 @@ def PDEsolvefixedtargets(targets, *, p=None, q=None, r=None, init="uniform", cou
                                                 startlocationmed=slm, returnsol=True, dt=dt, precision=precision, ctx=ctx,
                                                 integrator=integrator, dtmin=dtmin)
     return fs, sp, [sol1] + sols, [(p, q1)] + Ps
+
+
+def PDEsolveopt(*, p=None, q=None, r=None, alg="LN_COBYLA", mtime=1000, meval=-1, ftol_rel=1e-4, xtol_rel=1e-2, x0=None,
+                countercontrol="no", stubborntarget=None, multistart=False, save=True, savedt=0.05, dt=None, precision="f32",
+                ctx=None, integrator="fixed", nstarts=8, rng=None):
+    """controlstrategies.jl:137-209: maximise the follower objective over the 2*ntarg target coordinates.
+
+    The reference hands the objective to NLopt (COBYLA, optionally MLSL multistart), one evaluation at a time.
+    NLopt is not part of the reference tree and is not reproduced; what is kept is the problem (objective incl.
+    its quirk that alpha multiplies the speed penalty twice for maximize="follower", `:156,165`; box bounds =
+    the domain, `:186-189`; stopping rules mtime / meval / ftol_rel / xtol_rel, `:194-198`; return tuple `:206`)
+    and it is solved with a derivative-free compass search whose 2*ndim polling points per iteration are
+    evaluated as ONE device batch (`fixedtargets_objectives`).  multistart: `nstarts` low-discrepancy starting
+    points (the role of G_MLSL_LDS) are evaluated as one batch and the search starts from the best.
+    ``alg`` is accepted for signature compatibility.  Returns (maxf, maxx, ret, numevals, x_list,
+    followersum_list, penalty_list)."""
+    import time as _time
+    p = PDEconstructcoarse() if p is None else p
+    q = parametersstronginf() if q is None else q
+    r = parameterscontrol() if r is None else r
+    ntarg, Tmax, tequil, dtmin, maximize, alpha = r.ntarg, r.Tmax, r.tequil, r.dtmin, r.maximize, r.alpha
+    if maximize not in ("follower", "counter_follower"):
+        raise ValueError(f"This obj is unknown: {maximize!r}")
+    uzy0, startlocation, (p, q2), slm = prep(tequil, p=p, q=q, r=r, dtmin=dtmin, countercontrol=countercontrol, savedt=savedt,
+                                             dt=dt, precision=precision, ctx=ctx, integrator=integrator)
+    ts = np.concatenate([[0.0], Tmax / ntarg * np.arange(1, ntarg + 1)])
+    ndim = 2 * ntarg
+    lb, ub = float(p.domain[0, 0]), float(p.domain[0, 1])
+    x_list, followersum_list, penalty_list = [], [], []
+    t_start = _time.perf_counter()
+
+    def objective(X):
+        """objective of every row of X (one device batch); records the evaluations like Objfun (:148-171)"""
+        cands = [np.reshape(x, (2, ntarg), order="F") for x in X]
+        fs, sp = fixedtargets_objectives(ts, cands, startlocation, (p, q2), r, uzy0, savedt=savedt, dtmin=dtmin,
+                                         countercontrol=countercontrol, stubborntarget=stubborntarget, startlocationmed=slm,
+                                         dt=dt, precision=precision, ctx=ctx, integrator=integrator)
+        pen = alpha * sp
+        for x, f_, s_ in zip(X, fs, pen):
+            x_list.append(np.array(x)); followersum_list.append(float(f_)); penalty_list.append(float(s_))
+        return fs - alpha * pen if maximize == "follower" else -fs - pen
+
+    def budget_left(n):
+        if meval > 0 and len(x_list) + n > meval:
+            return False
+        return _time.perf_counter() - t_start < mtime
+
+    x = np.zeros(ndim) if x0 is None else np.clip(np.asarray(x0, float).ravel(), lb, ub)
+    if multistart:
+        try:
+            from scipy.stats import qmc
+            pts = qmc.scale(qmc.Sobol(ndim, seed=0 if rng is None else rng).random(nstarts), [lb] * ndim, [ub] * ndim)
+        except ImportError:
+            pts = np.random.default_rng(0 if rng is None else rng).uniform(lb, ub, (nstarts, ndim))
+        starts = np.vstack([x[None, :], pts])
+        fstart = objective(starts)
+        x, fx = starts[int(np.argmax(fstart))].copy(), float(np.max(fstart))
+    else:
+        fx = float(objective(x[None, :])[0])
+    step, ret = 0.25 * (ub - lb), "MAXEVAL_REACHED"
+    while True:
+        if step < xtol_rel * max(np.abs(x).max(), 1e-3 * (ub - lb)):
+            ret = "XTOL_REACHED"
+            break
+        poll = np.repeat(x[None, :], 2 * ndim, axis=0)
+        for i in range(ndim):
+            poll[2 * i, i] = min(ub, x[i] + step)
+            poll[2 * i + 1, i] = max(lb, x[i] - step)
+        poll = poll[np.any(poll != x[None, :], axis=1)]
+        if not budget_left(len(poll)):
+            ret = "MAXEVAL_REACHED" if (meval > 0 and len(x_list) + len(poll) > meval) else "MAXTIME_REACHED"
+            break
+        fp = objective(poll)
+        k = int(np.argmax(fp))
+        if fp[k] > fx:
+            gain = fp[k] - fx
+            x, fx = poll[k].copy(), float(fp[k])
+            if gain < ftol_rel * abs(fx):
+                ret = "FTOL_REACHED"
+                break
+        else:
+            step *= 0.5
+    numevals = len(x_list)
+    if save:
+        import os
+        os.makedirs("data", exist_ok=True)
+        name = f"data/opt_strategy{ntarg}{alg}{maximize}{r.start}{str(bool(multistart)).lower()}{countercontrol}.npz"   # :203-205
+        np.savez(name, maxf=fx, maxx=x, ret=ret, numevals=numevals, x_list=np.array(x_list),
+                 followersum_list=np.array(followersum_list), penalty_list=np.array(penalty_list))
+    return fx, x, ret, numevals, x_list, followersum_list, penalty_list

@@ -92,3 +92,28 @@ def test_adaptive_integrator_with_reference_keywords(cc):
         f1, p1 = smm.PDEsolvefixedtargetsfast(ts, c, sl, (p2, q2), r, uzy0, savedt=0.01, countercontrol=cc, dtmin=1e-4,
                                               stubborntarget=[1.5, 1.5], startlocationmed=slm, precision="f64", integrator="adaptive")
         assert abs(fb[k] - f1) < 1e-9 and abs(pb[k] - p1) < 1e-13
+
+
+def test_PDEsolveopt_batched_compass_search(tmp_path, monkeypatch):
+    """PDEsolveopt (controlstrategies.jl:137-209) on the batched objective: improves on the starting point, stays
+    inside the domain bounds, honours meval, records every evaluation, keeps the objective's alpha quirk."""
+    monkeypatch.chdir(tmp_path)
+    p = smm.PDEconstructcoarse()
+    q = smm.parametersstronginf()
+    r = smm.parameterscontrol(ntarg=1, start="zero", Tmax=0.1, tequil=0.02, alpha=0.05)
+    x0 = np.array([0.2, -0.1])
+    maxf, maxx, ret, numevals, xs, fsl, penl = smm.PDEsolveopt(p=p, q=q, r=r, x0=x0, countercontrol="inf", stubborntarget=[1.5, 1.5],
+                                                               meval=30, savedt=0.02, dt=1e-3, precision="f64", save=True)
+    assert numevals == len(xs) == len(fsl) == len(penl) <= 30 and numevals >= 5
+    obj = np.array(fsl) - r.alpha * np.array(penl)                       # follower: alpha enters twice (:156,165)
+    assert abs(maxf - obj.max()) < 1e-15 and maxf > obj[0]
+    assert np.all(np.abs(maxx) <= p.domain[0, 1]) and np.all(np.abs(np.array(xs)) <= p.domain[0, 1] + 1e-12)
+    np.testing.assert_array_equal(xs[0], x0)
+    # the recorded objective of the best point equals a fresh single evaluation
+    uzy0, sl, (p2, q2), slm = smm.prep(0.02, p=p, q=q, r=r, savedt=0.02, dt=1e-3, countercontrol="inf", precision="f64")
+    f1, s1 = smm.PDEsolvefixedtargetsfast([0.0, 0.1], maxx.reshape(2, 1), sl, (p2, q2), r, uzy0, savedt=0.02, dt=1e-3,
+                                          countercontrol="inf", stubborntarget=[1.5, 1.5], precision="f64")
+    assert abs((f1 - r.alpha * r.alpha * s1) - maxf) < 1e-12
+    assert ret in ("MAXEVAL_REACHED", "XTOL_REACHED", "FTOL_REACHED")
+    import os
+    assert os.path.exists("data/opt_strategy1LN_COBYLAfollowerzerofalseinf.npz")
