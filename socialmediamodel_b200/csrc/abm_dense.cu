@@ -13,7 +13,40 @@ namespace {
 
 constexpr int kThreads = 128;
 
-template <typename real>
+// Packed FP32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 — two FP32 operations per issue slot).
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+// 2^(-sqrt(r2)) for coordinates pre-scaled by log2(e): exp(-|x_i - x_j|) with two MUFU ops and nothing else
+__device__ __forceinline__ float w_of_scaled_r2(float r2) {
+  float r, w;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(r2));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(-r));
+  return w;
+}
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+// SYM: every unordered agent pair is evaluated once (w_ij = w_ji, abm.jl:59) — see phase P3.
+constexpr int kSymMaxGroups = 16;  // n <= 512: the per-offset partial sums must fit shared memory
+constexpr float kPadPos = 1e15f;   // padding agents of the last 32-group: exp(-|x - pad|) = 0 exactly
+
+template <typename real, bool SYM>
 __global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) {
   using real2 = typename vec2<real>::type;
   const AbmConst& K = A.k;
@@ -40,6 +73,13 @@ __global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) 
   float* finy = finx + L;                                  //     for the guarded FP32 switch decision
   float* ffr = finy + L;
   signed char* st = reinterpret_cast<signed char*>(ffr + L);  // [npad]
+  // SYM: positions once more, every 32-group stored twice in a row ([G][64]) so that the rotated partner
+  // index lane +- s needs no wrap-around arithmetic, and the partial sums [1 + D][G*32] x (ws, ax, ay)
+  const int G = (n + 31) >> 5, D = G >> 1, NG = G * 32;
+  // xs2[g][i] = log2(e) * (x of agent g*32 + (i & 31), x of agent g*32 + ((i + 16) & 31)), i < 64; ys2 likewise
+  float2* xs2 = reinterpret_cast<float2*>(smem + ((reinterpret_cast<unsigned char*>(st + npad) - smem + 15) & ~(size_t)15));
+  float2* ys2 = xs2 + (SYM ? G * 64 : 0);
+  float* part = reinterpret_cast<float*>(ys2 + (SYM ? G * 64 : 0));
 
   // ---- load the initial condition --------------------------------------------------------
   const real* x0 = static_cast<const real*>(A.x0) + (size_t)r * 2 * n;
@@ -119,6 +159,17 @@ __global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) 
     real2* xn = cur ? xbuf0 : xbuf1;
     const int nxt = cur ^ 1;
 
+    if constexpr (SYM) {
+      for (int j = tid; j < NG; j += kThreads) {
+        const real2 p = j < n ? xc[j] : mk2((real)kPadPos, (real)kPadPos);
+        const float sx = (float)p.x * kLog2e, sy = (float)p.y * kLog2e;
+        const int l = j & 31, l2 = (l + 16) & 31;
+        float2* ox = xs2 + (j >> 5) * 64;
+        float2* oy = ys2 + (j >> 5) * 64;
+        ox[l].x = sx; ox[l + 32].x = sx; ox[l2].y = sx; ox[l2 + 32].y = sx;
+        oy[l].x = sy; oy[l + 32].x = sy; oy[l2].y = sy; oy[l2 + 32].y = sy;
+      }
+    }
     // ---- P1: S_i, cnt_i, state sums of the OLD positions / followers (abm.jl:96-100,179-180,188-191)
     bin_sums(xc);
     __syncthreads();
@@ -205,6 +256,71 @@ __global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) 
       xn[j] = mk2((real)xn0, (real)xn1);
       fol[j] = fnew;  // only this thread reads fol[j] during P3
     };
+    if constexpr (SYM) {
+      // Attraction with every unordered pair evaluated once.  Agents are split into G groups of 32; a warp
+      // owns row groups g = warp, warp + 4, ..: lane l is agent g*32 + l.  For the group offsets d = 1..D the
+      // tile (g, h = g + d mod G) pairs row agent l with column agent (l + s) & 31 at rotation step s: the
+      // weight goes into the row agent's registers and, through one shuffle, to the lane that owns the column
+      // agent (which re-reads the row position from shared memory).  Offsets 1..D cover every unordered group
+      // pair exactly once (for even G the offset G/2 only from the lower half); the diagonal tile (g, g) is
+      // evaluated in ordered form and contains the self pair (abm.jl:42).  Every partial sum has its own
+      // shared-memory slot and is added in a fixed order: results are deterministic.
+      for (int g = warp; g < G; g += nwarps) {
+        const float2* rowx = xs2 + g * 64 + lane;
+        const float2* rowy = ys2 + g * 64 + lane;
+        const float rx = rowx[0].x, ry = rowy[0].x;
+        const float2 nrx = make_float2(-rx, -rx), nry = make_float2(-ry, -ry);
+        float2 ws2 = make_float2(0.f, 0.f), ax2 = ws2, ay2 = ws2;
+        // diagonal tile: lane l against all 32 agents of its own group, two partners per step
+#pragma unroll 8
+        for (int t = 0; t < 16; t++) {
+          const float2 dx = add2(rowx[t], nrx), dy = add2(rowy[t], nry);
+          const float2 r2 = fma2(dx, dx, mul2(dy, dy));
+          const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
+          ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
+        }
+        for (int d = 1; d <= D; d++) {
+          if (2 * d == G && g >= D) break;
+          int h = g + d;
+          if (h >= G) h -= G;
+          const float2* colx = xs2 + h * 64 + lane;
+          const float2* coly = ys2 + h * 64 + lane;
+          const float cx = colx[0].x, cy = coly[0].x;
+          const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy);
+          float2 cws2 = make_float2(0.f, 0.f), cax2 = cws2, cay2 = cws2;
+          // step t: row agent l with the column agents (l + t) & 31 and (l + t + 16) & 31; their weights go
+          // to the lanes that own those column agents, which pair them with the rows (l - t) & 31 and
+          // (l - t - 16) & 31 — stored next to each other at index l - t + 32
+#pragma unroll 8
+          for (int t = 0; t < 16; t++) {
+            const float2 dx = add2(colx[t], nrx), dy = add2(coly[t], nry);
+            const float2 r2 = fma2(dx, dx, mul2(dy, dy));
+            const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
+            ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
+            float2 wv;
+            wv.x = __shfl_sync(0xffffffffu, w.x, lane - t);
+            wv.y = __shfl_sync(0xffffffffu, w.y, lane - t - 16);
+            const float2 ex = add2(rowx[32 - t], ncx), ey = add2(rowy[32 - t], ncy);
+            cws2 = add2(cws2, wv); cax2 = fma2(wv, ex, cax2); cay2 = fma2(wv, ey, cay2);
+          }
+          float* o = part + (size_t)d * 3 * NG + h * 32 + lane;
+          o[0] = cws2.x + cws2.y; o[NG] = (cax2.x + cax2.y) * kLn2; o[2 * NG] = (cay2.x + cay2.y) * kLn2;
+        }
+        float* o = part + g * 32 + lane;
+        o[0] = ws2.x + ws2.y; o[NG] = (ax2.x + ax2.y) * kLn2; o[2 * NG] = (ay2.x + ay2.y) * kLn2;
+      }
+      __syncthreads();
+      for (int j = tid; j < n; j += kThreads) {
+        real ws = part[j], ax = part[NG + j], ay = part[2 * NG + j];
+        const int hg = j >> 5;
+        for (int d = 1; d <= D; d++) {
+          if (2 * d == G && hg < D) break;  // that slot is only written for the upper half of the groups
+          const real* o = part + (size_t)d * 3 * NG + j;
+          ws += o[0]; ax += o[NG]; ay += o[2 * NG];
+        }
+        finish(j, xc[j], ax, ay, ws);
+      }
+    } else
     for (int j0 = tid; j0 < n; j0 += 2 * kThreads) {
       const int j1 = j0 + kThreads;
       const bool has1 = j1 < n;
@@ -305,24 +421,35 @@ __global__ void abm_draws_kernel(int n, uint64_t seed, uint32_t realization, int
   u2[t] = d;
 }
 
-size_t dense_smem_bytes(int n, int L, int M, size_t real_size) {
+size_t dense_smem_bytes(int n, int L, int M, size_t real_size, bool sym) {
   int npad = (n + 3) & ~3;
-  return 2 * (size_t)npad * 2 * real_size + sizeof(double) * (4 * L + 4 * M + L + 2 * (L + M)) +
-         sizeof(int) * (2 * (L + M) + npad) + sizeof(float) * 3 * L + npad + 16;
+  size_t b = 2 * (size_t)npad * 2 * real_size + sizeof(double) * (4 * L + 4 * M + L + 2 * (L + M)) +
+             sizeof(int) * (2 * (L + M) + npad) + sizeof(float) * 3 * L + npad + 16;
+  if (sym) {
+    const size_t G = (n + 31) / 32, D = G / 2;
+    b += 16 + 2 * G * 64 * 8 + (1 + D) * 3 * G * 32 * 4;
+  }
+  return b;
 }
 
 }  // namespace
 
 int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
-  size_t sm = dense_smem_bytes(A.k.n, A.k.L, A.k.M, precision == SMM_PREC_F64 ? 8 : 4);
+  // FP32 all-to-all populations of up to 512 agents take the symmetric-pair path (SMM_ABM_SYM=0: ordered pairs)
+  const char* ev = getenv("SMM_ABM_SYM");
+  const bool sym = precision == SMM_PREC_F32 && A.rowptr == nullptr && (A.k.n + 31) / 32 <= kSymMaxGroups && !(ev && ev[0] == '0');
+  size_t sm = dense_smem_bytes(A.k.n, A.k.L, A.k.M, precision == SMM_PREC_F64 ? 8 : 4, sym);
   SMM_REQUIRE(ctx, sm <= 227 * 1024, "dense ABM kernel: n=%d does not fit shared memory (%zu B); pass a CSR network", A.k.n, sm);
   SMM_REQUIRE(ctx, A.k.L + A.k.M <= kThreads && A.k.L * A.k.M <= kThreads, "dense ABM kernel: L+M and L*M must be <= %d", kThreads);
   if (precision == SMM_PREC_F64) {
-    SMM_CUDA(ctx, cudaFuncSetAttribute(abm_dense_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    abm_dense_kernel<double><<<A.R, kThreads, sm, ctx->stream>>>(A);
+    SMM_CUDA(ctx, cudaFuncSetAttribute(abm_dense_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    abm_dense_kernel<double, false><<<A.R, kThreads, sm, ctx->stream>>>(A);
+  } else if (sym) {
+    SMM_CUDA(ctx, cudaFuncSetAttribute(abm_dense_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    abm_dense_kernel<float, true><<<A.R, kThreads, sm, ctx->stream>>>(A);
   } else {
-    SMM_CUDA(ctx, cudaFuncSetAttribute(abm_dense_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    abm_dense_kernel<float><<<A.R, kThreads, sm, ctx->stream>>>(A);
+    SMM_CUDA(ctx, cudaFuncSetAttribute(abm_dense_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    abm_dense_kernel<float, false><<<A.R, kThreads, sm, ctx->stream>>>(A);
   }
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());
