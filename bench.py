@@ -216,11 +216,20 @@ def run_abm_ensemble(args, rank, world, local):
     peaks = measured_peaks()
     abm_ms = float(np.mean(kms["abm"]))
     pairs = R * NT * n * n                                              # ordered pairs per launch
-    mufu_peak = 148 * 16 * peaks["sm_max_mhz"] * 1e6 / 2 / 1e9          # Gpair/s: 2 MUFU per pair, 16 MUFU/clk/SM
-    roofline = dict(kernel="abm_dense_kernel<float>", bound="mufu", achieved=pairs / (abm_ms * 1e-3) / 1e9,
-                    peak=mufu_peak, unit="Gpair/s", frac=pairs / (abm_ms * 1e-3) / 1e9 / mufu_peak, traffic=None,
-                    note="state lives in shared memory; not HBM-bound (SURVEY 8d): 2 MUFU per ordered pair, "
-                         f"peak = 148 SM x 16 MUFU/clk x {peaks['sm_max_mhz']:.0f} MHz / 2 (derived, nominal clock)",
+    sym = os.environ.get("SMM_ABM_SYM", "1") != "0"
+    mufu_per_pair = 1 if sym else 2    # sqrt + ex2 per evaluated pair; the symmetric kernel evaluates unordered pairs
+    mufu_peak = 148 * 16 * peaks["sm_max_mhz"] * 1e6 / mufu_per_pair / 1e9   # G ordered pairs/s, 16 MUFU/clk/SM
+    # issue-slot view (ncu, profiles/r1_abm_dense_sym_*): warp instructions per realization-step, 4 issue slots/clk/SM
+    winst = 20550 if sym else 27700
+    issue_ms = R * NT * winst / (148 * 4 * peaks["sm_max_mhz"] * 1e6) * 1e3
+    roofline = dict(kernel="abm_dense_kernel<float,sym>" if sym else "abm_dense_kernel<float>", bound="mufu",
+                    achieved=pairs / (abm_ms * 1e-3) / 1e9, peak=mufu_peak, unit="Gpair/s",
+                    frac=pairs / (abm_ms * 1e-3) / 1e9 / mufu_peak, traffic=None,
+                    note="state lives in shared memory; not HBM-bound (SURVEY 8d). Algorithmic work: 2 MUFU (sqrt, ex2) per "
+                         "UNORDERED pair = 1 per ordered pair (w_ij = w_ji), "
+                         f"peak = 148 SM x 16 MUFU/clk x {peaks['sm_max_mhz']:.0f} MHz (derived, nominal clock); "
+                         "the kernel is co-limited by instruction issue (issue_frac)",
+                    issue_frac=issue_ms / abm_ms, warp_inst_per_realization_step=winst,
                     kernel_ms=abm_ms, share_of_step=abm_ms * args.steps / dev_ms if world == 1 else None)
     kde_ms = float(np.mean(kms["kde"]))
     kde_bytes = R * per_real * 4

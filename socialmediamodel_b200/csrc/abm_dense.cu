@@ -47,7 +47,7 @@ constexpr int kSymMaxGroups = 16;  // n <= 512: the per-offset partial sums must
 constexpr float kPadPos = 1e15f;   // padding agents of the last 32-group: exp(-|x - pad|) = 0 exactly
 
 template <typename real, bool SYM>
-__global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) {
+__global__ void __launch_bounds__(kThreads, SYM ? 7 : 8) abm_dense_kernel(AbmDenseArgs A) {
   using real2 = typename vec2<real>::type;
   const AbmConst& K = A.k;
   const int n = K.n, L = K.L, M = K.M, NT = A.NT;
@@ -76,10 +76,9 @@ __global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) 
   // SYM: positions once more, every 32-group stored twice in a row ([G][64]) so that the rotated partner
   // index lane +- s needs no wrap-around arithmetic, and the partial sums [1 + D][G*32] x (ws, ax, ay)
   const int G = (n + 31) >> 5, D = G >> 1, NG = G * 32;
-  // xs2[g][i] = log2(e) * (x of agent g*32 + (i & 31), x of agent g*32 + ((i + 16) & 31)), i < 64; ys2 likewise
-  float2* xs2 = reinterpret_cast<float2*>(smem + ((reinterpret_cast<unsigned char*>(st + npad) - smem + 15) & ~(size_t)15));
-  float2* ys2 = xs2 + (SYM ? G * 64 : 0);
-  float* part = reinterpret_cast<float*>(ys2 + (SYM ? G * 64 : 0));
+  // xy2[g][i] = log2(e) * (x_a, x_b, y_a, y_b) of the agents a = g*32 + (i & 31), b = g*32 + ((i + 16) & 31), i < 64
+  float4* xy2 = reinterpret_cast<float4*>(smem + ((reinterpret_cast<unsigned char*>(st + npad) - smem + 15) & ~(size_t)15));
+  float* part = reinterpret_cast<float*>(xy2 + (SYM ? G * 64 : 0));
 
   // ---- load the initial condition --------------------------------------------------------
   const real* x0 = static_cast<const real*>(A.x0) + (size_t)r * 2 * n;
@@ -164,10 +163,9 @@ __global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) 
         const real2 p = j < n ? xc[j] : mk2((real)kPadPos, (real)kPadPos);
         const float sx = (float)p.x * kLog2e, sy = (float)p.y * kLog2e;
         const int l = j & 31, l2 = (l + 16) & 31;
-        float2* ox = xs2 + (j >> 5) * 64;
-        float2* oy = ys2 + (j >> 5) * 64;
-        ox[l].x = sx; ox[l + 32].x = sx; ox[l2].y = sx; ox[l2 + 32].y = sx;
-        oy[l].x = sy; oy[l + 32].x = sy; oy[l2].y = sy; oy[l2 + 32].y = sy;
+        float4* o = xy2 + (j >> 5) * 64;
+        o[l].x = sx; o[l + 32].x = sx; o[l2].y = sx; o[l2 + 32].y = sx;
+        o[l].z = sy; o[l + 32].z = sy; o[l2].w = sy; o[l2 + 32].w = sy;
       }
     }
     // ---- P1: S_i, cnt_i, state sums of the OLD positions / followers (abm.jl:96-100,179-180,188-191)
@@ -266,15 +264,15 @@ __global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) 
       // evaluated in ordered form and contains the self pair (abm.jl:42).  Every partial sum has its own
       // shared-memory slot and is added in a fixed order: results are deterministic.
       for (int g = warp; g < G; g += nwarps) {
-        const float2* rowx = xs2 + g * 64 + lane;
-        const float2* rowy = ys2 + g * 64 + lane;
-        const float rx = rowx[0].x, ry = rowy[0].x;
+        const float4* rowp = xy2 + g * 64 + lane;
+        const float rx = rowp[0].x, ry = rowp[0].z;
         const float2 nrx = make_float2(-rx, -rx), nry = make_float2(-ry, -ry);
         float2 ws2 = make_float2(0.f, 0.f), ax2 = ws2, ay2 = ws2;
         // diagonal tile: lane l against all 32 agents of its own group, two partners per step
 #pragma unroll 8
         for (int t = 0; t < 16; t++) {
-          const float2 dx = add2(rowx[t], nrx), dy = add2(rowy[t], nry);
+          const float4 p = rowp[t];
+          const float2 dx = add2(make_float2(p.x, p.y), nrx), dy = add2(make_float2(p.z, p.w), nry);
           const float2 r2 = fma2(dx, dx, mul2(dy, dy));
           const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
           ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
@@ -283,24 +281,25 @@ __global__ void __launch_bounds__(kThreads, 8) abm_dense_kernel(AbmDenseArgs A) 
           if (2 * d == G && g >= D) break;
           int h = g + d;
           if (h >= G) h -= G;
-          const float2* colx = xs2 + h * 64 + lane;
-          const float2* coly = ys2 + h * 64 + lane;
-          const float cx = colx[0].x, cy = coly[0].x;
+          const float4* colp = xy2 + h * 64 + lane;
+          const float cx = colp[0].x, cy = colp[0].z;
           const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy);
           float2 cws2 = make_float2(0.f, 0.f), cax2 = cws2, cay2 = cws2;
           // step t: row agent l with the column agents (l + t) & 31 and (l + t + 16) & 31; their weights go
           // to the lanes that own those column agents, which pair them with the rows (l - t) & 31 and
           // (l - t - 16) & 31 — stored next to each other at index l - t + 32
-#pragma unroll 8
+#pragma unroll 16
           for (int t = 0; t < 16; t++) {
-            const float2 dx = add2(colx[t], nrx), dy = add2(coly[t], nry);
+            const float4 p = colp[t];
+            const float2 dx = add2(make_float2(p.x, p.y), nrx), dy = add2(make_float2(p.z, p.w), nry);
             const float2 r2 = fma2(dx, dx, mul2(dy, dy));
             const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
             ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
             float2 wv;
             wv.x = __shfl_sync(0xffffffffu, w.x, lane - t);
             wv.y = __shfl_sync(0xffffffffu, w.y, lane - t - 16);
-            const float2 ex = add2(rowx[32 - t], ncx), ey = add2(rowy[32 - t], ncy);
+            const float4 q = rowp[32 - t];
+            const float2 ex = add2(make_float2(q.x, q.y), ncx), ey = add2(make_float2(q.z, q.w), ncy);
             cws2 = add2(cws2, wv); cax2 = fma2(wv, ex, cax2); cay2 = fma2(wv, ey, cay2);
           }
           float* o = part + (size_t)d * 3 * NG + h * 32 + lane;
