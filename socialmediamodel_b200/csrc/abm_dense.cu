@@ -13,26 +13,6 @@ namespace {
 
 constexpr int kThreads = 128;
 
-// Packed FP32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 — two FP32 operations per issue slot).
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  float2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
-  return d;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-  float2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
-  return d;
-}
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
-        "l"(reinterpret_cast<unsigned long long&>(c)));
-  return d;
-}
 // 2^(-sqrt(r2)) for coordinates pre-scaled by log2(e): exp(-|x_i - x_j|) with two MUFU ops and nothing else
 __device__ __forceinline__ float w_of_scaled_r2(float r2) {
   float r, w;

@@ -61,12 +61,19 @@ __global__ void __launch_bounds__(KW * 32) kde_kernel(KdeArgs A) {
     for (int c = 0; c < ncls; c++) off[c + 1] += off[c];
   }
   __syncthreads();
-  // stable placement (one thread per class scans the agents in order): summation order, and
-  // therefore the FP32 result, is reproducible run to run
-  for (int c = tid; c < ncls; c += nthreads) {
+  // stable placement, one warp per class: the agents are scanned in order, 32 at a time; a ballot gives every
+  // member its rank within the class.  Summation order, and therefore the FP32 result, is reproducible run to run
+  for (int c = warp; c < ncls; c += KW) {
     int pos = off[c];
-    for (int a = 0; a < n; a++) {
-      if (fol[a] * 2 + (st[a] == 1 ? 1 : 0) == c) { ax[pos] = xs[a]; ay[pos] = xs[n + a]; pos++; }
+    for (int a0 = 0; a0 < n; a0 += 32) {
+      const int a = a0 + lane;
+      const bool in = a < n && fol[a] * 2 + (st[a] == 1 ? 1 : 0) == c;
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      if (in) {
+        const int q = pos + __popc(m & ((1u << lane) - 1u));
+        ax[q] = xs[a]; ay[q] = xs[n + a];
+      }
+      pos += __popc(m);
     }
   }
   __syncthreads();
@@ -80,10 +87,11 @@ __global__ void __launch_bounds__(KW * 32) kde_kernel(KdeArgs A) {
       const int iy0 = sy0 + warp * TYW;
       for (int c = 0; c < ncls; c++) {
         real acc[TYW][TXL];
+        float2 acc2[TYW / 2][TXL];  // FP32: rows (2b, 2b+1) as packed pairs -> FFMA2, two FMAs per issue slot
 #pragma unroll
         for (int b = 0; b < TYW; b++)
 #pragma unroll
-          for (int a = 0; a < TXL; a++) acc[b][a] = 0;
+          for (int a = 0; a < TXL; a++) { acc[b][a] = 0; acc2[b / 2][a] = make_float2(0.f, 0.f); }
         for (int k0 = off[c]; k0 < off[c + 1]; k0 += KC) {
           const int kc = min(KC, off[c + 1] - k0);
           __syncthreads();  // previous chunk fully consumed
@@ -100,11 +108,25 @@ __global__ void __launch_bounds__(KW * 32) kde_kernel(KdeArgs A) {
             for (int a = 0; a < TXL; a++) vx[a] = ex[k * SPAN + lane + 32 * a];
 #pragma unroll
             for (int b = 0; b < TYW; b += 4) ld4(vy + b, ey + k * SPAN + warp * TYW + b);
+            if constexpr (sizeof(real) == 4) {
 #pragma unroll
-            for (int b = 0; b < TYW; b++)
+              for (int b = 0; b < TYW; b += 2)
 #pragma unroll
-              for (int a = 0; a < TXL; a++) acc[b][a] += vx[a] * vy[b];
+                for (int a = 0; a < TXL; a++)
+                  acc2[b / 2][a] = fma2(make_float2((float)vx[a], (float)vx[a]), make_float2((float)vy[b], (float)vy[b + 1]), acc2[b / 2][a]);
+            } else {
+#pragma unroll
+              for (int b = 0; b < TYW; b++)
+#pragma unroll
+                for (int a = 0; a < TXL; a++) acc[b][a] += vx[a] * vy[b];
+            }
           }
+        }
+        if constexpr (sizeof(real) == 4) {
+#pragma unroll
+          for (int b = 0; b < TYW; b += 2)
+#pragma unroll
+            for (int a = 0; a < TXL; a++) { acc[b][a] = acc2[b / 2][a].x; acc[b + 1][a] = acc2[b / 2][a].y; }
         }
         real* o = us + (size_t)c * Nx * Ny;
 #pragma unroll

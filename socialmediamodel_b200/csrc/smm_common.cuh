@@ -95,6 +95,26 @@ template <> struct vec2<double> { using type = double2; };
 __device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
 
+// Packed FP32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 — two FP32 operations per issue slot).
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
 // exp(-sqrt(r2)) -- the interaction weight of abm.jl:59 / pde.jl:17.
 // FP32: two MUFU ops (sqrt.approx, ex2.approx), rel. error ~2e-7; sqrt.approx(0) = 0 so the
 // self-pair gives w = 1 exactly (abm.jl:42 self-loop).  FP64: libm-accurate.
