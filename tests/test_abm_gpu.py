@@ -341,3 +341,32 @@ def test_abm_against_golden_fixtures(name):
                                    injected=inj, network=net, want=("us",))
         if same:
             assert np.abs(ens["us"][..., 0] - g["us"]).max() / g["us"].max() < max(rtol, 1e-10)
+
+
+@pytest.mark.parametrize("n", [20, 33, 64, 90, 250, 300, 512, 520])
+def test_dense_kernel_symmetric_pair_schedule(n):
+    """FP32 all-to-all populations of up to 512 agents evaluate every unordered pair once (tiles of 32 x 32 agents,
+    group offsets 1..G/2).  Every tile schedule — one group, odd / even group counts, a partly filled last group,
+    the ordered-pair fallback above 512 agents — against the oracle and against the ordered-pair kernel."""
+    import os
+    NT = 12
+    p, q = smm.ABMconstruct(), smm.parameters(n=n)
+    runs = make_run(100 + n, n=n, NT=NT, R=2)
+    init, inj = stack_inputs(runs)
+    sym = smm.abm_solve_raw(NT, p=p, q=q, R=2, precision="f32", init_state=init, injected=inj)
+    os.environ["SMM_ABM_SYM"] = "0"
+    try:
+        ordered = smm.abm_solve_raw(NT, p=p, q=q, R=2, precision="f32", init_state=init, injected=inj)
+    finally:
+        del os.environ["SMM_ABM_SYM"]
+    for k, r in enumerate(runs):
+        o = oracle_solve(r, NT, p, q)
+        for out in (sym, ordered):
+            fol = out["follows"][:, :, k].T
+            same = np.array_equal(fol, o["follows"])
+            assert same or o["min_margin"] < 1e-5
+            if same:
+                xs = np.transpose(out["xs"][:, :, :, k], (2, 0, 1))
+                assert relerr(xs, o["xs"]) < RTOL_F32
+                assert relerr(np.transpose(out["infs"][:, :, :, k], (2, 0, 1)), o["infs"]) < RTOL_F32
+    assert relerr(sym["xs"], ordered["xs"]) < 5e-6
