@@ -44,11 +44,13 @@ __global__ void __launch_bounds__(kThreads, SYM ? 7 : 8) abm_dense_kernel(AbmDen
   double* medx = infy + 2 * L;                             // [2][M]
   double* medy = medx + 2 * M;
   double* frac = medy + 2 * M;                             // [L]
-  double* bsx = frac + L;                                  // [L+M] bin sums of old positions
-  double* bsy = bsx + (L + M);
-  int* bcnt = reinterpret_cast<int*>(bsy + (L + M));       // [L+M]
-  int* bss = bcnt + (L + M);                               // [L+M] sum of states per bin
-  int* fol = bss + (L + M);                                // [npad]
+  // bin sums of old positions: every bin is summed in two halves (agents a with (a >> 5) even / odd) so that
+  // the 2(L+M) work items balance over the 4 warps; entry 2*bin + half
+  double* bsx = frac + L;                                  // [2(L+M)]
+  double* bsy = bsx + 2 * (L + M);
+  int* bcnt = reinterpret_cast<int*>(bsy + 2 * (L + M));   // [2(L+M)]
+  int* bss = bcnt + 2 * (L + M);                           // [2(L+M)] sum of states per bin
+  int* fol = bss + 2 * (L + M);                            // [npad]
   float* finx = reinterpret_cast<float*>(fol + npad);      // [L] FP32 copies of the UPDATED influencers / fractions
   float* finy = finx + L;                                  //     for the guarded FP32 switch decision
   float* ffr = finy + L;
@@ -108,23 +110,24 @@ __global__ void __launch_bounds__(kThreads, SYM ? 7 : 8) abm_dense_kernel(AbmDen
 
   // bin sums over the current followers: bins 0..L-1 by influencer, L..L+M-1 by medium
   auto bin_sums = [&](const real2* xc) {
-    for (int bin = warp; bin < L + M; bin += nwarps) {
-      double sx = 0.0, sy = 0.0;
+    for (int item = warp; item < 2 * (L + M); item += nwarps) {
+      const int bin = item >> 1;
+      real sx = 0, sy = 0;  // `real` accumulation: Float64 in Float64 mode, FP32 (<= 8 terms per lane + a tree) in FP32 mode
       int c = 0, ss = 0;
-      for (int a = lane; a < n; a += 32) {
+      for (int a = lane + 32 * (item & 1); a < n; a += 64) {
         int s = st[a];
         bool in = bin < L ? (fol[a] == bin) : (s == (bin == L ? -1 : 1));
-        if (in) { real2 p = xc[a]; sx += (double)p.x; sy += (double)p.y; c++; ss += s; }
+        if (in) { real2 p = xc[a]; sx += p.x; sy += p.y; c++; ss += s; }
       }
       sx = warp_sum(sx); sy = warp_sum(sy); c = warp_sum(c); ss = warp_sum(ss);
-      if (lane == 0) { bsx[bin] = sx; bsy[bin] = sy; bcnt[bin] = c; bss[bin] = ss; }
+      if (lane == 0) { bsx[item] = (double)sx; bsy[item] = (double)sy; bcnt[item] = c; bss[item] = ss; }
     }
   };
   auto add_numbers = [&](int hist_index) {
     // plotting.jl:284-307: numbers[t,i,j] = #agents with medium i following influencer j
     if (A.numbers && tid < L * M) {
       int j = tid / M, i = tid % M;
-      int c = bcnt[j], ss = bss[j];
+      int c = bcnt[2 * j] + bcnt[2 * j + 1], ss = bss[2 * j] + bss[2 * j + 1];
       int v = i == 1 ? (c + ss) / 2 : (c - ss) / 2;
       atomicAdd(reinterpret_cast<unsigned long long*>(A.numbers) + ((size_t)hist_index * L + j) * M + i,
                 (unsigned long long)v);
@@ -176,9 +179,9 @@ __global__ void __launch_bounds__(kThreads, SYM ? 7 : 8) abm_dense_kernel(AbmDen
         }
       }
       const double nz = 1.0 / fr * sdt * sg;
-      const int cnt = bcnt[tid];
+      const int cnt = bcnt[2 * tid] + bcnt[2 * tid + 1];
       if (cnt > 0) {
-        double mcx = bsx[tid] / (double)cnt, mcy = bsy[tid] / (double)cnt;
+        double mcx = (bsx[2 * tid] + bsx[2 * tid + 1]) / (double)cnt, mcy = (bsy[2 * tid] + bsy[2 * tid + 1]) / (double)cnt;
         px = px + K.dt / fr * (mcx - px) + nz * z0;
         py = py + K.dt / fr * (mcy - py) + nz * z1;
       } else {
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, SYM ? 7 : 8) abm_dense_kernel(AbmDen
       py = reflect1(py, K.lo1, K.hi1);
       if (is_inf) {
         infx[nxt * L + e] = px; infy[nxt * L + e] = py;
-        const double fr_e = (double)bss[e] / (double)cnt;  // abm.jl:99; 0/0 = NaN (Q5)
+        const double fr_e = (double)(bss[2 * e] + bss[2 * e + 1]) / (double)cnt;  // abm.jl:99; 0/0 = NaN (Q5)
         frac[e] = fr_e;
         finx[e] = (float)px; finy[e] = (float)py; ffr[e] = (float)fr_e;
       } else {
@@ -402,8 +405,8 @@ __global__ void abm_draws_kernel(int n, uint64_t seed, uint32_t realization, int
 
 size_t dense_smem_bytes(int n, int L, int M, size_t real_size, bool sym) {
   int npad = (n + 3) & ~3;
-  size_t b = 2 * (size_t)npad * 2 * real_size + sizeof(double) * (4 * L + 4 * M + L + 2 * (L + M)) +
-             sizeof(int) * (2 * (L + M) + npad) + sizeof(float) * 3 * L + npad + 16;
+  size_t b = 2 * (size_t)npad * 2 * real_size + sizeof(double) * (4 * L + 4 * M + L + 4 * (L + M)) +
+             sizeof(int) * (4 * (L + M) + npad) + sizeof(float) * 3 * L + npad + 16;
   if (sym) {
     const size_t G = (n + 31) / 32, D = G / 2;
     b += 16 + 2 * G * 64 * 8 + (1 + D) * 3 * G * 32 * 4;
