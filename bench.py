@@ -363,7 +363,7 @@ def cpu_baseline_abm(realizations=None):
     cores = os.cpu_count() or 1
     try:
         _c_port_run(cores)                                    # warm-up (library load, thread pool)
-        realizations = realizations or 16 * max(cores, 8)     # ~10-20 s of CPU work
+        realizations = realizations or min(C2["R"], 64 * cores)   # ~10 s on 16 cores: the whole C2 ensemble
         done, dt, used = _c_port_run(realizations)
         return dict(value=done / dt, unit="agent-steps/s", cores=used, kind="port",
                     sample=f"{realizations} realizations of C2 (NT=200, n=250, KDE at 4 save points): C restatement of the "
