@@ -265,10 +265,12 @@ __device__ void moments_epilogue(const StageArgs& A, int b, double* part_w, doub
     double s = 0.0;
     for (int w = 0; w < nwarps; w++) s += part_w[w * (2 * L * 3) + tid];
     A.partials[((size_t)b * nblk + blk) * (2 * L * 3) + tid] = s;
-    __threadfence();
   }
   __syncthreads();
   if (tid == 0) {
+    // release: the barrier orders the CTA's partial stores before this thread; its fence is cumulative, so one
+    // fence per CTA (not one per writer) publishes them before the ticket
+    __threadfence();
     unsigned prev = atomicAdd(&A.counters[b], 1u);
     is_last = (prev == (unsigned)(nblk - 1));
   }
@@ -589,7 +591,6 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
       double t = 0.0;
       for (int w = 0; w < BY; w++) t += s_esq[w];
       A.errpart[(size_t)b * (gridDim.x * gridDim.y) + blockIdx.y * gridDim.x + blockIdx.x] = t;
-      __threadfence();
     }
   }
   // block-level moments: warp `w` reduces plane w, w + 8, ..: column sums over the 8 rows in fixed
@@ -610,8 +611,7 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
       sy = warp_sum(sy);
       if (tx == 0) {
         double* o = A.partials + ((size_t)b * nblk + blk) * (NP * 3) + p * 3;
-        o[0] = (double)s0; o[1] = (double)sx; o[2] = (double)sy;
-        __threadfence();
+        o[0] = (double)s0; o[1] = (double)sx; o[2] = (double)sy;  // published by the single fence in moments_ticket
       }
     }
   }
