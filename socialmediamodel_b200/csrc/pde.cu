@@ -413,6 +413,31 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
     if (A.out_role == ROLE_OTHER) out_base = cur ? A.P[0] : A.P[1];
   }
   const real* U = static_cast<const real*>(Uin) + (size_t)b * NP * plane;
+  const real* un = static_cast<const real*>(un_base) + (size_t)b * NP * plane;
+  real* Uout = static_cast<real*>(out_base) + (size_t)b * NP * plane;
+  real* acc = A.acc ? static_cast<real*>(A.acc) + (size_t)b * NP * plane : nullptr;
+  real* errb = AD ? static_cast<real*>(A.err) + (size_t)b * NP * plane : nullptr;
+  const size_t o_c = (size_t)min(iy, Ny - 1) * Pw + min(ix, Nx - 1);
+  const real dtA = (real)A.A, dtB = (real)A.Bc, dtC = (real)(A.C * dt_b), dtw = (real)(A.bw * dt_b);
+  const real dte = AD ? (real)(A.ew * dt_b) : (real)0;
+  const real e_atol = AD ? (real)A.ctl[b].abstol : (real)0, e_rtol = AD ? (real)A.ctl[b].reltol : (real)0;
+  const bool need_err = AD && A.err_mode != ACC_INIT;
+  real esq = 0;
+  // step-start state and accumulator of this grid point for all planes, loaded before the tiles are staged:
+  // independent loads in flight together, their latency overlaps the TMA transfer (inside the plane loop
+  // they would queue behind possibly-aliasing stores)
+  constexpr int NPT = LT ? 2 * LT : 1;
+  real unv[NPT], accv[NPT], errv[AD ? NPT : 1];
+  const bool need_un = dtA != (real)0 || A.acc_mode == ACC_INIT || (AD && A.err_mode == ACC_FINAL);
+  const bool need_acc = A.acc_mode == ACC_ADD || A.acc_mode == ACC_FINAL;
+  if (LT) {
+#pragma unroll
+    for (int p = 0; p < NPT; p++) {
+      unv[p] = need_un ? un[(size_t)p * plane + o_c] : (real)0;
+      accv[p] = need_acc ? acc[(size_t)p * plane + o_c] : (real)0;
+      if (AD) errv[AD ? p : 0] = need_err ? errb[(size_t)p * plane + o_c] : (real)0;
+    }
+  }
   // ---- stage the tiles (clamped at the domain edge; the clamped values are never used there)
   if (A.use_tma) {
     // One elected thread issues three bulk tensor copies (TMA): the 2L x 10 x 36 density box with its
@@ -503,30 +528,6 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
     for (int i = 0; i < 2; i++) {
       rsum[i] += tc[(j * 2 + i) * TH * TW];
       gsum[i] += Ej * s_R[i][j];
-    }
-  }
-  const real* un = static_cast<const real*>(un_base) + (size_t)b * NP * plane;
-  real* Uout = static_cast<real*>(out_base) + (size_t)b * NP * plane;
-  real* acc = A.acc ? static_cast<real*>(A.acc) + (size_t)b * NP * plane : nullptr;
-  real* errb = AD ? static_cast<real*>(A.err) + (size_t)b * NP * plane : nullptr;
-  const size_t o_c = (size_t)cy * Pw + cx;
-  const real dtA = (real)A.A, dtB = (real)A.Bc, dtC = (real)(A.C * dt_b), dtw = (real)(A.bw * dt_b);
-  const real dte = AD ? (real)(A.ew * dt_b) : (real)0;
-  const real e_atol = AD ? (real)A.ctl[b].abstol : (real)0, e_rtol = AD ? (real)A.ctl[b].reltol : (real)0;
-  const bool need_err = AD && A.err_mode != ACC_INIT;
-  real esq = 0;
-  // step-start state and accumulator of this grid point for all planes, loaded up front (independent
-  // loads in flight together; inside the plane loop they would queue behind possibly-aliasing stores)
-  constexpr int NPT = LT ? 2 * LT : 1;
-  real unv[NPT], accv[NPT], errv[AD ? NPT : 1];
-  const bool need_un = dtA != (real)0 || A.acc_mode == ACC_INIT || (AD && A.err_mode == ACC_FINAL);
-  const bool need_acc = A.acc_mode == ACC_ADD || A.acc_mode == ACC_FINAL;
-  if (LT) {
-#pragma unroll
-    for (int p = 0; p < NPT; p++) {
-      unv[p] = need_un ? un[(size_t)p * plane + o_c] : (real)0;
-      accv[p] = need_acc ? acc[(size_t)p * plane + o_c] : (real)0;
-      if (AD) errv[AD ? p : 0] = need_err ? errb[(size_t)p * plane + o_c] : (real)0;
     }
   }
   real rs_out = 0;
