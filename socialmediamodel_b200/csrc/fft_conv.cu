@@ -30,6 +30,14 @@ template <typename real2> __device__ __forceinline__ real2 cmulc(real2 a, real2 
 //   position(k) = (k mod r3) * m + bitrev_a(k div r3)
 struct FftDims { int P, m, a, r3; };
 
+// Shared-memory swizzle of an FFT column: logical element i lives at physical slot i ^ ((i >> 2) & 15).
+// The radix-2^2 passes with small butterfly distance (q = 1, 4: element strides 4 and 16) were 4-way
+// bank-conflicted in the natural layout (48 % of all shared wavefronts of fft_cols at P = 768); with the
+// swizzle every pass of every supported length is conflict-free (checked by enumeration).
+// It permutes within aligned blocks of 64 (of 8 inside a trailing half block), so it is a bijection on
+// [0, P) for every P = r3 * 2^a, a >= 5.
+__device__ __forceinline__ int swz(int i) { return i ^ ((i >> 2) & 15); }
+
 __device__ __forceinline__ int brev_a(int i, int a) { return a ? (int)(__brev((unsigned)i) >> (32 - a)) : 0; }
 __device__ __forceinline__ int pos_of_freq(int k, FftDims d) {
   return d.r3 == 3 ? (k % 3) * d.m + brev_a(k / 3, d.a) : brev_a(k, d.a);
@@ -72,15 +80,16 @@ __device__ void fft_dif_fwd(typename vec2<real>::type* sh, int ncol, int cs, Fft
     const real2* t3 = tw + m;
     for (int t = tid; t < ncol * m; t += nt) {
       const int c = t >> a, j = t & (m - 1);
-      real2* x = sh + c * cs + j;
-      const real2 a0 = x[0], a1 = x[m], a2 = x[2 * m];
+      real2* col = sh + c * cs;
+      const int i0 = swz(j), i1 = swz(j + m), i2 = swz(j + 2 * m);
+      const real2 a0 = col[i0], a1 = col[i1], a2 = col[i2];
       // y1 = a0 + w3 a1 + w3^2 a2, y2 = a0 + w3^2 a1 + w3 a2  (w3^2 = conj(w3), w3^4 = w3)
       const real sr = a1.x + a2.x, si = a1.y + a2.y, dr = a1.x - a2.x, di = a1.y - a2.y;
       const real tr = a0.x + (real)SMM_W3_RE * sr, ti = a0.y + (real)SMM_W3_RE * si;
       const real ur = -(real)SMM_W3_IM * di, ui = (real)SMM_W3_IM * dr;  // i*Im(w3)*(a1-a2) = (-Im*di, Im*dr)
-      x[0] = mk2(a0.x + sr, a0.y + si);
-      x[m] = cmul(mk2(tr + ur, ti + ui), t3[j]);
-      x[2 * m] = cmul(mk2(tr - ur, ti - ui), t3[2 * j]);
+      col[i0] = mk2(a0.x + sr, a0.y + si);
+      col[i1] = cmul(mk2(tr + ur, ti + ui), t3[j]);
+      col[i2] = cmul(mk2(tr - ur, ti - ui), t3[2 * j]);
     }
     __syncthreads();
   }
@@ -92,15 +101,16 @@ __device__ void fft_dif_fwd(typename vec2<real>::type* sh, int ncol, int cs, Fft
       const int cc = t >> (a - 2), bt = t & (qp - 1);
       const int c = r3 == 3 ? cc / 3 : cc, r = cc - c * r3;
       const int j = bt & (q - 1), i0 = ((bt >> (s - 2)) << s) + j;
-      real2* x = sh + c * cs + r * m + i0;
-      const real2 a0 = x[0], a1 = x[q], a2 = x[2 * q], a3 = x[3 * q];
+      real2* col = sh + c * cs;
+      const int e0 = r * m + i0, p0 = swz(e0), p1 = swz(e0 + q), p2 = swz(e0 + 2 * q), p3 = swz(e0 + 3 * q);
+      const real2 a0 = col[p0], a1 = col[p1], a2 = col[p2], a3 = col[p3];
       const real2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), tw[2 * q + j]);
       const real2 b1 = cadd(a1, a3), b3 = cmul(csub(a1, a3), tw[3 * q + j]);
       const real2 w = tw[q + j];
-      x[0] = cadd(b0, b1);
-      x[q] = cmul(csub(b0, b1), w);
-      x[2 * q] = cadd(b2, b3);
-      x[3 * q] = cmul(csub(b2, b3), w);
+      col[p0] = cadd(b0, b1);
+      col[p1] = cmul(csub(b0, b1), w);
+      col[p2] = cadd(b2, b3);
+      col[p3] = cmul(csub(b2, b3), w);
     }
     __syncthreads();
   }
@@ -108,10 +118,11 @@ __device__ void fft_dif_fwd(typename vec2<real>::type* sh, int ncol, int cs, Fft
     for (int t = tid; t < nsub * (m >> 1); t += nt) {
       const int cc = t >> (a - 1), bt = t & ((m >> 1) - 1);
       const int c = r3 == 3 ? cc / 3 : cc, r = cc - c * r3;
-      real2* x = sh + c * cs + r * m + 2 * bt;
-      const real2 p = x[0], q2 = x[1];
-      x[0] = cadd(p, q2);
-      x[1] = csub(p, q2);
+      real2* col = sh + c * cs;
+      const int p0 = swz(r * m + 2 * bt), p1 = swz(r * m + 2 * bt + 1);
+      const real2 p = col[p0], q2 = col[p1];
+      col[p0] = cadd(p, q2);
+      col[p1] = csub(p, q2);
     }
     __syncthreads();
   }
@@ -129,10 +140,11 @@ __device__ void fft_dit_inv(typename vec2<real>::type* sh, int ncol, int cs, Fft
     for (int t = tid; t < nsub * (m >> 1); t += nt) {
       const int cc = t >> (a - 1), bt = t & ((m >> 1) - 1);
       const int c = r3 == 3 ? cc / 3 : cc, r = cc - c * r3;
-      real2* x = sh + c * cs + r * m + 2 * bt;
-      const real2 p = x[0], q2 = x[1];
-      x[0] = cadd(p, q2);
-      x[1] = csub(p, q2);
+      real2* col = sh + c * cs;
+      const int p0 = swz(r * m + 2 * bt), p1 = swz(r * m + 2 * bt + 1);
+      const real2 p = col[p0], q2 = col[p1];
+      col[p0] = cadd(p, q2);
+      col[p1] = csub(p, q2);
     }
     __syncthreads();
     s = 2;
@@ -143,16 +155,17 @@ __device__ void fft_dit_inv(typename vec2<real>::type* sh, int ncol, int cs, Fft
       const int cc = t >> (a - 2), bt = t & (qp - 1);
       const int c = r3 == 3 ? cc / 3 : cc, r = cc - c * r3;
       const int j = bt & (q - 1), i0 = ((bt >> (s - 1)) << (s + 1)) + j;
-      real2* x = sh + c * cs + r * m + i0;
-      const real2 a0 = x[0], a2 = x[2 * q];
+      real2* col = sh + c * cs;
+      const int e0 = r * m + i0, p0 = swz(e0), p1 = swz(e0 + q), p2 = swz(e0 + 2 * q), p3 = swz(e0 + 3 * q);
+      const real2 a0 = col[p0], a2 = col[p2];
       const real2 w1 = tw[q + j];
-      const real2 t1 = cmulc(x[q], w1), t3 = cmulc(x[3 * q], w1);
+      const real2 t1 = cmulc(col[p1], w1), t3 = cmulc(col[p3], w1);
       const real2 b0 = cadd(a0, t1), b1 = csub(a0, t1), b2 = cadd(a2, t3), b3 = csub(a2, t3);
       const real2 u2 = cmulc(b2, tw[2 * q + j]), u3 = cmulc(b3, tw[3 * q + j]);
-      x[0] = cadd(b0, u2);
-      x[2 * q] = csub(b0, u2);
-      x[q] = cadd(b1, u3);
-      x[3 * q] = csub(b1, u3);
+      col[p0] = cadd(b0, u2);
+      col[p2] = csub(b0, u2);
+      col[p1] = cadd(b1, u3);
+      col[p3] = csub(b1, u3);
     }
     __syncthreads();
   }
@@ -160,15 +173,16 @@ __device__ void fft_dit_inv(typename vec2<real>::type* sh, int ncol, int cs, Fft
     const real2* t3 = tw + m;
     for (int t = tid; t < ncol * m; t += nt) {
       const int c = t >> a, j = t & (m - 1);
-      real2* x = sh + c * cs + j;
-      const real2 b0 = x[0], b1 = cmulc(x[m], t3[j]), b2 = cmulc(x[2 * m], t3[2 * j]);
+      real2* col = sh + c * cs;
+      const int i0 = swz(j), i1 = swz(j + m), i2 = swz(j + 2 * m);
+      const real2 b0 = col[i0], b1 = cmulc(col[i1], t3[j]), b2 = cmulc(col[i2], t3[2 * j]);
       // a1 = b0 + conj(w3) b1 + w3 b2, a2 = b0 + w3 b1 + conj(w3) b2
       const real sr = b1.x + b2.x, si = b1.y + b2.y, dr = b1.x - b2.x, di = b1.y - b2.y;
       const real tr = b0.x + (real)SMM_W3_RE * sr, ti = b0.y + (real)SMM_W3_RE * si;
       const real ur = -(real)SMM_W3_IM * di, ui = (real)SMM_W3_IM * dr;
-      x[0] = mk2(b0.x + sr, b0.y + si);
-      x[m] = mk2(tr - ur, ti - ui);
-      x[2 * m] = mk2(tr + ur, ti + ui);
+      col[i0] = mk2(b0.x + sr, b0.y + si);
+      col[i1] = mk2(tr - ur, ti - ui);
+      col[i2] = mk2(tr + ur, ti + ui);
     }
     __syncthreads();
   }
@@ -207,14 +221,14 @@ __global__ void __launch_bounds__(256) fft_rows_fwd_kernel(int nrows, int rowlen
   const real* rowb = in + ((size_t)b * nrows + rb) * rowpitch;
   const bool hasb = rb < nrows;
   for (int i = tid; i < P; i += nt) tw[i] = twg[i];
-  for (int i = tid; i < P; i += nt) sh[i] = i < rowlen ? mk2(rowa[i], hasb ? rowb[i] : (real)0) : mk2((real)0, (real)0);
+  for (int i = tid; i < P; i += nt) sh[swz(i)] = i < rowlen ? mk2(rowa[i], hasb ? rowb[i] : (real)0) : mk2((real)0, (real)0);
   __syncthreads();
   fft_dif_fwd<real>(sh, 1, P, d, tw);
   const int hp1 = P / 2 + 1;
   real2* oa = out + ((size_t)b * nrows + ra) * hp1;
   real2* ob = out + ((size_t)b * nrows + rb) * hp1;
   for (int k = tid; k < hp1; k += nt) {
-    const real2 zk = sh[pos_of_freq(k, d)], zm = sh[pos_of_freq(k ? P - k : 0, d)];
+    const real2 zk = sh[swz(pos_of_freq(k, d))], zm = sh[swz(pos_of_freq(k ? P - k : 0, d))];
     oa[k] = mk2((real)0.5 * (zk.x + zm.x), (real)0.5 * (zk.y - zm.y));
     if (hasb) ob[k] = mk2((real)0.5 * (zk.y + zm.y), (real)-0.5 * (zk.x - zm.x));
   }
@@ -244,7 +258,7 @@ __global__ void __launch_bounds__(512) fft_cols_kernel(int nrows, int nkeep, Fft
     const int jy = e / cols, c = e - jy * cols;
     real2 v = mk2((real)0, (real)0);
     if (jy < nrows && kx0 + c < hp1) v = Ab[(size_t)jy * hp1 + kx0 + c];
-    R[c * cs + jy] = v;
+    R[c * cs + swz(jy)] = v;
   }
   __syncthreads();
   fft_dif_fwd<real>(R, cols, cs, d, tw);
@@ -252,7 +266,7 @@ __global__ void __launch_bounds__(512) fft_cols_kernel(int nrows, int nkeep, Fft
     for (int e = tid; e < P * cols; e += nt) {
       const int c = e / P, i = e - c * P;
       if (kx0 + c < hp1) {
-        real2 v = R[c * cs + i];
+        real2 v = R[c * cs + swz(i)];
         G[((size_t)b * hp1 + kx0 + c) * P + i] = mk2((real)(v.x * scale), (real)(v.y * scale));
       }
     }
@@ -262,15 +276,15 @@ __global__ void __launch_bounds__(512) fft_cols_kernel(int nrows, int nkeep, Fft
     for (int e = tid; e < P * cols; e += nt) {
       const int c = e / P, i = e - c * P;
       real2 v = mk2((real)0, (real)0);
-      if (kx0 + c < hp1) v = cmul(R[c * cs + i], khat[((size_t)k * hp1 + kx0 + c) * P + i]);
-      Wk[c * cs + i] = v;
+      if (kx0 + c < hp1) v = cmul(R[c * cs + swz(i)], khat[((size_t)k * hp1 + kx0 + c) * P + i]);
+      Wk[c * cs + swz(i)] = v;
     }
     __syncthreads();
     fft_dit_inv<real>(Wk, cols, cs, d, tw);
     real2* Gk = G + (size_t)k * gstride + (size_t)b * nkeep * hp1;
     for (int e = tid; e < nkeep * cols; e += nt) {
       const int iy = e / cols, c = e - iy * cols;
-      if (kx0 + c < hp1) Gk[(size_t)iy * hp1 + kx0 + c] = Wk[c * cs + iy];
+      if (kx0 + c < hp1) Gk[(size_t)iy * hp1 + kx0 + c] = Wk[c * cs + swz(iy)];
     }
     __syncthreads();
   }
@@ -304,12 +318,13 @@ __global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, int P
     real2 a = Gk[(size_t)ra * hp1 + src];
     real2 bb = hasb ? Gk[(size_t)rb * hp1 + src] : mk2((real)0, (real)0);
     if (up) { a.y = -a.y; bb.y = -bb.y; }
-    sh[k * cs + pos] = mk2(a.x - bb.y, a.y + bb.x);  // A + i B
+    sh[k * cs + swz(pos)] = mk2(a.x - bb.y, a.y + bb.x);  // A + i B
   }
   __syncthreads();
   fft_dit_inv<real>(sh, 3, cs, d, tw);
   for (int ix = tid; ix < Nx; ix += nt) {
-    const real2 o0 = sh[ix], ox = sh[cs + ix], oy = sh[2 * cs + ix];
+    const int px = swz(ix);
+    const real2 o0 = sh[px], ox = sh[cs + px], oy = sh[2 * cs + px];
     const size_t oa = ((size_t)b * Ny + ra) * Pw + ix;
     Fx[oa] = ox.x / o0.x;  // pde.jl:58 force ./ norms
     Fy[oa] = oy.x / o0.x;
