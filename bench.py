@@ -221,7 +221,7 @@ def run_abm_ensemble(args, rank, world, local):
     mufu_per_pair = 1 if sym else 2    # sqrt + ex2 per evaluated pair; the symmetric kernel evaluates unordered pairs
     mufu_peak = 148 * 16 * peaks["sm_max_mhz"] * 1e6 / mufu_per_pair / 1e9   # G ordered pairs/s, 16 MUFU/clk/SM
     # issue-slot view (ncu, profiles/r1_abm_dense_sym_*): warp instructions per realization-step, 4 issue slots/clk/SM
-    winst = 20550 if sym else 27700
+    winst = 19860 if sym else 27700
     issue_ms = R * NT * winst / (148 * 4 * peaks["sm_max_mhz"] * 1e6) * 1e3
     roofline = dict(kernel="abm_dense_kernel<float,sym>" if sym else "abm_dense_kernel<float>", bound="mufu",
                     achieved=pairs / (abm_ms * 1e-3) / 1e9, peak=mufu_peak, unit="Gpair/s",
