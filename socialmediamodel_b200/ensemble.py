@@ -109,12 +109,15 @@ def ensemble_means(us, zs, ys):
 
 
 def PDEsolveensemble(tmax=0.1, N=10, *, savepoints=4, alg=None, init="4inf", p=None, q=None, save=True, dt=None,
-                     scheme="rk4", precision="f32", qs=None, rng=None, ctx=None):
+                     scheme="rk4", precision="f32", qs=None, rng=None, ctx=None, adaptive=False, abstol=1e-6, reltol=1e-3,
+                     dtmin=0.0, force_dtmin=False):
     """ensemble.jl:58-85: N PDE solves saved at LinRange(0, tmax, savepoints).  The reference runs N
     *identical* solves unless init="random"; ``qs`` (a list of N parameter sets) turns the call into a
     parameter sweep.  All instances advance together as one device-resident batch.  Returns
-    (us, zs, ys, (p, q)) with us[N_x,N_y,2,L,savepoints,N], zs[2,2,savepoints,N], ys[2,L,savepoints,N]."""
-    from .pde import constructinitial, default_dt, pde_solve_raw
+    (us, zs, ys, (p, q)) with us[N_x,N_y,2,L,savepoints,N], zs[2,2,savepoints,N], ys[2,L,savepoints,N].
+    ``adaptive=True`` (or ``alg="BS3"``): the adaptive integrator with per-instance step control and the reference's
+    solve keywords instead of the fixed-step scheme."""
+    from .pde import constructinitial, default_dt, pde_solve_adaptive_raw, pde_solve_raw
     from .setting import PDEconstruct
     p = PDEconstruct() if p is None else p
     q = parameters() if q is None else q
@@ -123,6 +126,15 @@ def PDEsolveensemble(tmax=0.1, N=10, *, savepoints=4, alg=None, init="4inf", p=N
     u0 = np.stack([uz.x[0] for uz, _ in inits], axis=-1)
     z0 = np.stack([uz.x[1] for uz, _ in inits], axis=-1)
     y0 = np.stack([uz.x[2] for uz, _ in inits], axis=-1)
+    if adaptive or (isinstance(alg, str) and alg.upper() in ("BS3", "ADAPTIVE")):
+        times = np.linspace(0.0, tmax, savepoints) if savepoints > 1 else np.array([0.0])     # ensemble.jl:65
+        out = pde_solve_adaptive_raw(p, qlist, u0, z0, y0, savetimes=times, abstol=abstol, reltol=reltol, dtmin=dtmin,
+                                     force_dtmin=force_dtmin, precision=precision, ctx=ctx)
+        us, zs, ys = out["us"], out["zs"], out["ys"]
+        if save:
+            os.makedirs("data", exist_ok=True)
+            np.savez(os.path.join("data", f"pde_ensemble_{init}.npz"), us=us, zs=zs, ys=ys)
+        return us, zs, ys, (p, qlist[-1])
     dt = min(default_dt(p, qq) for qq in qlist) if dt is None else dt
     per = max(1, int(np.ceil(tmax / (savepoints - 1) / dt - 1e-9))) if savepoints > 1 else max(1, int(np.ceil(tmax / dt - 1e-9)))
     nsteps = per * max(savepoints - 1, 1)

@@ -160,3 +160,16 @@ def test_PDEsolve_adaptive_keyword(coarse):
     fixed, _ = smm.PDEsolve(0.05, p=p, q=smm.parameters(), precision="f32")
     assert rel(sol(0.05).x[0], fixed(0.05).x[0]) < 5e-3
     assert np.abs(sol(0.025).x[2] - fixed(0.025).x[2]).max() < 5e-3
+
+
+def test_PDEsolveensemble_adaptive_parameter_sweep(coarse):
+    """ensemble.jl:58-85 on the adaptive integrator: a parameter sweep saved at LinRange(0, tmax, savepoints) agrees
+    with the fixed-step sweep within the tolerance."""
+    p, q, _ = coarse
+    qs = [smm.parameters(a=a) for a in (0.5, 1.0, 2.0)]
+    ua, za, ya, _ = smm.PDEsolveensemble(0.06, 3, savepoints=3, p=p, qs=qs, save=False, adaptive=True, precision="f32")
+    uf, zf, yf, _ = smm.PDEsolveensemble(0.06, 3, savepoints=3, p=p, qs=qs, save=False, precision="f32")
+    assert ua.shape == uf.shape == (p.N_x, p.N_y, 2, 4, 3, 3)
+    np.testing.assert_array_equal(ua[..., 0, :], uf[..., 0, :])            # t = 0
+    assert rel(ua, uf) < 5e-3 and np.abs(ya - yf).max() < 5e-3
+    assert rel(ua[..., -1, 0], ua[..., -1, 2]) > 1e-2                      # the sweep parameter matters
