@@ -220,7 +220,9 @@ __global__ void __launch_bounds__(256) fft_rows_fwd_kernel(int nrows, int rowlen
   const real* rowa = in + ((size_t)b * nrows + ra) * rowpitch;
   const real* rowb = in + ((size_t)b * nrows + rb) * rowpitch;
   const bool hasb = rb < nrows;
-  for (int i = tid; i < P; i += nt) tw[i] = twg[i];
+  for (int i = tid; i < P; i += nt) tw[i] = twg[i];  // constant table: before the dependency wait
+  pdl_wait();
+  pdl_launch_dependents();
   for (int i = tid; i < P; i += nt) sh[swz(i)] = i < rowlen ? mk2(rowa[i], hasb ? rowb[i] : (real)0) : mk2((real)0, (real)0);
   __syncthreads();
   fft_dif_fwd<real>(sh, 1, P, d, tw);
@@ -252,7 +254,9 @@ __global__ void __launch_bounds__(512) fft_cols_kernel(int nrows, int nkeep, Fft
   const int hp1 = P / 2 + 1;
   const int b = blockIdx.y, kx0 = blockIdx.x * cols;
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < P; i += nt) tw[i] = twg[i];
+  for (int i = tid; i < P; i += nt) tw[i] = twg[i];  // constant table: before the dependency wait
+  pdl_wait();
+  pdl_launch_dependents();
   const real2* Ab = A + (size_t)b * nrows * hp1;
   for (int e = tid; e < P * cols; e += nt) {
     const int jy = e / cols, c = e - jy * cols;
@@ -305,7 +309,9 @@ __global__ void __launch_bounds__(256) fft_rows_inv_kernel(int Nx, int Ny, int P
   const int b = blockIdx.y, ra = blockIdx.x * 2, rb = ra + 1;
   const bool hasb = rb < Ny;
   const int tid = threadIdx.x, nt = blockDim.x;
-  for (int i = tid; i < P; i += nt) tw[i] = twg[i];
+  for (int i = tid; i < P; i += nt) tw[i] = twg[i];  // constant table: before the dependency wait
+  pdl_wait();
+  pdl_launch_dependents();
   // the DIT inverse wants its input bit-reversed: iterate over shared-memory positions (conflict-free
   // stores) and fetch spectrum index brev(pos) from the 4 KB global row (L1-resident) -- scattering
   // into bit-reversed shared addresses instead was a 32-way bank conflict
@@ -458,13 +464,15 @@ static int fft_conv_launch(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, vo
   size_t sm_cols = ((size_t)2 * cols * (P + 1) + P) * sizeof(real2);
   size_t sm_inv = ((size_t)3 * (P + 1) + P) * sizeof(real2);
   const int rt = P >= 512 ? 256 : 128;
-  fft_rows_fwd_kernel<real><<<dim3((p->Ny + 1) / 2, p->B), rt, sm_rows, ctx->stream>>>(
-      p->Ny, p->Nx, p->Pw, d, (const real*)rhosum, (real2*)p->ahat, (const real2*)p->tw);
+  static const bool pdl = !(getenv("SMM_PDE_PDL") && getenv("SMM_PDE_PDL")[0] == '0');
+  SMM_CUDA(ctx, smm_launch_pdl(pdl, fft_rows_fwd_kernel<real>, dim3((p->Ny + 1) / 2, p->B), dim3(rt), sm_rows, ctx->stream,
+                               p->Ny, p->Nx, p->Pw, d, (const real*)rhosum, (real2*)p->ahat, (const real2*)p->tw));
   const int ct = (P * cols) / 2 >= 2048 ? 512 : ((P * cols) / 2 >= 256 ? 256 : 128);
-  fft_cols_kernel<real, 0><<<dim3((hp1 + cols - 1) / cols, p->B), ct, sm_cols, ctx->stream>>>(
-      p->Ny, p->Ny, d, cols, 1.0, (const real2*)p->ahat, (const real2*)p->khat, (real2*)p->g, (const real2*)p->tw, gstride);
-  fft_rows_inv_kernel<real><<<dim3((p->Ny + 1) / 2, p->B), rt, sm_inv, ctx->stream>>>(
-      p->Nx, p->Ny, p->Pw, d, (const real2*)p->g, gstride, (real*)Fx, (real*)Fy, (const real2*)p->tw);
+  SMM_CUDA(ctx, smm_launch_pdl(pdl, fft_cols_kernel<real, 0>, dim3((hp1 + cols - 1) / cols, p->B), dim3(ct), sm_cols, ctx->stream,
+                               p->Ny, p->Ny, d, cols, 1.0, (const real2*)p->ahat, (const real2*)p->khat, (real2*)p->g,
+                               (const real2*)p->tw, gstride));
+  SMM_CUDA(ctx, smm_launch_pdl(pdl, fft_rows_inv_kernel<real>, dim3((p->Ny + 1) / 2, p->B), dim3(rt), sm_inv, ctx->stream,
+                               p->Nx, p->Ny, p->Pw, d, (const real2*)p->g, gstride, (real*)Fx, (real*)Fy, (const real2*)p->tw));
   ctx->launches += 3;
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;

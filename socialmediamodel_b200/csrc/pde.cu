@@ -380,6 +380,8 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
   const int ix = bx0 + tx, iy = by0 + ty;
   const int tid = ty * BX + tx;
   const bool in = ix < Nx && iy < Ny;
+  pdl_wait();               // programmatic dependent launch: everything below reads the predecessors' results
+  pdl_launch_dependents();
   extern __shared__ __align__(128) unsigned char smem_stage[];
   // every TMA destination starts on a 128-byte boundary
   real* tile = reinterpret_cast<real*>(smem_stage);                                             // [NP][TH][TW]
@@ -799,7 +801,8 @@ static int launch_stage_t(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
   const size_t sm = stage_smem(pb->L, sizeof(real));
   // static + dynamic shared memory can exceed 48 KB even when the dynamic part alone does not: always opt in
   SMM_CUDA(ctx, cudaFuncSetAttribute(pde_stage_kernel<real, LT, AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 48 * 1024)));
-  pde_stage_kernel<real, LT, AD><<<grid, block, sm, ctx->stream>>>(A);
+  static const bool pdl = !(getenv("SMM_PDE_PDL") && getenv("SMM_PDE_PDL")[0] == '0');
+  SMM_CUDA(ctx, smm_launch_pdl(pdl, pde_stage_kernel<real, LT, AD>, grid, block, sm, ctx->stream, A));
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;

@@ -1,5 +1,6 @@
 // smm_common.cuh -- shared host/device plumbing of libsmm_b200.so (sm_100a only).
 #pragma once
+#include <cstring>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -94,6 +95,30 @@ template <> struct vec2<double> { using type = double2; };
 
 __device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
+
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running; it blocks at pdl_wait() until the
+// predecessor has completed and its memory is visible.  pdl_launch_dependents() lets the successor's CTAs be
+// scheduled as soon as every CTA of this grid has reached it.  Both are no-ops for plainly launched kernels.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t smm_launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  // Only for grids of at most 1.5 CTAs per SM: the successor's CTAs become resident (and hold registers / shared memory at
+  // pdl_wait) while this grid is still running, which pays for latency-bound launches (C3: 96.5 -> 89.2 us per
+  // RK4 step) and costs throughput for large ones (177^2 x 16: 0.41 -> 0.46 ms when applied everywhere).
+  const size_t ctas = (size_t)grid.x * grid.y * grid.z;
+  cfg.attrs = at; cfg.numAttrs = (pdl && 2 * ctas <= 3 * 148) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 // Packed FP32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 — two FP32 operations per issue slot).
 __device__ __forceinline__ float2 add2(float2 a, float2 b) {
