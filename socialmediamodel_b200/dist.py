@@ -70,3 +70,40 @@ def sharded_abm_ensemble(NT, N, *, p, q, savepoints=4, sigma=0.1, precision="f32
     means = dict(av_u=out["sum_us"] / N, av_z=out["sum_zs"] / N, av_y=out["sum_ys"] / N,
                  numbers=np.round(numbers).astype(np.int64))
     return dict(lo=lo, hi=hi, us=out["us"], zs=out["zs"], ys=out["ys"], means=means)
+
+
+def sharded_pde_ensemble(tmax, qs, *, p, u0, z0, y0, savepoints=4, precision="f32", adaptive=False, dt=None, runner=None,
+                         device=None, **solver_kw):
+    """PDEsolveensemble (ensemble.jl:58-85) as a parameter sweep over all ranks: rank r integrates the contiguous
+    block of the instances ``qs`` returned by ``shard_range`` as one device-resident batch, saved at
+    LinRange(0, tmax, savepoints); the ensemble means (plotting.jl:361-363) are one all-reduce of the per-rank sums.
+    ``u0/z0/y0`` are the shared initial state (one instance).  `runner(p, qs, U, Z, Y, times, ...)` returning
+    dict(us, zs, ys, sum_us, sum_zs, sum_ys) defaults to the CUDA solvers; the CPU tests inject a stand-in."""
+    rank, world = rank_world()
+    N = len(qs)
+    lo, hi = shard_range(N, rank, world)
+    times = np.linspace(0.0, tmax, savepoints) if savepoints > 1 else np.array([0.0])
+    L = int(qs[0].L)
+    Nx, Ny = p.N_x, p.N_y
+    if runner is None:
+        def runner(p, qloc, U, Z, Y, times, **kw):
+            from .pde import default_dt, pde_solve_adaptive_raw, pde_solve_raw
+            if adaptive:
+                return pde_solve_adaptive_raw(p, qloc, U, Z, Y, savetimes=times, precision=precision, want_sums=True, **solver_kw)
+            h = min(default_dt(p, qq) for qq in qloc) if dt is None else dt
+            per = max(1, int(np.ceil(tmax / max(savepoints - 1, 1) / h - 1e-9)))
+            nsteps = per * max(savepoints - 1, 1)
+            st = (np.arange(savepoints) * per).astype(np.int32) if savepoints > 1 else np.array([0], np.int32)
+            return pde_solve_raw(p, qloc, U, Z, Y, dt=tmax / nsteps, nsteps=nsteps, savesteps=st, precision=precision,
+                                 want_sums=True, **solver_kw)
+    if hi > lo:
+        B = hi - lo
+        U = np.stack([u0] * B, axis=-1); Z = np.stack([z0] * B, axis=-1); Y = np.stack([y0] * B, axis=-1)
+        out = runner(p, list(qs[lo:hi]), U, Z, Y, times)
+    else:  # more ranks than instances: contribute zeros
+        out = dict(us=np.zeros((Nx, Ny, 2, L, len(times), 0), order="F"), zs=np.zeros((2, 2, len(times), 0), order="F"),
+                   ys=np.zeros((2, L, len(times), 0), order="F"), sum_us=np.zeros((Nx, Ny, 2, L, len(times)), order="F"),
+                   sum_zs=np.zeros((2, 2, len(times)), order="F"), sum_ys=np.zeros((2, L, len(times)), order="F"))
+    allreduce_sums([out["sum_us"], out["sum_zs"], out["sum_ys"]], device)
+    means = dict(av_u=out["sum_us"] / N, av_z=out["sum_zs"] / N, av_y=out["sum_ys"] / N)
+    return dict(lo=lo, hi=hi, t=times, us=out["us"], zs=out["zs"], ys=out["ys"], means=means)

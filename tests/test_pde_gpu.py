@@ -245,3 +245,21 @@ def test_pde_against_golden_fixtures():
         uzy0, q2 = smm.constructinitial("4inf", (p, q))
         out = smm.pde_solve_raw(p, [q2], *uzy0.x, dt=1e-3, nsteps=10, savesteps=[10], precision=precision)
         assert rel(out["us"][..., 0, 0], g["u_rk4_10"]) < max(tol, 1e-10)
+
+
+def test_sharded_pde_sweep_single_rank_equals_direct(coarse):
+    """dist.sharded_pde_ensemble without a process group = the whole sweep on this GPU; its means are the sums of
+    smm_pde_solve divided by the number of instances, fixed-step and adaptive."""
+    from socialmediamodel_b200 import dist as D
+    p, q, uzy0 = coarse
+    qs = [q.merge(a=a) for a in (0.5, 1.0, 1.5)]
+    u0, z0, y0 = uzy0.x
+    for adaptive in (False, True):
+        res = D.sharded_pde_ensemble(0.02, qs, p=p, u0=u0, z0=z0, y0=y0, savepoints=3, precision="f64", adaptive=adaptive)
+        assert (res["lo"], res["hi"]) == (0, 3) and res["us"].shape == (p.N_x, p.N_y, 2, 4, 3, 3)
+        np.testing.assert_allclose(res["means"]["av_u"], res["us"].sum(axis=-1) / 3, rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(res["means"]["av_y"], res["ys"].sum(axis=-1) / 3, rtol=1e-13)
+        np.testing.assert_array_equal(res["us"][..., 0, 0], u0)
+    us, zs, ys, _ = smm.PDEsolveensemble(0.02, 3, savepoints=3, p=p, qs=[smm.parameters(a=a) for a in (0.5, 1.0, 1.5)],
+                                         save=False, precision="f64", adaptive=True)
+    assert rel(res["us"], us) < 1e-12
