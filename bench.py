@@ -196,7 +196,7 @@ def run_abm_ensemble(args, rank, world, local):
                                       _lib.ptr(s_ys), None)
         ctx.check(rc, "smm_abm_ensemble")
 
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(args.steps, 5))
     e2e_pass()
     barrier(world)
     t0 = time.perf_counter()
