@@ -7,15 +7,22 @@ from . import pde_oracle as P
 
 
 def _solve(u, z, y, T, savedt, dt, p, q, ci, cm):
-    nsave = int(round(T / savedt)); per = max(1, int(np.ceil(savedt / dt - 1e-9))); h = savedt / per
-    saved = P.rk_solve(u, z, y, nsave * per, h, p, q, ci, cm, save_every=per)
-    return saved  # list of (step,u,z,y), includes step 0
+    """Saved states at k*savedt <= T (saveat = 0:savedt:T, controlstrategies.jl:10,96) and the state at T itself
+    (the restart value sol(T), :101): when T is not a multiple of savedt the remainder is integrated separately."""
+    nsave = int(np.floor(T / savedt + 1e-9)); per = max(1, int(np.ceil(savedt / dt - 1e-9))); h = savedt / per
+    saved = P.rk_solve(u, z, y, nsave * per, h, p, q, ci, cm, save_every=per) if nsave > 0 else [(0, u, z, y)]
+    rem = T - nsave * savedt
+    final = saved[-1][1:]
+    if rem > 1e-12 * max(1.0, T):
+        nrem = max(1, int(np.ceil(rem / h - 1e-9)))
+        final = P.rk_solve(*final, nrem, rem / nrem, p, q, ci, cm)
+    return saved, final  # saved: list of (step,u,z,y) incl. step 0
 
 
 def prep(tequil, p, q, start="zero", savedt=0.05, dt=1e-3, countercontrol="no"):
     """controlstrategies.jl:5-63."""
     u0, z0, y0, ci, cm = P.uniforminit(p, q)
-    _, u, z, y = _solve(u0, z0, y0, tequil, savedt, dt, p, q, ci, cm)[-1]
+    u, z, y = _solve(u0, z0, y0, tequil, savedt, dt, p, q, ci, cm)[1]
     Lold = q["L"]
     if countercontrol == "no":
         L, ci2, cm2 = Lold + 1, np.append(ci, 3.0), cm
@@ -50,9 +57,9 @@ def fixedtargets(ts, targets, startlocation, p, q, ci, cm, uzy0, savedt=0.05, dt
         target = targets[:, n]; Dt = ts[n + 1] - ts[n]
         speed = np.linalg.norm(target - sl) / Dt
         q1 = dict(q, controltarget1=target, controlspeed1=speed)
-        saved = _solve(u, z, y, Dt, savedt, dt, p, q1, ci, cm)
+        saved, final = _solve(u, z, y, Dt, savedt, dt, p, q1, ci, cm)
         fsum += sum(s[1][:, :, :, L - 1].sum() / s[1].sum() for s in saved) * savedt
         pen += speed ** 2 * Dt
         sl = target
-        _, u, z, y = saved[-1]
+        u, z, y = final
     return fsum, np.sqrt(pen), (u, z, y)

@@ -21,24 +21,39 @@ from .setting import PDEconstruct, PDEconstructcoarse, parameterscontrol, parame
 
 
 def _segment_steps(T, savedt, dt):
-    nsave = int(round(T / savedt))
-    assert abs(nsave * savedt - T) < 1e-9 * max(1.0, T), "segment length must be a multiple of savedt"
+    nsave = int(np.floor(T / savedt + 1e-9))                 # saveat = 0:savedt:T keeps the points k*savedt <= T
     per = max(1, int(np.ceil(savedt / dt - 1e-9)))
     return nsave, per, savedt / per
 
 
 def _solve_segments(p, qs, u0, z0, y0, T, savedt, dt, precision, ctx, adapt=None):
-    """integrate B instances over [0,T], saving every savedt (both ends, like saveat=0:savedt:T).
-    adapt = None: fixed step; else dict(atol, rtol, dtmin) for the adaptive integrator (force_dtmin = true)."""
+    """Integrate B instances over [0,T].  Returns (out, times, final): the states saved every savedt (like
+    saveat=0:savedt:T, controlstrategies.jl:10,96) and ``final`` = (u, z, y) at T itself, the restart value
+    sol(T) (:101).  When T is not a multiple of savedt (the reference's defaults: Tmax/ntarg = 5/3) the reference
+    evaluates sol(T) on a saveat-only solution, i.e. by extrapolating the last saved interval; here the remainder
+    is integrated.  adapt = None: fixed step; else dict(atol, rtol, dtmin) for the adaptive integrator
+    (force_dtmin = true)."""
     nsave, per, h = _segment_steps(T, savedt, dt)
+    rem = T - nsave * savedt
+    has_rem = rem > 1e-12 * max(1.0, T)
     if adapt is not None:
         times = np.arange(nsave + 1) * savedt
-        out = pde_solve_adaptive_raw(p, qs, u0, z0, y0, savetimes=times, abstol=adapt["atol"], reltol=adapt["rtol"],
+        allt = np.append(times, T) if has_rem else times
+        out = pde_solve_adaptive_raw(p, qs, u0, z0, y0, savetimes=allt, abstol=adapt["atol"], reltol=adapt["rtol"],
                                      dtmin=adapt["dtmin"], force_dtmin=True, precision=precision, ctx=ctx)
-        return out, times
+        final = (out["us"][..., -1, :], out["zs"][..., -1, :], out["ys"][..., -1, :])
+        if has_rem:
+            out = dict(out, us=out["us"][..., :-1, :], zs=out["zs"][..., :-1, :], ys=out["ys"][..., :-1, :])
+        return out, times, final
     savesteps = (np.arange(nsave + 1) * per).astype(np.int32)
     out = pde_solve_raw(p, qs, u0, z0, y0, dt=h, nsteps=nsave * per, savesteps=savesteps, precision=precision, ctx=ctx)
-    return out, savesteps * h
+    final = (out["us"][..., -1, :], out["zs"][..., -1, :], out["ys"][..., -1, :])
+    if has_rem:
+        nrem = max(1, int(np.ceil(rem / h - 1e-9)))
+        tail = pde_solve_raw(p, qs, *final, dt=rem / nrem, nsteps=nrem, savesteps=np.array([nrem], np.int32),
+                             precision=precision, ctx=ctx)
+        final = (tail["us"][..., 0, :], tail["zs"][..., 0, :], tail["ys"][..., 0, :])
+    return out, savesteps * h, final
 
 
 def _adapt(integrator, atol, rtol, dtmin):
@@ -57,9 +72,9 @@ def prep(tequil=5.0, *, p=None, q=None, r=None, init="uniform", savedt=0.05, ato
     r = parameterscontrol() if r is None else r
     uzy0, q1 = constructinitial(init, (p, q))
     dt = default_dt(p, q1) if dt is None else dt
-    out, ts = _solve_segments(p, [q1], *uzy0.x, tequil, savedt, dt, precision, ctx, _adapt(integrator, atol, rtol, dtmin))
+    out, ts, final = _solve_segments(p, [q1], *uzy0.x, tequil, savedt, dt, precision, ctx, _adapt(integrator, atol, rtol, dtmin))
     sol1 = PDESolution(ts, [ArrayPartition(out["us"][..., m, 0], out["zs"][..., m, 0], out["ys"][..., m, 0]) for m in range(len(ts))])
-    u, z, y = sol1.u[-1].x
+    u, z, y = final[0][..., 0], final[1][..., 0], final[2][..., 0]
     Lold = q1.L
     ci = list(np.asarray(q1.controlled_inf, float))
     if countercontrol == "no":
@@ -120,11 +135,11 @@ def fixedtargets_objectives(ts, targets_list, startlocation, pq, r, uzy0, *, sav
             qs.append(q.merge(controltarget1=target, controlspeed1=speed))
             speedpen[k] += speed ** 2 * Dt
             start[k] = target
-        out, tsave = _solve_segments(p, qs, u, z, y, Dt, savedt, dt, precision, ctx, _adapt(integrator, atol, rtol, dtmin))
+        out, tsave, final = _solve_segments(p, qs, u, z, y, Dt, savedt, dt, precision, ctx, _adapt(integrator, atol, rtol, dtmin))
         us = out["us"]                                                       # [Nx,Ny,2,L,nsave,K]
         share = us[:, :, :, L - 1].sum(axis=(0, 1, 2)) / us.sum(axis=(0, 1, 2, 3))   # [nsave, K]
         followersum += share.sum(axis=0) * savedt                            # controlstrategies.jl:98
-        u, z, y = us[..., -1, :], out["zs"][..., -1, :], out["ys"][..., -1, :]
+        u, z, y = final
         if returnsol:
             for k in range(K):
                 sols[k].append(PDESolution(tsave, [ArrayPartition(us[..., m, k], out["zs"][..., m, k], out["ys"][..., m, k])

@@ -117,3 +117,25 @@ def test_PDEsolveopt_batched_compass_search(tmp_path, monkeypatch):
     assert ret in ("MAXEVAL_REACHED", "XTOL_REACHED", "FTOL_REACHED")
     import os
     assert os.path.exists("data/opt_strategy1LN_COBYLAfollowerzerofalseinf.npz")
+
+
+def test_segments_that_are_not_multiples_of_savedt():
+    """The reference's defaults (Tmax / ntarg = 5/3, savedt = 0.05) give control windows that are not multiples of the
+    save interval: the objective sums over the save points k*savedt <= Dt (saveat = 0:savedt:Dt) and the next window
+    starts from the state at Dt.  Float64 parity with the oracle, both integrators consistent."""
+    p = smm.PDEconstructcoarse()
+    po = P.pde_construct_coarse()
+    q = smm.parametersstronginf()
+    qo = A.default_q(eta=1.0)
+    r = smm.parameterscontrol(ntarg=2, start="zero", Tmax=0.05, tequil=0.025)
+    targets = np.array([[0.3, 0.3], [-0.5, 0.8]]).T
+    fs, sp, sols, Ps = smm.PDEsolvefixedtargets(targets.reshape(-1, order="F"), p=p, q=q, r=r, countercontrol="inf",
+                                                stubborntarget=[1.5, 1.5], savedt=0.01, dt=1e-3, precision="f64")
+    uzy0, sl, q2, ci2, cm2, slm = CO.prep(0.025, po, qo, start="zero", savedt=0.01, dt=1e-3, countercontrol="inf")
+    fr, pr, (ur, zr, yr) = CO.fixedtargets(np.array([0.0, 0.025, 0.05]), targets, sl, po, q2, ci2, cm2, uzy0, savedt=0.01,
+                                           dt=1e-3, countercontrol="inf", stubborntarget=np.array([1.5, 1.5]))
+    assert abs(fs - fr) < 1e-10 * max(1.0, abs(fr)) + 1e-12 and abs(sp - pr) < 1e-12
+    assert [len(s.t) for s in sols] == [3, 3, 3]                     # 0, 0.01, 0.02 in every window of 0.025
+    fa, sa, _, _ = smm.PDEsolvefixedtargets(targets.reshape(-1, order="F"), p=p, q=q, r=r, countercontrol="inf",
+                                            stubborntarget=[1.5, 1.5], savedt=0.01, precision="f64", integrator="adaptive")
+    assert abs(fa - fs) < 5e-3 * abs(fs) + 1e-7 and abs(sa - sp) < 1e-6
