@@ -60,7 +60,27 @@ def pde_case():
                 du5=du5, dz5=dz5, dy5=dy5, u_rk4_10=ur, z_rk4_10=zr, y_rk4_10=yr)
 
 
+def adaptive_control_case():
+    """Adaptive integrator (controller log + states) and one fixed-target control evaluation on the coarse grid."""
+    from oracle import control_oracle as CO
+    p = P.pde_construct_coarse()
+    q = A.default_q()
+    u0, z0, y0, ci, cm = P.uniforminit(p, q)
+    save = np.array([0.0, 0.02, 0.05])
+    states, log = P.bs3_adaptive(u0, z0, y0, save, p, q)
+    qo = A.default_q(eta=1.0)
+    uzy0, sl, q2, ci2, cm2, slm = CO.prep(0.02, p, qo, start="zero", savedt=0.01, dt=1e-3, countercontrol="inf")
+    ts = np.array([0.0, 0.025, 0.05]); targets = np.array([[0.3, 0.3], [-0.5, 0.8]]).T
+    fs, pen, (uf, zf, yf) = CO.fixedtargets(ts, targets, sl, p, q2, ci2, cm2, uzy0, savedt=0.01, dt=1e-3, countercontrol="inf",
+                                            stubborntarget=np.array([1.5, 1.5]))
+    return dict(save=save, log=np.array([(t, dt, n, float(a)) for t, dt, n, a in log]),
+                u_adapt=np.stack([s_[0] for s_ in states], axis=-1), y_adapt=np.stack([s_[2] for s_ in states], axis=-1),
+                ctrl_ts=ts, ctrl_targets=targets, ctrl_followersum=fs, ctrl_penalty=pen, ctrl_y_final=yf,
+                ctrl_u_final_sum=uf.sum(axis=(0, 1)))
+
+
 if __name__ == "__main__":
+    np.savez_compressed(os.path.join(HERE, "pde_adaptive_control.npz"), **adaptive_control_case())
     np.savez_compressed(os.path.join(HERE, "abm_dense_n60.npz"), **abm_case(101, 60, 25))
     np.savez_compressed(os.path.join(HERE, "abm_csr_n80.npz"), **abm_case(202, 80, 15, net_k=6))
     np.savez_compressed(os.path.join(HERE, "pde_coarse.npz"), **pde_case())

@@ -37,3 +37,22 @@ def test_pde_goldens_reproduced_by_oracle():
     du5, dz5, dy5 = P.rhs(g["u5"], g["z"], g["y5"], p, dict(q, L=5), g["ci5"], g["cm5"])
     np.testing.assert_allclose(du5, g["du5"], rtol=1e-11, atol=1e-12)
     np.testing.assert_allclose(dz5, g["dz5"], rtol=1e-12)
+
+
+def test_adaptive_and_control_goldens_reproduced_by_oracle():
+    from oracle import control_oracle as CO
+    g = np.load(os.path.join(G, "pde_adaptive_control.npz"))
+    p, q = P.pde_construct_coarse(), A.default_q()
+    u0, z0, y0, ci, cm = P.uniforminit(p, q)
+    states, log = P.bs3_adaptive(u0, z0, y0, g["save"], p, q)
+    got = np.array([(t, dt, n, float(a)) for t, dt, n, a in log])
+    assert got.shape == g["log"].shape
+    np.testing.assert_array_equal(got[:, 3], g["log"][:, 3])                 # accept / reject sequence
+    np.testing.assert_allclose(got[:, :2], g["log"][:, :2], rtol=1e-12)      # times and step sizes
+    np.testing.assert_allclose(np.stack([s[0] for s in states], axis=-1), g["u_adapt"], rtol=1e-11, atol=1e-14)
+    qo = A.default_q(eta=1.0)
+    uzy0, sl, q2, ci2, cm2, slm = CO.prep(0.02, p, qo, start="zero", savedt=0.01, dt=1e-3, countercontrol="inf")
+    fs, pen, (uf, zf, yf) = CO.fixedtargets(g["ctrl_ts"], g["ctrl_targets"], sl, p, q2, ci2, cm2, uzy0, savedt=0.01, dt=1e-3,
+                                            countercontrol="inf", stubborntarget=np.array([1.5, 1.5]))
+    assert abs(fs - float(g["ctrl_followersum"])) < 1e-13 and abs(pen - float(g["ctrl_penalty"])) < 1e-13
+    np.testing.assert_allclose(yf, g["ctrl_y_final"], rtol=1e-12)

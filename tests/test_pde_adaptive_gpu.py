@@ -173,3 +173,20 @@ def test_PDEsolveensemble_adaptive_parameter_sweep(coarse):
     np.testing.assert_array_equal(ua[..., 0, :], uf[..., 0, :])            # t = 0
     assert rel(ua, uf) < 5e-3 and np.abs(ya - yf).max() < 5e-3
     assert rel(ua[..., -1, 0], ua[..., -1, 2]) > 1e-2                      # the sweep parameter matters
+
+
+def test_adaptive_and_control_against_golden_fixture(coarse):
+    """tests/golden/pde_adaptive_control.npz (oracle-generated): controller log, states, control objective."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pde_adaptive_control.npz"))
+    p, q, uzy0 = coarse
+    out = smm.pde_solve_adaptive_raw(p, [q], *uzy0.x, savetimes=g["save"], precision="f64")
+    assert int(out["naccept"][0]) == int(g["log"][:, 3].sum()) and int(out["nreject"][0]) == int((1 - g["log"][:, 3]).sum())
+    assert rel(out["us"][..., 0], g["u_adapt"]) < 1e-10
+    assert np.abs(out["ys"][..., 0] - g["y_adapt"]).max() < 1e-10
+    r = smm.parameterscontrol(ntarg=2, start="zero", Tmax=0.05, tequil=0.02)
+    fs, pen, sols, Ps = smm.PDEsolvefixedtargets(g["ctrl_targets"].reshape(-1, order="F"), p=p, q=smm.parametersstronginf(), r=r,
+                                                 countercontrol="inf", stubborntarget=[1.5, 1.5], savedt=0.01, dt=1e-3,
+                                                 precision="f64")
+    assert abs(fs - float(g["ctrl_followersum"])) < 1e-10 * max(1.0, abs(fs)) + 1e-12
+    assert abs(pen - float(g["ctrl_penalty"])) < 1e-12
