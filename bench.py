@@ -208,7 +208,7 @@ def run_abm_ensemble(args, rank, world, local):
     # the per-realization densities cross PCIe as FP32 and are widened into the Float64 host array by the
     # library's host threads (csrc/host_widen.cpp); everything else is copied as Float64
     hw = os.environ.get("SMM_HOST_WIDEN")
-    widen = hw == "1" or (hw != "0" and (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", "1")) >= 6)
+    widen = hw == "1" or (hw != "0" and (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", "1")) >= 12)
     d2h = (out_us.nbytes // 2 if widen else out_us.nbytes) + zs.nbytes + ys.nbytes + s_us.nbytes + s_zs.nbytes + s_ys.nbytes
     h2d = C.sizeof(_lib.smm_params) + C.sizeof(_lib.smm_grid) + savesteps.nbytes
     mean_check = float(s_us.sum() * p.dV / (R * sp))

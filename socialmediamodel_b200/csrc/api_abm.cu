@@ -509,15 +509,16 @@ extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t preci
   if (sum_us && nsave) SMM_TRY(smm_scratch(ctx, S_SUMUS, per_real * 8, &d_sum_us));
   // FP32 mode: the chunks cross PCIe as FP32 (half the bytes) into a pinned ring and host threads widen
   // them into `us` (host_widen.cpp); each chunk is copied in kSub units so that DMA and widening overlap.
-  // Host widening halves the PCIe bytes.  Alone on a 16-core host it needs most of the cores (108 GB/s of
-  // Float64 output); with two ranks on a 24-core host it still wins (51 ms per pass against 65 ms for Float64
-  // over PCIe).  Below 6 threads per rank (threads = cores / LOCAL_WORLD_SIZE) the Float64 conversion stays on
-  // the device and the DMA writes the destination directly.  SMM_HOST_WIDEN=1 / 0 forces the choice.
+  // Host widening halves the PCIe bytes but needs host cores and memory bandwidth (108 GB/s of Float64 output on a
+  // 16-core host).  Measured per pass and rank: 1 GPU / 16 threads 28-35 ms with it, 41 ms without; 2 GPUs / 12
+  // threads each 51 vs 65 ms; 4 GPUs / 8 threads each 99 vs 82 ms; 8 GPUs / 4 threads each 202 vs 181 ms.  Hence:
+  // widen on the host when the rank has >= 12 threads (cores / LOCAL_WORLD_SIZE), else convert on the device and
+  // let the DMA write the destination directly.  SMM_HOST_WIDEN=1 / 0 forces the choice.
   const char* hw_env = getenv("SMM_HOST_WIDEN");
   bool host_widen = nchunks > 1 && precision == SMM_PREC_F32 && !(hw_env && hw_env[0] == '0');
   if (host_widen) {
     if (!ctx->hostpool) ctx->hostpool = smm_hostpool_create(0);
-    if (smm_hostpool_threads(ctx->hostpool) < 6 && !(hw_env && hw_env[0] == '1')) host_widen = false;
+    if (smm_hostpool_threads(ctx->hostpool) < 12 && !(hw_env && hw_env[0] == '1')) host_widen = false;
   }
   int kSub = 2;
   if (const char* e = getenv("SMM_HOST_WIDEN_SUB")) kSub = std::max(1, atoi(e));
