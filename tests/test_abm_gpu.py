@@ -370,3 +370,23 @@ def test_dense_kernel_symmetric_pair_schedule(n):
                 assert relerr(xs, o["xs"]) < RTOL_F32
                 assert relerr(np.transpose(out["infs"][:, :, :, k], (2, 0, 1)), o["infs"]) < RTOL_F32
     assert relerr(sym["xs"], ordered["xs"]) < 5e-6
+
+
+def test_c99_program_calls_the_abi(tmp_path):
+    """tests/c/abi_example.c, compiled with gcc against include/smm_b200.h and linked to libsmm_b200.so, runs the same
+    ensemble as the ctypes path and gets the same numbers: the boundary is usable from a compiled host language."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "socialmediamodel_b200")
+    exe = str(tmp_path / "abi_example")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-I", os.path.join(root, "include"), os.path.join(root, "tests", "c", "abi_example.c"),
+                           "-o", exe, "-L", libdir, "-lsmm_b200", "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    s_us, s_ys, launches = out.stdout.split()
+    p, q = smm.ABMconstruct(dx=0.2), smm.parameters(n=50)
+    ref = smm.abm_ensemble_raw(20, 4, p=p, q=q, savesteps=smm.savetimes_abm(20, 2), first_realization=1, seed=0, precision="f32")
+    assert abs(float(s_us) - ref["us"].sum()) <= 1e-9 * abs(ref["us"].sum())
+    assert abs(float(s_ys) - ref["sum_ys"].sum()) <= 1e-12 * max(1.0, abs(ref["sum_ys"].sum()))
+    assert int(launches) > 0

@@ -71,3 +71,11 @@ def test_setting_constructors_match_reference_defaults():
     assert W.shape == (47 * 47, 47 * 47) and np.all(np.diag(W) == 1)
     with pytest.raises(MemoryError):
         smm.PDEconstruct().K_matrix
+
+
+def test_header_is_valid_c99_and_cxx():
+    """include/smm_b200.h must be consumable by a C compiler (the boundary is a C ABI) and by C++."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "smm_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Wextra", "-pedantic", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++11", "-fsyntax-only", "-x", "c++", hdr])
