@@ -11,7 +11,11 @@ default-parameter ABM (n=250, L=4, M=2, NT=200, 4 save points, KDE on the 89x89 
 NCCL).  A "step" is one full pass: 1 024 x 200 time steps + KDE + ensemble sums.
 metric = ABM agent-steps/s (whole job).  `value`: results stay in HBM.  `e2e`: the same pass
 through the host-buffer C-ABI call the Julia shim makes (smm_abm_ensemble), D2H of us/zs/ys
-included.  Secondary workloads (C5 population kernel, C3/C4 PDE) are reported under "workloads".
+included, with its measured floor (PCIe and host-write rates of this box).
+"workloads" carries, at every N: the end-to-end variants (pageable caller array, Float32 densities,
+means only), configs[1] as written (1 024 realizations over ALL GPUs of the job; at N>1 also through
+ONE call from one process, smm_ctx_create_multi) and the PDE half of the metric (C4: 64 instances
+per GPU at 353x353, sharded by rank, means all-reduced); at N=1 also C1, C5 and C3.
 """
 import argparse
 import json
@@ -117,126 +121,191 @@ def max_over_ranks(x, world):
 # ------------------------------------------------------------------------------------------
 # C2: ABM ensemble (default)
 # ------------------------------------------------------------------------------------------
-def run_abm_ensemble(args, rank, world, local):
-    import ctypes as C
+# DRAM traffic per launch of the dominant kernels, from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum;
+# the .csv pages are under profiles/): kernel -> (bytes per launch at the benchmarked size, source)
+NCU_TRAFFIC = {
+    "abm_dense": (3.5e6, "profiles/r1_c2_dense_kde_full_raw_v3.csv (1 024 realizations x 200 steps)"),
+    "kde": (1.04e9, "profiles/r1_c2_dense_kde_full_raw_v3.csv"),
+    "pop_step": (1.03e9, "profiles/r1_pop_full_raw_v3.csv (n = 1e7)"),
+}
 
+
+class AbmEnsemble:
+    """Device buffers + the two timed calls of one ensemble shard of R realizations on this rank's GPU."""
+
+    def __init__(self, ctx, stream, R, first, cfg=C2):
+        import ctypes as C
+
+        import torch
+
+        import socialmediamodel_b200 as smm
+        from socialmediamodel_b200 import _lib
+        self.C, self._lib, self.ctx, self.stream, self.R, self.first, self.cfg = C, _lib, ctx, stream, R, first, cfg
+        NT, n, L, M, sp = cfg["NT"], cfg["n"], cfg["L"], cfg["M"], cfg["savepoints"]
+        self.p, self.q = smm.ABMconstruct(), smm.parameters(n=n, L=L)
+        self.Nx, self.Ny = self.p.X.shape
+        self.savesteps = smm.savetimes_abm(NT, sp)
+        self.per_real = self.Nx * self.Ny * 2 * L * sp
+        self.us_dev = torch.empty(R * self.per_real, dtype=torch.float32, device="cuda")
+        self.sum_us = torch.zeros(self.per_real, dtype=torch.float64, device="cuda")
+        self.sum_zs = torch.zeros(2 * 2 * sp, dtype=torch.float64, device="cuda")
+        self.sum_ys = torch.zeros(2 * L * sp, dtype=torch.float64, device="cuda")
+        self.numbers = torch.zeros(M * L * (NT + 1), dtype=torch.int64, device="cuda")
+        self.spar, self.grid = _lib.make_params(self.q, self.p), _lib.make_grid(self.p)
+
+    def device_pass(self, world):
+        C, cfg, ctx = self.C, self.cfg, self.ctx
+        rc = ctx.lib.smm_abm_ensemble_dev(ctx.h, C.byref(self.spar), 0, cfg["NT"], self.R, self.first, 0, None, None, cfg["savepoints"],
+                                          self._lib.ptr(self.savesteps), cfg["kde_sigma"], C.byref(self.grid),
+                                          C.c_void_p(self.us_dev.data_ptr()), C.c_void_p(self.sum_us.data_ptr()),
+                                          C.c_void_p(self.sum_zs.data_ptr()), C.c_void_p(self.sum_ys.data_ptr()),
+                                          C.c_void_p(self.numbers.data_ptr()))
+        ctx.check(rc, "smm_abm_ensemble_dev")
+        if world > 1:   # ensemble mean over all GPUs (plotting.jl:361-363): the path's only exchange
+            import torch.distributed as dist
+            dist.all_reduce(self.sum_us); dist.all_reduce(self.sum_zs); dist.all_reduce(self.sum_ys)
+
+    def time_device(self, steps, warmup, world, flush):
+        """K passes, CUDA events on the launching stream, L2 flushed between passes; max over ranks."""
+        import torch
+        ctx, stream = self.ctx, self.stream
+        for _ in range(warmup):
+            self.device_pass(world); flush.fill_(1)
+        barrier(world)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        kms = {"abm": [], "kde": [], "reduce": []}
+        l0 = ctx.launches
+        barrier(world)
+        t0 = time.perf_counter()
+        for k in range(steps):
+            ev[k][0].record(stream)
+            self.device_pass(world)
+            ev[k][1].record(stream)
+            flush.fill_(k & 1)                       # L2 flush between timed passes (outside the event pair)
+            ctx.sync()                               # collects the per-kernel CUDA-event times of this pass
+            kms["abm"].append(ctx.kernel_ms(0)); kms["kde"].append(ctx.kernel_ms(1)); kms["reduce"].append(ctx.kernel_ms(2))
+        barrier(world)
+        wall = time.perf_counter() - t0
+        dev_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev), world)
+        return dict(dev_ms=dev_ms, wall_s=wall, launches=ctx.launches - l0, kms={k: float(np.mean(v)) for k, v in kms.items()})
+
+    def time_e2e(self, steps, world, mode="f64", pinned=True, ctx=None, R=None, first=None):
+        """The host-buffer C-ABI call the Julia shim makes (smm_abm_ensemble), wall clock around the blocking call, max over
+        ranks.  mode: "f64" = the reference's return type (us Float64), "f32" = smm_abm_ensemble_f32, "means" = us NULL
+        (ensemble sums only).  pinned=False: the caller's `us` is ordinary pageable memory, as the Julia shim allocates it."""
+        C, _lib, cfg = self.C, self._lib, self.cfg
+        ctx = ctx or self.ctx
+        R = R or self.R
+        first = self.first if first is None else first
+        NT, L, sp = cfg["NT"], cfg["L"], cfg["savepoints"]
+        shape = (self.Nx, self.Ny, 2, L, sp, R)
+        dt = np.float32 if mode == "f32" else np.float64
+        out_us = None
+        if mode != "means":
+            out_us = ctx.pinned_empty(shape, dt) if pinned else np.zeros(shape, dt, order="F")   # zeros(): what the shim does
+        zs = np.empty((2, 2, sp, R), order="F"); ys = np.empty((2, L, sp, R), order="F")
+        s_us = np.empty((self.Nx, self.Ny, 2, L, sp), order="F"); s_zs = np.empty((2, 2, sp), order="F"); s_ys = np.empty((2, L, sp), order="F")
+        ns = _lib.smm_noise(); ns.mode = 0; ns.seed = 0
+        tail = (None, None, None, None, None, None, None, C.byref(ns), sp, _lib.ptr(self.savesteps), cfg["kde_sigma"],
+                C.byref(self.grid), _lib.ptr(out_us), _lib.ptr(zs), _lib.ptr(ys), _lib.ptr(s_us), _lib.ptr(s_zs), _lib.ptr(s_ys), None)
+
+        def one():
+            if mode == "f32":
+                rc = ctx.lib.smm_abm_ensemble_f32(ctx.h, C.byref(self.spar), NT, R, first, *tail)
+            else:
+                rc = ctx.lib.smm_abm_ensemble(ctx.h, C.byref(self.spar), 0, NT, R, first, *tail)
+            ctx.check(rc, "smm_abm_ensemble")
+
+        one()
+        barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        barrier(world)
+        secs = max_over_ranks(time.perf_counter() - t0, world)
+        small = zs.nbytes + ys.nbytes + s_us.nbytes + s_zs.nbytes + s_ys.nbytes
+        # the library widens FP32 -> Float64 on the host only for chunked shards (>= 512 realizations per GPU) and only
+        # when the GPU's share of the host cores is >= 12 threads (api_abm.cu); otherwise Float64 crosses PCIe
+        hw = os.environ.get("SMM_HOST_WIDEN")
+        multi = ctx.gpu_count > 1
+        share = ctx.gpu_count if multi else int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
+        threads = min(16, (os.cpu_count() or 1) // max(1, share))
+        widen = mode == "f64" and R // ctx.gpu_count >= 512 and (hw == "1" or (hw != "0" and threads >= 12))
+        us_bytes = 0 if out_us is None else out_us.nbytes
+        d2h = (us_bytes // 2 if widen else us_bytes) + small
+        mass = float(s_us.sum() * self.p.dV / (R * sp))
+        if out_us is not None and pinned:
+            ctx.free_pinned(out_us)
+        return dict(ms_per_step=secs / steps * 1e3, steps=steps, d2h_bytes_per_step=d2h,
+                    h2d_bytes_per_step=C.sizeof(_lib.smm_params) + C.sizeof(_lib.smm_grid) + self.savesteps.nbytes,
+                    host_bytes_written_per_step=us_bytes + small, host_widen=bool(widen), mass_check=mass,
+                    caller_array="pinned (smm_host_alloc)" if pinned else "pageable zeros(), as the Julia shim allocates it")
+
+
+def e2e_floor(ctx, host_bytes_f64, widen):
+    """Floor of the full-`us` call on this box: the densities must cross PCIe (as FP32 when the host widens, else Float64)
+    and be written into the caller's Float64 array; both rates are measured here (smm_microbench), the two overlap."""
+    d2h = ctx.microbench("d2h", 256 << 20)
+    wid = ctx.microbench("widen", 256 << 20)
+    pcie_ms = (host_bytes_f64 / 2 if widen else host_bytes_f64) / (d2h * 1e9) * 1e3
+    host_ms = host_bytes_f64 / (wid * 1e9) * 1e3 if widen else 0.0
+    return dict(floor_ms=max(pcie_ms, host_ms), pcie_d2h_gbs=d2h, host_widen_gbs=wid, pcie_ms=pcie_ms, host_write_ms=host_ms)
+
+
+def run_abm_ensemble(args, rank, world, local):
     import torch
 
     import socialmediamodel_b200 as smm
-    from socialmediamodel_b200 import _lib
 
     cfg = dict(C2)
     if args.realizations:
         cfg["R"] = args.realizations
     R, NT, n, L, M, sp = cfg["R"], cfg["NT"], cfg["n"], cfg["L"], cfg["M"], cfg["savepoints"]
-    p, q = smm.ABMconstruct(), smm.parameters(n=n, L=L)
     ctx = smm.Context(local)
     stream = torch.cuda.Stream()             # a real stream (the legacy default stream cannot be graph-captured)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    Nx, Ny = p.X.shape
-    savesteps = smm.savetimes_abm(NT, sp)
-    per_real = Nx * Ny * 2 * L * sp
-    us_dev = torch.empty(R * per_real, dtype=torch.float32, device="cuda")
-    sum_us = torch.zeros(per_real, dtype=torch.float64, device="cuda")
-    sum_zs = torch.zeros(2 * 2 * sp, dtype=torch.float64, device="cuda")
-    sum_ys = torch.zeros(2 * L * sp, dtype=torch.float64, device="cuda")
-    numbers = torch.zeros(M * L * (NT + 1), dtype=torch.int64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
-    spar, grid = _lib.make_params(q, p), _lib.make_grid(p)
-    first = rank * R + 1                                               # seeds k = 1..N (ensemble.jl:25)
-
-    def one_pass():
-        rc = ctx.lib.smm_abm_ensemble_dev(ctx.h, C.byref(spar), 0, NT, R, first, 0, None, None, sp,
-                                          _lib.ptr(savesteps), cfg["kde_sigma"], C.byref(grid),
-                                          C.c_void_p(us_dev.data_ptr()), C.c_void_p(sum_us.data_ptr()),
-                                          C.c_void_p(sum_zs.data_ptr()), C.c_void_p(sum_ys.data_ptr()),
-                                          C.c_void_p(numbers.data_ptr()))
-        ctx.check(rc, "smm_abm_ensemble_dev")
-        if world > 1:   # ensemble mean over all GPUs (plotting.jl:361-363): the path's only exchange
-            import torch.distributed as dist
-            dist.all_reduce(sum_us); dist.all_reduce(sum_zs); dist.all_reduce(sum_ys)
-
+    ens = AbmEnsemble(ctx, stream, R, rank * R + 1, cfg)               # seeds k = 1..N (ensemble.jl:25)
     sampler = ClockSampler(local); sampler.start()   # started before the warm-up so it is sampling by the timed region
     for _ in range(args.warmup):
-        one_pass(); flush.fill_(1)
-    barrier(world)
-    l0 = ctx.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kms = {"abm": [], "kde": [], "reduce": []}
+        ens.device_pass(world); flush.fill_(1)
     barrier(world)
     sampler.mark()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        ev[k][0].record(stream)
-        one_pass()
-        ev[k][1].record(stream)
-        flush.fill_(k & 1)                       # L2 flush between timed passes (outside the event pair)
-        ctx.sync()                               # collects the per-kernel CUDA-event times of this pass
-        kms["abm"].append(ctx.kernel_ms(0)); kms["kde"].append(ctx.kernel_ms(1)); kms["reduce"].append(ctx.kernel_ms(2))
-    barrier(world)
-    t_wall = time.perf_counter() - t_wall0
-    launches = ctx.launches - l0
+    t = ens.time_device(args.steps, 0, world, flush)
     clocks = sampler.stop()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    dev_ms = max_over_ranks(dev_ms, world)
-    agent_steps = world * R * NT * n * args.steps
-    value = agent_steps / (dev_ms * 1e-3)
+    dev_ms, kms, launches = t["dev_ms"], t["kms"], t["launches"]
+    value = world * R * NT * n * args.steps / (dev_ms * 1e-3)
 
     # ---- e2e: host-buffer C-ABI call (what the Julia shim's ABMsolveensemble makes) ------------
-    out_us = ctx.pinned_empty((Nx, Ny, 2, L, sp, R))
-    zs = np.empty((2, 2, sp, R), order="F"); ys = np.empty((2, L, sp, R), order="F")
-    s_us = np.empty((Nx, Ny, 2, L, sp), order="F"); s_zs = np.empty((2, 2, sp), order="F"); s_ys = np.empty((2, L, sp), order="F")
-    ns = _lib.smm_noise(); ns.mode = 0; ns.seed = 0
-
-    def e2e_pass():
-        rc = ctx.lib.smm_abm_ensemble(ctx.h, C.byref(spar), 0, NT, R, first, None, None, None, None, None, None, None,
-                                      C.byref(ns), sp, _lib.ptr(savesteps), cfg["kde_sigma"], C.byref(grid),
-                                      _lib.ptr(out_us), _lib.ptr(zs), _lib.ptr(ys), _lib.ptr(s_us), _lib.ptr(s_zs),
-                                      _lib.ptr(s_ys), None)
-        ctx.check(rc, "smm_abm_ensemble")
-
     e2e_steps = max(1, min(args.steps, 5))
-    e2e_pass()
-    barrier(world)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_pass()
-    barrier(world)
-    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
-    e2e_value = world * R * NT * n * e2e_steps / e2e_s
-    # the per-realization densities cross PCIe as FP32 and are widened into the Float64 host array by the
-    # library's host threads (csrc/host_widen.cpp); everything else is copied as Float64
-    hw = os.environ.get("SMM_HOST_WIDEN")
-    widen = hw == "1" or (hw != "0" and (os.cpu_count() or 1) // int(os.environ.get("LOCAL_WORLD_SIZE", "1")) >= 12)
-    d2h = (out_us.nbytes // 2 if widen else out_us.nbytes) + zs.nbytes + ys.nbytes + s_us.nbytes + s_zs.nbytes + s_ys.nbytes
-    h2d = C.sizeof(_lib.smm_params) + C.sizeof(_lib.smm_grid) + savesteps.nbytes
-    mean_check = float(s_us.sum() * p.dV / (R * sp))
-    ctx.free_pinned(out_us)
+    e = ens.time_e2e(e2e_steps, world, mode="f64", pinned=True)
+    e2e_value = world * R * NT * n / (e["ms_per_step"] * 1e-3)
+    floor = e2e_floor(ctx, R * ens.per_real * 8, e["host_widen"]) if rank == 0 else None
 
     peaks = measured_peaks()
-    abm_ms = float(np.mean(kms["abm"]))
+    abm_ms = kms["abm"]
     pairs = R * NT * n * n                                              # ordered pairs per launch (SURVEY 8d)
     sym = os.environ.get("SMM_ABM_SYM", "1") != "0"
     mufu_per_pair = 1 if sym else 2    # sqrt + ex2 per evaluated pair; the symmetric kernel evaluates unordered pairs
-    mufu_peak = 148 * 16 * peaks["sm_max_mhz"] * 1e6 / mufu_per_pair / 1e9   # G ordered pairs/s, 16 MUFU/clk/SM
-    # issue-slot view (ncu, profiles/r1_abm_dense_sym_*): warp instructions per realization-step, 4 issue slots/clk/SM
-    winst = 19860 if sym else 27700
-    issue_ms = R * NT * winst / (148 * 4 * peaks["sm_max_mhz"] * 1e6) * 1e3
+    mufu_meas = ctx.microbench("mufu")                                   # G MUFU/s, measured on this GPU right now
+    mufu_nominal = 148 * 16 * peaks["sm_max_mhz"] * 1e6 / 1e9
+    mufu_peak = mufu_meas / mufu_per_pair                                # G ordered pairs/s
     roofline = dict(kernel="abm_dense_kernel<float,sym>" if sym else "abm_dense_kernel<float>", bound="mufu",
                     achieved=pairs / (abm_ms * 1e-3) / 1e9, peak=mufu_peak, unit="Gpair/s",
-                    frac=pairs / (abm_ms * 1e-3) / 1e9 / mufu_peak, traffic=None,
+                    frac=pairs / (abm_ms * 1e-3) / 1e9 / mufu_peak, traffic=NCU_TRAFFIC["abm_dense"][0],
+                    traffic_source=NCU_TRAFFIC["abm_dense"][1],
                     note="state lives in shared memory; not HBM-bound (SURVEY 8d). Algorithmic work: 2 MUFU (sqrt, ex2) per "
-                         "UNORDERED pair = 1 per ordered pair (w_ij = w_ji), "
-                         f"peak = 148 SM x 16 MUFU/clk x {peaks['sm_max_mhz']:.0f} MHz (derived, nominal clock); "
-                         "the kernel is co-limited by instruction issue (issue_frac)",
-                    issue_frac=issue_ms / abm_ms, warp_inst_per_realization_step=winst,
+                         "UNORDERED pair = 1 per ordered pair (w_ij = w_ji); peak = MUFU issue rate MEASURED by smm_microbench "
+                         f"(ex2.approx chains, {mufu_meas:.0f} G/s; nominal 148 SM x 16/clk x {peaks['sm_max_mhz']:.0f} MHz = "
+                         f"{mufu_nominal:.0f} G/s)",
+                    mufu_measured_gops=mufu_meas, mufu_nominal_gops=mufu_nominal,
                     kernel_ms=abm_ms, share_of_step=abm_ms * args.steps / dev_ms if world == 1 else None)
-    kde_ms = float(np.mean(kms["kde"]))
-    kde_bytes = R * per_real * 4
+    kde_ms = kms["kde"]
+    kde_bytes = R * ens.per_real * 4
     roofline_kde = dict(kernel="kde_kernel<float>", bound="hbm", achieved=kde_bytes / (kde_ms * 1e-3) / 1e9,
                         peak=peaks["hbm_gbs"], unit="GB/s", frac=kde_bytes / (kde_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                        traffic=None, kernel_ms=kde_ms, peak_source=peaks["source"])
+                        traffic=NCU_TRAFFIC["kde"][0], kernel_ms=kde_ms, peak_source=peaks["source"]) if kde_ms > 0 else None
     res = dict(metric="abm_agent_steps_per_s", value=value, unit="agent-steps/s", n_gpus=world, steps=args.steps,
                warmup=args.warmup, ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak",
                vs_baseline=None, dtype="f32", data="synthetic",
@@ -244,15 +313,81 @@ def run_abm_ensemble(args, rank, world, local):
                                     "KDE 89x89 sigma=0.1, Philox noise" % (R, NT, n, L, M, sp),
                            realizations_per_gpu=R, parallelism=f"ensemble-shard x{world}",
                            l2="flushed between timed passes (256 MiB write); working set is shared memory"),
-               e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                        ms_per_step=e2e_s / e2e_steps * 1e3, steps=e2e_steps,
-                        host_bytes_written_per_step=out_us.nbytes + zs.nbytes + ys.nbytes + s_us.nbytes + s_zs.nbytes + s_ys.nbytes,
+               e2e=dict(value=e2e_value, unit="agent-steps/s", h2d_bytes_per_step=e["h2d_bytes_per_step"],
+                        d2h_bytes_per_step=e["d2h_bytes_per_step"], ms_per_step=e["ms_per_step"], steps=e2e_steps,
+                        host_bytes_written_per_step=e["host_bytes_written_per_step"], floor=floor,
                         api="smm_abm_ensemble (host buffers; us/zs/ys + ensemble sums returned as Float64; "
-                            "us crosses PCIe as FP32 and is widened by host threads)" if widen else
+                            "us crosses PCIe as FP32 and is widened by host threads)" if e["host_widen"] else
                             "smm_abm_ensemble (host buffers; us/zs/ys + ensemble sums copied back as Float64)"),
                gpu_launches=launches, clocks=clocks, roofline=roofline, roofline_kde=roofline_kde,
-               wall_ms_per_step=t_wall / args.steps * 1e3, ensemble_mass_check=mean_check)
-    return res, ctx
+               wall_ms_per_step=t["wall_s"] / args.steps * 1e3, ensemble_mass_check=e["mass_check"])
+    return res, ctx, ens, flush
+
+
+def abm_variants(args, ctx, ens, flush, rank, world):
+    """Secondary ABM ensemble measurements: the end-to-end call with a pageable caller array / Float32 densities / means
+    only, and configs[1] exactly as written (1 024 realizations over ALL GPUs of the job = 1 024 / world per GPU)."""
+    import torch
+    cfg = ens.cfg
+    NT, n = cfg["NT"], cfg["n"]
+    out = {}
+    R = ens.R
+    steps = max(1, min(args.steps, 3))
+    for name, kw in (("e2e_pageable_caller_array", dict(mode="f64", pinned=False)),
+                     ("e2e_float32_densities", dict(mode="f32", pinned=True)),
+                     ("e2e_means_only", dict(mode="means"))):
+        try:
+            e = ens.time_e2e(steps, world, **kw)
+            e["value"] = world * R * NT * n / (e["ms_per_step"] * 1e-3)
+            e["unit"] = "agent-steps/s"
+            out[name] = e
+        except Exception as ex:
+            out[name] = dict(error=f"{type(ex).__name__}: {ex}")
+    # configs[1] as written: 1 024 realizations sharded over the job's GPUs (at 1 GPU also the 128-realization shard a
+    # rank runs at 8 GPUs, to show the small-ensemble occupancy)
+    shard_sizes = [C2["R"] // world] if world > 1 else [128]
+    for Rs in shard_sizes:
+        try:
+            sub = AbmEnsemble(ctx, ens.stream, Rs, rank * Rs + 1, cfg)
+            k = max(3, min(args.steps, 10))
+            t = sub.time_device(k, 3, world, flush)
+            e = sub.time_e2e(steps, world, mode="f64", pinned=True)
+            em = sub.time_e2e(steps, world, mode="means")
+            out[f"abm_C2_strong_{Rs}_per_gpu"] = dict(
+                workload=f"configs[1] as written: {Rs * world} realizations over {world} GPU(s) = {Rs} per GPU",
+                metric="abm_agent_steps_per_s", scaling="strong", value=world * Rs * NT * n * k / (t["dev_ms"] * 1e-3),
+                ms_per_step=t["dev_ms"] / k, kernel_ms=t["kms"],
+                e2e=dict(value=world * Rs * NT * n / (e["ms_per_step"] * 1e-3), ms_per_step=e["ms_per_step"],
+                         d2h_bytes_per_step=e["d2h_bytes_per_step"]),
+                e2e_means_only=dict(value=world * Rs * NT * n / (em["ms_per_step"] * 1e-3), ms_per_step=em["ms_per_step"],
+                                    d2h_bytes_per_step=em["d2h_bytes_per_step"]))
+            del sub
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            out[f"abm_C2_strong_{Rs}_per_gpu"] = dict(error=f"{type(ex).__name__}: {ex}")
+    return out
+
+
+def abm_one_call_multi_gpu(args, ens, world):
+    """configs[1] through ONE call from ONE process (rank 0), every GPU of the job behind one context
+    (smm_ctx_create_multi: one host thread per GPU, NCCL all-reduce of the sums inside the library) -- what the Julia
+    shim's unchanged ABMsolveensemble(200, 1024) does with devices = all.  The other ranks idle at the next barrier."""
+    import socialmediamodel_b200 as smm
+    cfg = ens.cfg
+    NT, n, R = cfg["NT"], cfg["n"], C2["R"]
+    out = {}
+    ctx = smm.Context(devices=list(range(world)))
+    try:
+        out["gpus"], out["nccl"] = ctx.gpu_count, ctx.nccl_active
+        for name, kw in (("full_us_float64", dict(mode="f64", pinned=True)), ("float32_densities", dict(mode="f32", pinned=True)),
+                         ("means_only", dict(mode="means"))):
+            e = ens.time_e2e(3, 1, ctx=ctx, R=R, first=1, **kw)
+            out[name] = dict(value=R * NT * n / (e["ms_per_step"] * 1e-3), unit="agent-steps/s", ms_per_step=e["ms_per_step"],
+                             d2h_bytes_per_step=e["d2h_bytes_per_step"], mass_check=e["mass_check"])
+    finally:
+        ctx.close()
+    out["workload"] = f"configs[1]: ABMsolveensemble(200, {R}) in ONE call, realizations sharded over {world} GPUs inside the library"
+    return out
 
 
 # ------------------------------------------------------------------------------------------
@@ -294,13 +429,23 @@ def run_abm_pop(args, ctx, n=10_000_000, L=64, k=16, steps=20, warmup=3):
     peaks = measured_peaks()
     bytes_per = 23 + 12 * (k + 1)                              # B = 23 + 12 deg
     ach = n * bytes_per / (ms_step * 1e-3) / 1e9
+    # measured ceiling of the access pattern itself: (k+1) random 8-byte gathers per agent from the same 80 MB table
+    # under the same persisting-L2 window, index rows streamed, nothing else (smm_microbench GATHER)
+    try:
+        gather_peak = ctx.microbench("gather", n)              # G gathers/s
+    except Exception:
+        gather_peak = None
+    gathers = n * (k + 1) / (ms_step * 1e-3) / 1e9
     return dict(workload=f"C5 ABM population n={n}, L={L}, CSR out-degree {k}+self, Philox, FP32",
                 metric="abm_agent_steps_per_s", value=n / (ms_step * 1e-3), ms_per_step=ms_step,
                 fp64_reevaluation_rate=st["fp64_reevaluations"] / (st["steps"] * n),
                 followers_conserved=bool(int(got["numbers"].sum()) == n),
                 roofline=dict(kernel="pop_step_kernel<float>", bound="hbm", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s",
-                              frac=ach / peaks["hbm_gbs"], traffic=None, bytes_per_agent_step=bytes_per,
-                              peak_source=peaks["source"]))
+                              frac=ach / peaks["hbm_gbs"], traffic=NCU_TRAFFIC["pop_step"][0], traffic_source=NCU_TRAFFIC["pop_step"][1],
+                              bytes_per_agent_step=bytes_per, peak_source=peaks["source"]),
+                gather_roofline=dict(bound="l2-gather", achieved=gathers, peak=gather_peak, unit="Ggather/s",
+                                     frac=gathers / gather_peak if gather_peak else None,
+                                     note="peak = pure random float2 gather kernel, same table / window / degree, measured now"))
 
 
 def run_abm_c1(ctx):
@@ -354,14 +499,14 @@ def _c_port_run(realizations, first=1):
     p, q = A.default_p(), A.default_q()
     st = E.savetimes_abm(C2["NT"], C2["savepoints"])
     t0 = time.perf_counter()
-    tot, used = CO.ensemble_bench(C2["NT"], realizations, p, q, st, first=first)
+    tot, used = CO.ensemble_bench(C2["NT"], realizations, p, q, st, first=first, threads=host_threads())
     dt = time.perf_counter() - t0
     assert np.isfinite(tot)
     return realizations * C2["NT"] * C2["n"], dt, used
 
 
 def cpu_baseline_abm(realizations=None):
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     try:
         _c_port_run(cores)                                    # warm-up (library load, thread pool)
         realizations = realizations or min(C2["R"], 64 * cores)   # ~10 s on 16 cores: the whole C2 ensemble
@@ -383,26 +528,54 @@ def cpu_baseline_abm(realizations=None):
                            f"C port unavailable: {type(e).__name__}", seconds=dt)
 
 
+def host_threads():
+    """Host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which silently turned the
+    reference arm into a single-thread run at N >= 2; the reference arm runs on rank 0 alone, so it takes every core."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    per_step = 4 * max(cores, 8)
-    for _ in range(min(args.warmup, 1)):
-        _c_port_run(cores)
-    done, dt, used = 0, 0.0, cores
-    for s in range(args.steps):
-        d, t, used = _c_port_run(per_step, first=1 + s * per_step)
-        done += d; dt += t
-    v = done / dt
+    threads = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    # each step = the whole C2 ensemble (1 024 realizations), i.e. the native arm's per-GPU step: same config.  On 16
+    # cores that is ~9.5 s per step; --steps is capped so that the arm ends within a few minutes.
+    per_step = C2["R"]
+    budget_s = float(os.environ.get("SMM_REF_BUDGET_S", "150"))
+    from oracle import abm_oracle as A
+    from oracle import c_oracle as CO
+    from oracle import ensemble_oracle as E
+    p, q = A.default_p(), A.default_q()
+    st = E.savetimes_abm(C2["NT"], C2["savepoints"])
+
+    def run(R, first):
+        t0 = time.perf_counter()
+        tot, used = CO.ensemble_bench(C2["NT"], R, p, q, st, first=first, threads=threads)
+        assert np.isfinite(tot)
+        return time.perf_counter() - t0, used
+
+    t_w, used = run(4 * threads, 1)                      # warm-up (library load, thread pool) + a rate estimate
+    est_step = t_w * per_step / (4 * threads)
+    steps = max(1, min(args.steps, int(budget_s / max(est_step, 1e-9))))
+    dt = 0.0
+    for s in range(steps):
+        t, used = run(per_step, 1 + s * per_step)
+        dt += t
+    v = steps * per_step * C2["NT"] * C2["n"] / dt
     sample = (f"each step = {per_step} realizations of C2 (NT=200, n=250, KDE at 4 save points) on {used} host threads: C "
               "restatement of the reference's loops (oracle/abm_oracle.c, Float64; Julia is not installed, the reference "
-              "itself cannot run here)")
+              f"itself cannot run here); {steps} of the requested {args.steps} steps timed (time cap {budget_s:.0f} s)")
     print(json.dumps(dict(impl="reference", metric="abm_agent_steps_per_s", value=v, unit="agent-steps/s",
-                          n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=dt / args.steps * 1e3,
+                          n_gpus=args.gpus, steps=steps, warmup=args.warmup, ms_per_step=dt / steps * 1e3,
                           higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                          config=dict(workload="C2 ABMsolveensemble (bounded sample)", sample=sample),
+                          config=dict(workload="C2 ABMsolveensemble: %d realizations x NT=%d, n=%d, L=%d, M=%d, %d save points, "
+                                               "KDE 89x89 sigma=0.1" % (per_step, C2["NT"], C2["n"], C2["L"], C2["M"], C2["savepoints"]),
+                                      realizations_per_gpu=per_step, sample=sample),
                           cpu_baseline=dict(value=v, unit="agent-steps/s", cores=used, kind="port", sample=sample),
                           e2e=dict(value=v, unit="agent-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                           gpu_launches=0)))
@@ -425,19 +598,33 @@ def main():
     if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_extra:
         cpu = cpu_baseline_abm()          # before CUDA is initialised in this process (fork-safe)
     rank, world, local = dist_setup(args.gpus)
-    res, ctx = run_abm_ensemble(args, rank, world, local)
-    if rank == 0 and world == 1 and not args.no_extra:
+    res, ctx, ens, flush = run_abm_ensemble(args, rank, world, local)
+    if not args.no_extra:
         extra = {}
-        for name, fn in (("abm_C1", lambda: run_abm_c1(ctx)), ("abm_population_C5", lambda: run_abm_pop(args, ctx))):
+
+        def attempt(name, fn, everyone=True):
+            """a secondary workload must not lose the headline line; `everyone`: all ranks take part (collectives inside)"""
+            if not everyone and rank != 0:
+                return
             try:
-                extra[name] = fn()
-            except Exception as e:  # a secondary workload must not lose the headline line
-                extra[name] = dict(error=f"{type(e).__name__}: {e}")
-        try:
-            from bench_pde import run_pde_workloads
-            extra.update(run_pde_workloads(ctx))
-        except ImportError:
-            pass
+                r = fn()
+                if isinstance(r, dict) and name is None:
+                    extra.update(r)
+                else:
+                    extra[name] = r
+            except Exception as e:
+                extra[name or fn.__name__] = dict(error=f"{type(e).__name__}: {e}")
+
+        attempt(None, lambda: abm_variants(args, ctx, ens, flush, rank, world))
+        from bench_pde import run_pde_c4_job, run_pde_workloads
+        attempt("pde_C4", lambda: run_pde_c4_job(ctx, rank, world))          # every rank: its shard of the sweep + all-reduce
+        if world == 1:
+            attempt("abm_C1", lambda: run_abm_c1(ctx))
+            attempt("abm_population_C5", lambda: run_abm_pop(args, ctx))
+            attempt(None, lambda: run_pde_workloads(ctx))
+        else:
+            barrier(world)
+            attempt("abm_C2_one_call", lambda: abm_one_call_multi_gpu(args, ens, world), everyone=False)
         res["workloads"] = extra
         res["cpu_baseline"] = cpu
     if world > 1:

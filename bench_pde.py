@@ -69,11 +69,65 @@ def run_pde_sweep(ctx, dx=0.025, B=64, steps=10, dt=None):
                                    "76 B/cell-step counts the stencil/RK traffic only (SURVEY 8d)"))
 
 
+def run_pde_c4_job(ctx, rank, world, B=64, steps=3, dx=0.0125):
+    """C4 (configs[3]): the 512-instance parameter sweep at the 4x refined grid, 64 instances per GPU.  Rank r integrates
+    lattice points r*64 .. r*64+63 as one device-resident batch (8 GPUs = the whole lattice; fewer GPUs = its first
+    world*64 points: weak scaling), every rank times its own RK4 steps with CUDA events, the job's time is the max over
+    ranks, and the ensemble-mean state (plotting.jl:361-363) is formed with one NCCL all-reduce of the per-rank sums --
+    the path's only exchange (ensemble.jl:58-85: the instance loop :69-70 is embarrassingly parallel)."""
+    import torch
+
+    import socialmediamodel_b200 as smm
+    from bench import barrier, max_over_ranks
+    p = smm.PDEconstruct(dx=dx)
+    qs_all = _sweep_qs(smm, 512)
+    qs = [qs_all[(rank * B + k) % 512] for k in range(B)]
+    uzy0, _ = smm.constructinitial("4inf", (p, qs[0]))
+    dt = min(smm.default_dt(p, q) for q in qs_all)
+    pb = smm.PDEBatch(p, qs, *uzy0.x, precision="f32", shared_init=True, ctx=ctx)
+    pb.step(dt, 2); ctx.sync()
+    barrier(world)
+    ms = []
+    for _ in range(3):
+        pb.step(dt, steps); ctx.sync()
+        ms.append(ctx.kernel_ms(4) / steps)
+        barrier(world)
+    ms_step = max_over_ranks(float(np.median(ms)), world)
+    # ensemble mean over the whole job: per-rank sums on the device, one all-reduce
+    per = p.N_x * p.N_y * 2 * 4
+    su = torch.zeros(per, dtype=torch.float64, device="cuda"); sz = torch.zeros(4, dtype=torch.float64, device="cuda")
+    sy = torch.zeros(8, dtype=torch.float64, device="cuda")
+    import ctypes as C
+    ctx.check(ctx.lib.smm_pde_batch_sum_dev(ctx.h, pb.h, C.c_void_p(su.data_ptr()), C.c_void_p(sz.data_ptr()),
+                                            C.c_void_p(sy.data_ptr())), "smm_pde_batch_sum_dev")
+    ctx.sync()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(su); dist.all_reduce(sz); dist.all_reduce(sy)
+    t1.record(); torch.cuda.synchronize()
+    allreduce_ms = t0.elapsed_time(t1)
+    mean_mass = float(su.sum().item()) * p.dV / (B * world)
+    pb.close()
+    cells = p.N_x * p.N_y * 2 * 4 * B * world
+    peaks = _peaks()
+    ach = cells / world * 76 / (ms_step * 1e-3) / 1e9      # per GPU: 19 B per cell per RK stage (SURVEY 8d)
+    return dict(workload=f"C4 parameter sweep: {B} PDE instances per GPU x {world} GPU(s), {p.N_x}x{p.N_y}x2x4, RK4 dt={dt:.2e}, "
+                         "lattice points sharded by rank, ensemble mean all-reduced",
+                metric="pde_cell_steps_per_s", scaling="weak", n_gpus=world, value=cells / (ms_step * 1e-3), ms_per_step=ms_step,
+                instances_per_gpu=B, mean_all_reduce_ms=allreduce_ms, ensemble_mean_mass=mean_mass,
+                roofline=dict(kernel="pde_stage_kernel<float,4> + FFT convolution kernels", bound="hbm", achieved=ach,
+                              peak=peaks["hbm_gbs"], unit="GB/s (per GPU)", frac=ach / peaks["hbm_gbs"], traffic=None,
+                              bytes_per_cell_step=76, peak_source=peaks["source"],
+                              note="whole RK4 step per GPU: 4 x (FFT evaluation of the interaction force + fused stage kernel); "
+                                   "76 B/cell-step counts the stencil/RK traffic only (SURVEY 8d)"))
+
+
 def run_pde_workloads(ctx):
     out = {}
     for name, fn in (("pde_C3", lambda: run_pde_c3(ctx)),
-                     ("pde_sweep_177", lambda: run_pde_sweep(ctx, dx=0.025, B=16, steps=4)),
-                     ("pde_C4_shard_353", lambda: run_pde_sweep(ctx, dx=0.0125, B=64, steps=3))):
+                     ("pde_sweep_177", lambda: run_pde_sweep(ctx, dx=0.025, B=16, steps=4))):
         try:
             out[name] = fn()
         except Exception as e:

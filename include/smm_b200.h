@@ -22,10 +22,10 @@
  *    failure is available from smm_last_error().  No exception crosses the ABI and there is
  *    NO CPU fallback: without a CUDA device every compute entry point fails with
  *    SMM_ERR_CUDA.
- *  - One smm_ctx is bound to one GPU (one process per GPU; ensemble shards are selected by
- *    `first_realization` / the instance range and reduced by the caller, see
- *    socialmediamodel_b200/dist.py).  Entry points are re-entrant per context, not
- *    thread-safe on the same context.
+ *  - smm_ctx_create binds a context to one GPU (one process per GPU: ensemble shards are selected by
+ *    `first_realization` / the instance range and reduced by the caller, socialmediamodel_b200/dist.py);
+ *    smm_ctx_create_multi puts several GPUs behind one context and shards inside the call.  Entry points
+ *    are re-entrant per context, not thread-safe on the same context.
  */
 #ifndef SMM_B200_H
 #define SMM_B200_H
@@ -93,6 +93,16 @@ typedef struct {
 int smm_version(void);
 int smm_device_count(void);                         /* 0 when no CUDA device is visible */
 int smm_ctx_create(int device, smm_ctx** out);      /* binds to `device`; creates its stream */
+/* Several GPUs of one box behind ONE context (single process).  ngpus <= 0: every visible device;
+ * device_ids NULL: devices 0..ngpus-1.  The ensemble entry points called on such a context (smm_abm_ensemble,
+ * smm_abm_ensemble_f32, smm_pde_solve) shard their realizations / instances over the GPUs -- contiguous blocks, one
+ * host thread per GPU, every GPU writing its slice of the caller's arrays -- and reduce the ensemble sums with one
+ * NCCL all-reduce (ncclCommInitAll communicators; libnccl is resolved with dlopen, host reduction without it).  All
+ * other entry points run on the first device.  This is what lets the unchanged reference call
+ * ABMsolveensemble(200, 1024) (ensemble.jl:11) use the whole box from one Julia task. */
+int smm_ctx_create_multi(int ngpus, const int* device_ids, smm_ctx** out);
+int smm_ctx_gpu_count(const smm_ctx* ctx);          /* GPUs behind the context (1 for smm_ctx_create) */
+int smm_ctx_nccl_active(const smm_ctx* ctx);        /* 1 when the ensemble sums of a multi-GPU context go through NCCL */
 int smm_ctx_destroy(smm_ctx* ctx);
 int smm_ctx_sync(smm_ctx* ctx);                     /* wait for the context's stream */
 int smm_ctx_set_stream(smm_ctx* ctx, void* cuda_stream); /* borrow a caller stream (e.g. torch's) */
@@ -106,6 +116,16 @@ int64_t smm_ctx_launch_count(const smm_ctx* ctx);
  * class of the most recent call: 0 ABM step, 1 KDE, 2 ensemble reduce, 3 PDE convolution,
  * 4 PDE stencil/RK stage, 5 PDE moments.  Negative when that class did not run. */
 double smm_ctx_kernel_ms(const smm_ctx* ctx, int which);
+
+/* Measured denominators for the rooflines MEASURED_PEAKS.json does not carry, and for the floor of the end-to-end
+ * ensemble call (bench.py): each runs a few-line kernel / copy, timed with CUDA events after a warm-up.
+ *   SMM_MB_MUFU   result = G ex2.approx/s          (bound of the dense ABM pair loop)
+ *   SMM_MB_GATHER result = G random 8-byte gathers/s from an L2-resident table of `size` entries (C5 neighbour reads)
+ *   SMM_MB_LDS    result = GB/s of conflict-free 16-byte shared-memory loads (bound of the FFT passes)
+ *   SMM_MB_D2H    result = GB/s of a `size`-byte device -> pinned-host copy
+ *   SMM_MB_WIDEN  result = GB/s of Float64 written by the context's host threads widening `size` bytes of Float32 */
+typedef enum { SMM_MB_MUFU = 0, SMM_MB_GATHER = 1, SMM_MB_LDS = 2, SMM_MB_D2H = 3, SMM_MB_WIDEN = 4 } smm_microbench_id;
+int smm_microbench(smm_ctx* ctx, int32_t which, uint64_t size, double* result);
 
 /* ---- ABM ---------------------------------------------------------------------------- */
 
@@ -157,6 +177,18 @@ int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t precision, int32
                      int32_t nsave, const int32_t* savesteps, double kde_sigma, const smm_grid* grid,
                      double* us, double* zs, double* ys, double* sum_us, double* sum_zs, double* sum_ys,
                      int64_t* numbers);
+
+/* smm_abm_ensemble with the per-realization densities returned as Float32 (an extension outside the reference's
+ * API for callers that accept it: `us` is 2.08 GB of Float64 for 1 024 realizations at 89x89, the FP32 state holds
+ * no more than 24 bits of it).  us Julia Float32 [Nx,Ny,2,L,nsave,R]; everything else as in smm_abm_ensemble with
+ * precision = SMM_PREC_F32.  Passing us = NULL to either entry point returns only the ensemble sums (means-only:
+ * 1 MB instead of 2 GB). */
+int smm_abm_ensemble_f32(smm_ctx* ctx, const smm_params* q, int32_t NT, int32_t R, int64_t first_realization,
+                         const double* x0, const int32_t* state, const int32_t* follow0, const double* inf0,
+                         const double* media0, const int32_t* rowptr, const int32_t* colidx, const smm_noise* noise,
+                         int32_t nsave, const int32_t* savesteps, double kde_sigma, const smm_grid* grid,
+                         float* us, double* zs, double* ys, double* sum_us, double* sum_zs, double* sum_ys,
+                         int64_t* numbers);
 
 /* Device-resident variant of smm_abm_ensemble for callers that keep results on the GPU
  * (bench `value`, NCCL reduction of the sums by torch.distributed): Philox noise, on-device

@@ -191,18 +191,21 @@ def abm_solve(NT, x0, state, follow0, inf0, media0, xi, u1, u2, p, q, net=None,
     """ABMsolve (abm.jl:154-217) with injected initial condition and draws.
     xi[NT,n,2], u1[NT,n], u2[NT,n].  Returns dict with xs[NT+1,n,2], follows[NT+1,n] (0-based;
     the reference's stateinfs = follows+1 as Float64, abm.jl:164,212), infs[NT+1,L,2],
-    meds[NT+1,M,2], min_margin."""
+    meds[NT+1,M,2], min_margin, margins[NT,n] (distance of every agent's decision variables to their thresholds at
+    each step: which FP32 decisions are near-ties of the Float64 arithmetic)."""
     x, inf, media, follow = x0.copy(), inf0.copy(), media0.copy(), follow0.copy()
     xs, fs, infs, meds = [x.copy()], [follow.copy()], [inf.copy()], [media.copy()]
     mm = np.inf
+    margins = []
     for k in range(NT):
         x, inf, media, follow, margin = abm_step(
             x, inf, media, follow, state, xi[k], u1[k], u2[k], p, q, net,
             None if xi_inf is None else xi_inf[k], None if xi_med is None else xi_med[k])
         mm = min(mm, np.nanmin(margin)) if np.isfinite(margin).any() else mm
+        margins.append(margin)
         xs.append(x.copy()); fs.append(follow.copy()); infs.append(inf.copy()); meds.append(media.copy())
     return dict(xs=np.array(xs), follows=np.array(fs), infs=np.array(infs), meds=np.array(meds),
-                min_margin=mm)
+                min_margin=mm, margins=np.array(margins).reshape(NT, -1))
 
 
 def follower_numbers(follows, state, L):

@@ -61,6 +61,9 @@ PROTOTYPES = {
     "smm_version": (C.c_int, []),
     "smm_device_count": (C.c_int, []),
     "smm_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "smm_ctx_create_multi": (C.c_int, [C.c_int, _P, C.POINTER(_P)]),
+    "smm_ctx_gpu_count": (C.c_int, [_P]),
+    "smm_ctx_nccl_active": (C.c_int, [_P]),
     "smm_ctx_destroy": (C.c_int, [_P]),
     "smm_ctx_sync": (C.c_int, [_P]),
     "smm_ctx_set_stream": (C.c_int, [_P, _P]),
@@ -69,6 +72,7 @@ PROTOTYPES = {
     "smm_host_free": (C.c_int, [_P, _P]),
     "smm_ctx_launch_count": (_I64, [_P]),
     "smm_ctx_kernel_ms": (_D, [_P, C.c_int]),
+    "smm_microbench": (C.c_int, [_P, _I32, _U64, C.POINTER(_D)]),
     "smm_abm_init": (C.c_int, [_P, C.POINTER(smm_params), _U64, _I64, _I32, _P, _P, _P, _P, _P]),
     "smm_abm_draws": (C.c_int, [_P, _I32, _U64, _I64, _I32, _P, _P, _P]),
     "smm_abm_solve": (C.c_int, [_P, C.POINTER(smm_params), _I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P,
@@ -76,6 +80,9 @@ PROTOTYPES = {
     "smm_abm_ensemble": (C.c_int, [_P, C.POINTER(smm_params), _I32, _I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P,
                                    C.POINTER(smm_noise), _I32, _P, _D, C.POINTER(smm_grid),
                                    _P, _P, _P, _P, _P, _P, _P]),
+    "smm_abm_ensemble_f32": (C.c_int, [_P, C.POINTER(smm_params), _I32, _I32, _I64, _P, _P, _P, _P, _P, _P, _P,
+                                       C.POINTER(smm_noise), _I32, _P, _D, C.POINTER(smm_grid),
+                                       _P, _P, _P, _P, _P, _P, _P]),
     "smm_abm_ensemble_dev": (C.c_int, [_P, C.POINTER(smm_params), _I32, _I32, _I32, _I64, _U64, _P, _P, _I32, _P, _D,
                                        C.POINTER(smm_grid), _P, _P, _P, _P, _P]),
     "smm_kde": (C.c_int, [_P, _I32, _I32, _I32, _P, _P, _P, _D, C.POINTER(smm_grid), _P]),
@@ -162,15 +169,32 @@ class Context:
     cuda:LOCAL_RANK (one process per GPU)."""
     _default = None
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """``devices``: None = one GPU (``device``); "all" or a list of device ids = several GPUs behind this one
+        context (smm_ctx_create_multi): the ensemble calls shard over them inside the call."""
         self.lib = load()
         h = _P()
-        rc = self.lib.smm_ctx_create(int(device), C.byref(h))
+        if devices is None:
+            rc = self.lib.smm_ctx_create(int(device), C.byref(h))
+            what = f"smm_ctx_create({device})"
+        else:
+            ids = None if isinstance(devices, str) else np.ascontiguousarray(devices, np.int32)
+            rc = self.lib.smm_ctx_create_multi(0 if ids is None else len(ids), ptr(ids), C.byref(h))
+            what = f"smm_ctx_create_multi({devices})"
+            device = 0 if ids is None else int(ids[0])
         if rc != 0:
-            raise SmmError(f"smm_ctx_create({device}) failed [{rc}]: {self.lib.smm_last_error(None).decode()}")
+            raise SmmError(f"{what} failed [{rc}]: {self.lib.smm_last_error(None).decode()}")
         self.h = h
         self.device = device
         self._pinned = {}
+
+    @property
+    def gpu_count(self):
+        return int(self.lib.smm_ctx_gpu_count(self.h))
+
+    @property
+    def nccl_active(self):
+        return bool(self.lib.smm_ctx_nccl_active(self.h))
 
     @classmethod
     def default(cls):
@@ -194,6 +218,13 @@ class Context:
 
     def kernel_ms(self, which):
         return float(self.lib.smm_ctx_kernel_ms(self.h, which))
+
+    def microbench(self, which, size=0):
+        """smm_microbench: measured MUFU / gather / shared-memory / PCIe / host-widening rates (see include/smm_b200.h)."""
+        ids = dict(mufu=0, gather=1, lds=2, d2h=3, widen=4)
+        r = _D(0.0)
+        self.check(self.lib.smm_microbench(self.h, ids[which], int(size), C.byref(r)), f"smm_microbench({which})")
+        return float(r.value)
 
     def pinned_empty(self, shape, dtype=np.float64, order="F"):
         """NumPy array backed by pinned host memory from smm_host_alloc (DMA target)."""

@@ -81,6 +81,7 @@ extern "C" int smm_ctx_destroy(smm_ctx* ctx) {
   for (int i = 0; i < 2; i++) if (ctx->ev_h[i]) cudaEventDestroy(ctx->ev_h[i]);
   if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
   smm_hostpool_destroy(ctx->hostpool);
+  smm_multi_destroy(ctx->multi);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -470,14 +471,19 @@ extern "C" int smm_abm_solve(smm_ctx* ctx, const smm_params* q, int32_t precisio
   return smm_collect_times(ctx);
 }
 
-extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t precision, int32_t NT, int32_t R,
-                                int64_t first_realization, const double* x0, const int32_t* state,
-                                const int32_t* follow0, const double* inf0, const double* media0,
-                                const int32_t* rowptr, const int32_t* colidx, const smm_noise* noise, int32_t nsave,
-                                const int32_t* savesteps, double kde_sigma, const smm_grid* grid, double* us,
-                                double* zs, double* ys, double* sum_us, double* sum_zs, double* sum_ys,
-                                int64_t* numbers) {
+// `us_any` is the caller's Float64 array, or (us_f32) a Float32 array of the same shape that receives the FP32
+// device densities without widening (half the PCIe bytes, half the host bytes written).
+static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precision, int32_t NT, int32_t R,
+                             int64_t first_realization, const double* x0, const int32_t* state,
+                             const int32_t* follow0, const double* inf0, const double* media0,
+                             const int32_t* rowptr, const int32_t* colidx, const smm_noise* noise, int32_t nsave,
+                             const int32_t* savesteps, double kde_sigma, const smm_grid* grid, void* us_any, bool us_f32,
+                             double* zs, double* ys, double* sum_us, double* sum_zs, double* sum_ys,
+                             int64_t* numbers) {
+  double* us = us_f32 ? nullptr : static_cast<double*>(us_any);
+  float* us32 = us_f32 ? static_cast<float*>(us_any) : nullptr;
   SMM_REQUIRE(ctx, ctx != nullptr, "smm_abm_ensemble: ctx is NULL");
+  SMM_REQUIRE(ctx, !us32 || precision == SMM_PREC_F32, "smm_abm_ensemble_f32: Float32 densities need precision = SMM_PREC_F32");
   SMM_REQUIRE(ctx, noise != nullptr, "smm_abm_ensemble: noise is NULL");
   SMM_TRY(check_grid(ctx, grid, "smm_abm_ensemble"));
   SMM_REQUIRE(ctx, kde_sigma > 0, "smm_abm_ensemble: kde_sigma must be > 0");
@@ -490,7 +496,7 @@ extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t preci
   // realizations are processed in chunks and the device->host copy of chunk c overlaps the
   // simulation of chunk c+1 (copy stream, double-buffered Float64 staging).
   int nchunks = 1;
-  if (us && nsave && R >= 512) nchunks = std::min(4, R / 256);
+  if (us_any && nsave && R >= 512) nchunks = std::min(4, R / 256);
   const int Rc0 = (R + nchunks - 1) / nchunks;
   if (nchunks > 1 && !ctx->copy_stream) {
     SMM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -515,16 +521,15 @@ extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t preci
   // widen on the host when the rank has >= 12 threads (cores / LOCAL_WORLD_SIZE), else convert on the device and
   // let the DMA write the destination directly.  SMM_HOST_WIDEN=1 / 0 forces the choice.
   const char* hw_env = getenv("SMM_HOST_WIDEN");
-  bool host_widen = nchunks > 1 && precision == SMM_PREC_F32 && !(hw_env && hw_env[0] == '0');
+  bool host_widen = nchunks > 1 && !us32 && precision == SMM_PREC_F32 && !(hw_env && hw_env[0] == '0');
   if (host_widen) {
-    if (!ctx->hostpool) ctx->hostpool = smm_hostpool_create(0);
+    if (!ctx->hostpool) ctx->hostpool = smm_hostpool_create(ctx->host_threads);
     if (smm_hostpool_threads(ctx->hostpool) < 12 && !(hw_env && hw_env[0] == '1')) host_widen = false;
   }
   int kSub = 2;
   if (const char* e = getenv("SMM_HOST_WIDEN_SUB")) kSub = std::max(1, atoi(e));
   const size_t unit_real = ((size_t)Rc0 + kSub - 1) / kSub;  // realizations per copy unit
   if (host_widen) {
-    if (!ctx->hostpool) ctx->hostpool = smm_hostpool_create(0);
     for (int i = 0; i < 2; i++)
       if (!ctx->ev_h[i]) SMM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_h[i], cudaEventDisableTiming));
     const size_t need = 2 * unit_real * per_real * 4;
@@ -565,10 +570,11 @@ extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t preci
     }
     return SMM_OK;
   };
-  auto issue_copy = [&](const Pending& pc) -> int {  // D2H of a converted chunk on the copy stream
+  auto issue_copy = [&](const Pending& pc) -> int {  // D2H of a staged chunk on the copy stream
     const int sl = pc.chunk & 1;
     SMM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[sl], 0));
-    SMM_CUDA(ctx, cudaMemcpyAsync(us + pc.r0 * per_real, stage[sl], pc.rc * per_real * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (us32) SMM_CUDA(ctx, cudaMemcpyAsync(us32 + pc.r0 * per_real, stage[sl], pc.rc * per_real * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    else SMM_CUDA(ctx, cudaMemcpyAsync(us + pc.r0 * per_real, stage[sl], pc.rc * per_real * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
     SMM_CUDA(ctx, cudaEventRecord(ctx->ev_copied[sl], ctx->copy_stream));
     return SMM_OK;
   };
@@ -590,7 +596,7 @@ extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t preci
       if (noise->xi_med) E.noise.xi_med = noise->xi_med + r0 * NT * M * 2;
     }
     E.nsave = nsave; E.savesteps = savesteps;
-    E.want_kde = us || sum_us; E.kde_sigma = kde_sigma; E.grid = *grid;
+    E.want_kde = us_any || sum_us; E.kde_sigma = kde_sigma; E.grid = *grid;
     E.want_yz = want_yz; E.want_numbers = numbers != nullptr;
     if (want_yz && nsave) { E.ys_ext = (double*)d_ys_all + r0 * nsave * L * 2; E.zs_ext = (double*)d_zs_all + r0 * nsave * M * 2; }
     E.d_numbers = (int64_t*)d_numbers; E.numbers_keep = c > 0; E.no_reset = c > 0;
@@ -600,9 +606,10 @@ extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t preci
       SMM_TRY(smm_launch_ensemble_sum(ctx, E.d_us, precision, (int)rc, per_real, (double*)d_sum_us, c > 0));
       smm_toc(ctx, SMM_K_REDUCE);
     }
-    if (us && nsave) {
+    if (us_any && nsave) {
       if (nchunks == 1) {
-        SMM_TRY(download_real(ctx, E.d_us, rc * per_real, precision, us));
+        if (us32) SMM_TRY(download(ctx, E.d_us, rc * per_real * 4, us32));
+        else SMM_TRY(download_real(ctx, E.d_us, rc * per_real, precision, us));
       } else if (host_widen) {
         const int sl = c & 1;
         SMM_TRY(smm_scratch(ctx, sl ? S_STAGE_B : S_STAGE_A, (size_t)Rc0 * per_real * 4, &stage[sl]));
@@ -616,9 +623,10 @@ extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t preci
         SMM_TRY(pump(drain_end, units.size()));
       } else {
         const int sl = c & 1;
-        SMM_TRY(smm_scratch(ctx, sl ? S_STAGE_B : S_STAGE_A, (size_t)Rc0 * per_real * 8, &stage[sl]));
+        SMM_TRY(smm_scratch(ctx, sl ? S_STAGE_B : S_STAGE_A, (size_t)Rc0 * per_real * (us32 ? 4 : 8), &stage[sl]));
         if (c >= 2) SMM_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[sl], 0));  // staging slot free again
-        SMM_TRY(smm_launch_convert_real_to_f64(ctx, E.d_us, (double*)stage[sl], rc * per_real, precision));
+        if (us32) SMM_CUDA(ctx, cudaMemcpyAsync(stage[sl], E.d_us, rc * per_real * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        else SMM_TRY(smm_launch_convert_real_to_f64(ctx, E.d_us, (double*)stage[sl], rc * per_real, precision));
         SMM_CUDA(ctx, cudaEventRecord(ctx->ev_ready[sl], ctx->stream));
         // the previous chunk's copy is issued only now, after this chunk's kernels are queued, so that a
         // host-blocking copy into pageable memory still overlaps them
@@ -630,23 +638,80 @@ extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t preci
   if (pending.chunk >= 0) SMM_TRY(issue_copy(pending));
   if (host_widen) SMM_TRY(pump(units.size(), units.size()));
   void* p;
-  if (sum_us && nsave) SMM_TRY(download(ctx, d_sum_us, per_real * 8, sum_us));
+  // shard mode (member of a multi-GPU context): the sums stay in device scratch (S_SUMUS / S_SUMZS / S_SUMYS /
+  // S_NUMBERS) for the NCCL all-reduce in multi.cu, which also delivers them to the caller
+  const bool deliver = !ctx->shard_mode;
+  if (sum_us && nsave && deliver) SMM_TRY(download(ctx, d_sum_us, per_real * 8, sum_us));
   if (sum_zs && nsave) {
     SMM_TRY(smm_scratch(ctx, S_SUMZS, nsave * M * 2 * 8, &p));
     SMM_TRY(smm_launch_small_sum(ctx, (const double*)d_zs_all, R, (int)(nsave * M * 2), (double*)p));
-    SMM_TRY(download(ctx, p, nsave * M * 2 * 8, sum_zs));
+    if (deliver) SMM_TRY(download(ctx, p, nsave * M * 2 * 8, sum_zs));
   }
   if (sum_ys && nsave) {
     SMM_TRY(smm_scratch(ctx, S_SUMYS, nsave * L * 2 * 8, &p));
     SMM_TRY(smm_launch_small_sum(ctx, (const double*)d_ys_all, R, (int)(nsave * L * 2), (double*)p));
-    SMM_TRY(download(ctx, p, nsave * L * 2 * 8, sum_ys));
+    if (deliver) SMM_TRY(download(ctx, p, nsave * L * 2 * 8, sum_ys));
   }
   if (zs && nsave) SMM_TRY(download(ctx, d_zs_all, (size_t)R * nsave * M * 2 * 8, zs));
   if (ys && nsave) SMM_TRY(download(ctx, d_ys_all, (size_t)R * nsave * L * 2 * 8, ys));
-  if (numbers) SMM_TRY(download(ctx, d_numbers, (size_t)(NT + 1) * L * M * 8, numbers));
+  if (numbers && deliver) SMM_TRY(download(ctx, d_numbers, (size_t)(NT + 1) * L * M * 8, numbers));
   SMM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->copy_stream) SMM_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   return smm_collect_times(ctx);
+}
+
+// An error return must not leave DMA into the caller's arrays (or into the pinned ring and the staging slots the
+// next call reuses) in flight: drain both streams before handing the error back.
+static int abm_ensemble_guarded(smm_ctx* ctx, int rc) {
+  if (rc != SMM_OK && ctx) {
+    const std::string keep = ctx->err;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    cudaGetLastError();
+    ctx->err = keep;
+  }
+  return rc;
+}
+
+extern "C" int smm_abm_ensemble(smm_ctx* ctx, const smm_params* q, int32_t precision, int32_t NT, int32_t R,
+                                int64_t first_realization, const double* x0, const int32_t* state,
+                                const int32_t* follow0, const double* inf0, const double* media0,
+                                const int32_t* rowptr, const int32_t* colidx, const smm_noise* noise, int32_t nsave,
+                                const int32_t* savesteps, double kde_sigma, const smm_grid* grid, double* us,
+                                double* zs, double* ys, double* sum_us, double* sum_zs, double* sum_ys,
+                                int64_t* numbers) {
+  if (ctx && ctx->multi)
+    return smm_multi_abm_ensemble(ctx, q, precision, NT, R, first_realization, x0, state, follow0, inf0, media0, rowptr, colidx, noise,
+                                  nsave, savesteps, kde_sigma, grid, us, false, zs, ys, sum_us, sum_zs, sum_ys, numbers);
+  return abm_ensemble_guarded(ctx, abm_ensemble_impl(ctx, q, precision, NT, R, first_realization, x0, state, follow0, inf0, media0, rowptr,
+                                                     colidx, noise, nsave, savesteps, kde_sigma, grid, us, false, zs, ys, sum_us,
+                                                     sum_zs, sum_ys, numbers));
+}
+
+extern "C" int smm_abm_ensemble_f32(smm_ctx* ctx, const smm_params* q, int32_t NT, int32_t R, int64_t first_realization,
+                                    const double* x0, const int32_t* state, const int32_t* follow0, const double* inf0,
+                                    const double* media0, const int32_t* rowptr, const int32_t* colidx,
+                                    const smm_noise* noise, int32_t nsave, const int32_t* savesteps, double kde_sigma,
+                                    const smm_grid* grid, float* us, double* zs, double* ys, double* sum_us,
+                                    double* sum_zs, double* sum_ys, int64_t* numbers) {
+  if (ctx && ctx->multi)
+    return smm_multi_abm_ensemble(ctx, q, SMM_PREC_F32, NT, R, first_realization, x0, state, follow0, inf0, media0, rowptr, colidx,
+                                  noise, nsave, savesteps, kde_sigma, grid, us, true, zs, ys, sum_us, sum_zs, sum_ys, numbers);
+  return abm_ensemble_guarded(ctx, abm_ensemble_impl(ctx, q, SMM_PREC_F32, NT, R, first_realization, x0, state, follow0, inf0, media0,
+                                                     rowptr, colidx, noise, nsave, savesteps, kde_sigma, grid, us, true, zs, ys,
+                                                     sum_us, sum_zs, sum_ys, numbers));
+}
+
+// entry for multi.cu: one shard of a multi-GPU ensemble on the member context `ctx`
+int smm_abm_ensemble_shard(smm_ctx* ctx, const smm_params* q, int32_t precision, int32_t NT, int32_t R, int64_t first_realization,
+                           const double* x0, const int32_t* state, const int32_t* follow0, const double* inf0, const double* media0,
+                           const int32_t* rowptr, const int32_t* colidx, const smm_noise* noise, int32_t nsave,
+                           const int32_t* savesteps, double kde_sigma, const smm_grid* grid, void* us, bool us_f32, double* zs,
+                           double* ys, double* sum_us, double* sum_zs, double* sum_ys, int64_t* numbers) {
+  return abm_ensemble_guarded(ctx, abm_ensemble_impl(ctx, q, precision, NT, R, first_realization, x0, state, follow0, inf0, media0, rowptr,
+                                                     colidx, noise, nsave, savesteps, kde_sigma, grid, us, us_f32, zs, ys, sum_us,
+                                                     sum_zs, sum_ys, numbers));
 }
 
 extern "C" int smm_abm_ensemble_dev(smm_ctx* ctx, const smm_params* q, int32_t precision, int32_t NT, int32_t R,
@@ -713,11 +778,19 @@ extern "C" int smm_kde(smm_ctx* ctx, int32_t n, int32_t L, int32_t precision, co
 // ---------------------------------------------------------------------------------------
 // large resident population (C5)
 // ---------------------------------------------------------------------------------------
+// The persisting-L2 carve-out is a per-device limit shared by every population (and every other user of the
+// device in this process): the value found before the first population raised it is restored when the last
+// population that holds a share is freed.
+static struct { int users; size_t saved_limit; } g_l2_carveout[64];
+
 static void pop_free(smm_abm_pop* p) {
   if (!p) return;
-  if (p->l2_persist_bytes > 0) {  // give the persisting carve-out back
-    cudaCtxResetPersistingL2Cache();
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+  if (p->l2_persist_bytes > 0 && p->device >= 0 && p->device < 64) {
+    auto& c = g_l2_carveout[p->device];
+    if (--c.users == 0) {  // last user: give the carve-out back
+      cudaCtxResetPersistingL2Cache();
+      cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c.saved_limit);
+    }
   }
   for (int i = 0; i < 2; i++) { if (p->x[i]) cudaFree(p->x[i]); if (p->ent[i]) cudaFree(p->ent[i]); }
   for (int i = 0; i < 3; i++) if (p->acc[i]) cudaFree(p->acc[i]);
@@ -769,6 +842,7 @@ extern "C" int smm_abm_pop_create(smm_ctx* ctx, const smm_params* q, int32_t pre
   SMM_CUDA(ctx, cudaSetDevice(ctx->device));
   smm_abm_pop* p = new smm_abm_pop();
   memset(p, 0, sizeof *p);
+  p->device = -1;
   p->k = make_abm_const(q);
   p->precision = precision; p->seed = seed; p->step = 0; p->has_net = rowptr != nullptr; p->nnz = nnz;
   // fixed-point scale: |sum| <= n * max|x| must stay below 2^62
@@ -788,9 +862,18 @@ extern "C" int smm_abm_pop_create(smm_ctx* ctx, const smm_params* q, int32_t pre
     if (!(ev && ev[0] == '0') && rowptr && cudaGetDeviceProperties(&prop, ctx->device) == cudaSuccess &&
         prop.persistingL2CacheMaxSize > 0) {
       size_t want = std::min((size_t)prop.persistingL2CacheMaxSize, n * 2 * (precision == SMM_PREC_F64 ? (size_t)8 : (size_t)4));
-      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
-        p->l2_persist_bytes = want;
-        p->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+      size_t cur = 0;
+      if (ctx->device < 64 && cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) == cudaSuccess) {
+        auto& c = g_l2_carveout[ctx->device];
+        if (c.users == 0) c.saved_limit = cur;
+        if (cur >= want || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+          c.users++;
+          p->device = ctx->device;
+          p->l2_persist_bytes = want;
+          p->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        } else {
+          cudaGetLastError();
+        }
       } else {
         cudaGetLastError();
       }
@@ -853,6 +936,10 @@ extern "C" int smm_abm_pop_step(smm_ctx* ctx, smm_abm_pop* p, int32_t nsteps) {
 
 extern "C" int smm_abm_pop_step_injected(smm_ctx* ctx, smm_abm_pop* p, const double* xi, const double* u1, const double* u2) {
   SMM_REQUIRE(ctx, ctx && p && xi && u1 && u2, "smm_abm_pop_step_injected: NULL argument");
+  // the entity noise of abm.jl:181-196 has no injected form here: refuse rather than silently drop it
+  if (p->k.sigmahat != 0.0 || p->k.sigmatilde != 0.0)
+    return smm_fail(ctx, SMM_ERR_UNSUPPORTED, "smm_abm_pop_step_injected: sigmahat=%g / sigmatilde=%g: injected influencer / media noise is "
+                    "not supported for populations (use smm_abm_solve with xi_inf / xi_med, or Philox steps)", p->k.sigmahat, p->k.sigmatilde);
   SMM_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t n = p->k.n;
   void *dxi, *du1, *du2;

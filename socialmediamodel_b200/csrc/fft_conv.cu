@@ -465,13 +465,13 @@ static int fft_conv_launch(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, vo
   size_t sm_inv = ((size_t)3 * (P + 1) + P) * sizeof(real2);
   const int rt = P >= 512 ? 256 : 128;
   static const bool pdl = !(getenv("SMM_PDE_PDL") && getenv("SMM_PDE_PDL")[0] == '0');
-  SMM_CUDA(ctx, smm_launch_pdl(pdl, fft_rows_fwd_kernel<real>, dim3((p->Ny + 1) / 2, p->B), dim3(rt), sm_rows, ctx->stream,
+  SMM_CUDA(ctx, smm_launch_pdl(pdl ? ctx->sm_count : 0, fft_rows_fwd_kernel<real>, dim3((p->Ny + 1) / 2, p->B), dim3(rt), sm_rows, ctx->stream,
                                p->Ny, p->Nx, p->Pw, d, (const real*)rhosum, (real2*)p->ahat, (const real2*)p->tw));
   const int ct = (P * cols) / 2 >= 2048 ? 512 : ((P * cols) / 2 >= 256 ? 256 : 128);
-  SMM_CUDA(ctx, smm_launch_pdl(pdl, fft_cols_kernel<real, 0>, dim3((hp1 + cols - 1) / cols, p->B), dim3(ct), sm_cols, ctx->stream,
+  SMM_CUDA(ctx, smm_launch_pdl(pdl ? ctx->sm_count : 0, fft_cols_kernel<real, 0>, dim3((hp1 + cols - 1) / cols, p->B), dim3(ct), sm_cols, ctx->stream,
                                p->Ny, p->Ny, d, cols, 1.0, (const real2*)p->ahat, (const real2*)p->khat, (real2*)p->g,
                                (const real2*)p->tw, gstride));
-  SMM_CUDA(ctx, smm_launch_pdl(pdl, fft_rows_inv_kernel<real>, dim3((p->Ny + 1) / 2, p->B), dim3(rt), sm_inv, ctx->stream,
+  SMM_CUDA(ctx, smm_launch_pdl(pdl ? ctx->sm_count : 0, fft_rows_inv_kernel<real>, dim3((p->Ny + 1) / 2, p->B), dim3(rt), sm_inv, ctx->stream,
                                p->Nx, p->Ny, p->Pw, d, (const real2*)p->g, gstride, (real*)Fx, (real*)Fy, (const real2*)p->tw));
   ctx->launches += 3;
   SMM_CUDA(ctx, cudaGetLastError());

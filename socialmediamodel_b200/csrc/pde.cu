@@ -802,7 +802,7 @@ static int launch_stage_t(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
   // static + dynamic shared memory can exceed 48 KB even when the dynamic part alone does not: always opt in
   SMM_CUDA(ctx, cudaFuncSetAttribute(pde_stage_kernel<real, LT, AD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 48 * 1024)));
   static const bool pdl = !(getenv("SMM_PDE_PDL") && getenv("SMM_PDE_PDL")[0] == '0');
-  SMM_CUDA(ctx, smm_launch_pdl(pdl, pde_stage_kernel<real, LT, AD>, grid, block, sm, ctx->stream, A));
+  SMM_CUDA(ctx, smm_launch_pdl(pdl ? ctx->sm_count : 0, pde_stage_kernel<real, LT, AD>, grid, block, sm, ctx->stream, A));
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;
@@ -937,6 +937,10 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
   *out = nullptr;
   SMM_REQUIRE(ctx, grid && q && u0 && z0 && y0, "smm_pde_batch_create: NULL input");
   SMM_REQUIRE(ctx, grid->Nx >= 2 && grid->Ny >= 2 && grid->dx > 0 && grid->dy > 0, "smm_pde_batch_create: bad grid");
+  // the reference builds C and MassM from dx alone and applies them along both axes (pde.jl:68-87,216-217,228;
+  // setting.jl:49 sets dy = dx): an anisotropic grid has no reference semantics
+  SMM_REQUIRE(ctx, grid->dx == grid->dy, "smm_pde_batch_create: dx=%g != dy=%g (the reference assumes a square mesh, setting.jl:49)",
+              grid->dx, grid->dy);
   SMM_REQUIRE(ctx, B >= 1 && L >= 1 && L <= LMAX, "smm_pde_batch_create: need B >= 1 and 1 <= L <= %d", LMAX);
   SMM_REQUIRE(ctx, precision == SMM_PREC_F32 || precision == SMM_PREC_F64, "smm_pde_batch_create: unknown precision");
   SMM_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1389,6 +1393,9 @@ extern "C" int smm_pde_solve(smm_ctx* ctx, const smm_grid* grid, const smm_param
                              int32_t scheme, int32_t nsave, const int32_t* savesteps, double* us, double* zs,
                              double* ys, double* sum_us, double* sum_zs, double* sum_ys) {
   SMM_REQUIRE(ctx, ctx != nullptr, "smm_pde_solve: ctx is NULL");
+  if (ctx->multi)  // several GPUs behind this context: instances are sharded over them (multi.cu)
+    return smm_multi_pde_solve(ctx, grid, q, B, L, precision, controlled_inf, controlled_med, u0, z0, y0, dt, nsteps, scheme, nsave,
+                               savesteps, us, zs, ys, sum_us, sum_zs, sum_ys);
   SMM_REQUIRE(ctx, nsteps >= 0 && dt > 0, "smm_pde_solve: need nsteps >= 0 and dt > 0");
   SMM_REQUIRE(ctx, nsave >= 0 && (nsave == 0 || savesteps), "smm_pde_solve: savesteps missing");
   for (int m = 0; m < nsave; m++) {

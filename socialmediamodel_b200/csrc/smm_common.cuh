@@ -37,6 +37,10 @@ struct smm_ctx {
   void* h_ring = nullptr;
   size_t h_ring_bytes = 0;
   cudaEvent_t ev_h[2] = {nullptr, nullptr};
+  int host_threads = 0;            // host widening threads (0 = default: cores / local ranks, <= 16)
+  // multi-GPU (multi.cu): a leader context owns one member context per GPU; members run in shard mode
+  struct smm_multi* multi = nullptr;
+  bool shard_mode = false;         // member of a multi-GPU context: ensemble sums stay in device scratch for the all-reduce
 };
 
 extern std::string g_smm_last_error;
@@ -104,7 +108,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t smm_launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+inline cudaError_t smm_launch_pdl(int pdl_sms /* SM count of the device; 0 = plain launch */, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                   Args... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof cfg);
@@ -116,7 +120,7 @@ inline cudaError_t smm_launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid,
   // pdl_wait) while this grid is still running, which pays for latency-bound launches (C3: 96.5 -> 89.2 us per
   // RK4 step) and costs throughput for large ones (177^2 x 16: 0.41 -> 0.46 ms when applied everywhere).
   const size_t ctas = (size_t)grid.x * grid.y * grid.z;
-  cfg.attrs = at; cfg.numAttrs = (pdl && 2 * ctas <= 3 * 148) ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (pdl_sms > 0 && 2 * ctas <= 3 * (size_t)pdl_sms) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -178,7 +182,9 @@ __device__ __forceinline__ void box_muller(uint32_t b0, uint32_t b1, float& n0, 
   // MUFU ops they are bit-reproducible in every kernel that inlines this function
   float ua = __fmul_rn(__fadd_rn(__uint2float_rn(b0 >> 8), 0.5f), 0x1p-24f);          // (0,1)
   float ang = __fmul_rn(__uint2float_rn(b1 >> 8), 6.283185307179586f * 0x1p-24f);     // [0, 2 pi)
-  float rad = __fsqrt_rn(__fmul_rn(-2.0f, __logf(ua)));
+  // ua < 1, but the absolute error of the hardware logarithm near 1 exceeds |log(1 - 2^-24)|: clamp so that a
+  // result of +0 or above can never put a NaN into the state
+  float rad = __fsqrt_rn(fmaxf(__fmul_rn(-2.0f, __logf(ua)), 0.0f));
   float s, c;
   __sincosf(ang, &s, &c);
   n0 = __fmul_rn(rad, c);

@@ -73,6 +73,7 @@ int smm_launch_convert_i32_to_i8(smm_ctx* ctx, const int32_t* in, signed char* o
 struct smm_abm_pop {
   AbmConst k;
   int precision;
+  int device;        // device whose persisting-L2 carve-out this population holds a share of (-1: none)
   uint64_t seed;
   int64_t step;      // number of steps taken so far
   int has_net;       // 0 = all-to-all
@@ -103,3 +104,21 @@ struct smm_fft_plan;
 int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, int Pw, double hx, double hy, int B, int precision, smm_fft_plan** out);
 int smm_fft_conv(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, void* Fx, void* Fy);
 void smm_fft_plan_destroy(smm_fft_plan* p);
+
+// several GPUs behind one context (multi.cu)
+struct smm_multi;
+void smm_multi_destroy(smm_multi* m);
+int smm_abm_ensemble_shard(smm_ctx* ctx, const smm_params* q, int32_t precision, int32_t NT, int32_t R, int64_t first_realization,
+                           const double* x0, const int32_t* state, const int32_t* follow0, const double* inf0, const double* media0,
+                           const int32_t* rowptr, const int32_t* colidx, const smm_noise* noise, int32_t nsave,
+                           const int32_t* savesteps, double kde_sigma, const smm_grid* grid, void* us, bool us_f32, double* zs,
+                           double* ys, double* sum_us, double* sum_zs, double* sum_ys, int64_t* numbers);
+int smm_multi_abm_ensemble(smm_ctx* lead, const smm_params* q, int32_t precision, int32_t NT, int32_t R, int64_t first,
+                           const double* x0, const int32_t* state, const int32_t* follow0, const double* inf0, const double* media0,
+                           const int32_t* rowptr, const int32_t* colidx, const smm_noise* noise, int32_t nsave,
+                           const int32_t* savesteps, double kde_sigma, const smm_grid* grid, void* us, bool us_f32, double* zs,
+                           double* ys, double* sum_us, double* sum_zs, double* sum_ys, int64_t* numbers);
+int smm_multi_pde_solve(smm_ctx* lead, const smm_grid* grid, const smm_params* q, int32_t B, int32_t L, int32_t precision,
+                        const double* controlled_inf, const double* controlled_med, const double* u0, const double* z0,
+                        const double* y0, double dt, int32_t nsteps, int32_t scheme, int32_t nsave, const int32_t* savesteps,
+                        double* us, double* zs, double* ys, double* sum_us, double* sum_zs, double* sum_ys);

@@ -18,8 +18,10 @@ def savetimes_abm(NT, savepoints):
 
 def abm_ensemble_raw(NT, R, *, p, q, savesteps, sigma=0.1, first_realization=0, seed=0, precision="f32",
                      init_state=None, injected=None, network=None, want=("us", "zs", "ys", "sums", "numbers"),
-                     pinned=False, ctx=None):
-    """smm_abm_ensemble for the local shard of R realizations; Julia-shaped outputs."""
+                     pinned=False, ctx=None, us_dtype=np.float64):
+    """smm_abm_ensemble for the local shard of R realizations; Julia-shaped outputs.  ``us_dtype=np.float32`` returns the
+    densities as Float32 (smm_abm_ensemble_f32, FP32 mode only); leaving "us" out of ``want`` returns the sums only.
+    A multi-GPU ``ctx`` (Context(devices=...)) shards the realizations over its GPUs inside the call."""
     ctx = _lib.Context.default() if ctx is None else ctx
     n, L, M = q.n, q.L, q.M
     Nx, Ny = p.X.shape
@@ -28,7 +30,9 @@ def abm_ensemble_raw(NT, R, *, p, q, savesteps, sigma=0.1, first_realization=0, 
     alloc = (lambda shape, dt=np.float64: ctx.pinned_empty(shape, dt)) if pinned else \
             (lambda shape, dt=np.float64: np.empty(shape, dt, order="F"))
     out = {}
-    if "us" in want: out["us"] = alloc((Nx, Ny, 2, L, sp_, R))
+    us_dtype = np.dtype(us_dtype)
+    assert us_dtype == np.float64 or (us_dtype == np.float32 and precision == "f32"), "Float32 densities need precision='f32'"
+    if "us" in want: out["us"] = alloc((Nx, Ny, 2, L, sp_, R), us_dtype)
     if "zs" in want: out["zs"] = np.empty((2, 2, sp_, R), order="F")
     if "ys" in want: out["ys"] = np.empty((2, L, sp_, R), order="F")
     if "sums" in want:
@@ -49,18 +53,21 @@ def abm_ensemble_raw(NT, R, *, p, q, savesteps, sigma=0.1, first_realization=0, 
     ns, keep = _noise_struct(seed, injected, n, L, M, NT, R)
     spar = _lib.make_params(q, p)
     g = _lib.make_grid(p)
-    rc = ctx.lib.smm_abm_ensemble(ctx.h, C.byref(spar), _lib.PREC[precision], int(NT), int(R), int(first_realization),
-                                  _lib.ptr(x0), _lib.ptr(st), _lib.ptr(f0), _lib.ptr(i0), _lib.ptr(m0),
-                                  _lib.ptr(rowptr), _lib.ptr(colidx), C.byref(ns), sp_, _lib.ptr(savesteps),
-                                  float(sigma), C.byref(g), _lib.ptr(out.get("us")), _lib.ptr(out.get("zs")),
-                                  _lib.ptr(out.get("ys")), _lib.ptr(out.get("sum_us")), _lib.ptr(out.get("sum_zs")),
-                                  _lib.ptr(out.get("sum_ys")), _lib.ptr(out.get("numbers")))
+    tail = (_lib.ptr(x0), _lib.ptr(st), _lib.ptr(f0), _lib.ptr(i0), _lib.ptr(m0),
+            _lib.ptr(rowptr), _lib.ptr(colidx), C.byref(ns), sp_, _lib.ptr(savesteps),
+            float(sigma), C.byref(g), _lib.ptr(out.get("us")), _lib.ptr(out.get("zs")),
+            _lib.ptr(out.get("ys")), _lib.ptr(out.get("sum_us")), _lib.ptr(out.get("sum_zs")),
+            _lib.ptr(out.get("sum_ys")), _lib.ptr(out.get("numbers")))
+    if us_dtype == np.float32:
+        rc = ctx.lib.smm_abm_ensemble_f32(ctx.h, C.byref(spar), int(NT), int(R), int(first_realization), *tail)
+    else:
+        rc = ctx.lib.smm_abm_ensemble(ctx.h, C.byref(spar), _lib.PREC[precision], int(NT), int(R), int(first_realization), *tail)
     ctx.check(rc, "smm_abm_ensemble")
     return out
 
 
 def ABMsolveensemble(NT=200, N=10, *, savepoints=4, init="4inf", p=None, q=None, sigma=0.1, save=True,
-                     precision="f32", ctx=None):
+                     precision="f32", ctx=None, devices=None, us_dtype=np.float64):
     """ensemble.jl:11-55: N realizations with seeds k = 1..N (ensemble.jl:25), KDE of the agents per
     (medium, influencer) at the save points.  Returns (us, zs, ys, (p, q)) with the reference's shapes
     us[N_x,N_y,2,L,savepoints,N], zs[2,2,savepoints,N], ys[2,L,savepoints,N].
@@ -70,8 +77,16 @@ def ABMsolveensemble(NT=200, N=10, *, savepoints=4, init="4inf", p=None, q=None,
     data/abm_ensemble_<init>.npz under the reference's variable names (us2, zs2, ys2; ensemble.jl:46-53)."""
     p = ABMconstruct() if p is None else p
     q = parameters() if q is None else q
-    out = abm_ensemble_raw(NT, N, p=p, q=q, savesteps=savetimes_abm(NT, savepoints), sigma=sigma,
-                           first_realization=1, seed=0, precision=precision, want=("us", "zs", "ys"), ctx=ctx)
+    own = None
+    if devices is not None and ctx is None:   # keyword extension: several GPUs of the box inside this one call
+        ctx = own = _lib.Context(devices=devices)
+    try:
+        out = abm_ensemble_raw(NT, N, p=p, q=q, savesteps=savetimes_abm(NT, savepoints), sigma=sigma,
+                               first_realization=1, seed=0, precision=precision, want=("us", "zs", "ys"), ctx=ctx,
+                               us_dtype=us_dtype)
+    finally:
+        if own is not None:
+            own.close()
     us, zs, ys = out["us"], out["zs"], out["ys"]
     if save:
         os.makedirs("data", exist_ok=True)

@@ -9,6 +9,7 @@ import socialmediamodel_b200 as smm
 from oracle import abm_oracle as A
 from oracle import ensemble_oracle as E
 from oracle import philox
+from parity_util import LEDGER, check_history
 
 pytestmark = pytest.mark.gpu
 
@@ -61,17 +62,13 @@ def test_abm_solve_injected_parity(precision, rtol):
         o = oracle_solve(r, NT, p, q)
         xs = np.transpose(out["xs"][:, :, :, k], (2, 0, 1))
         fol = out["follows"][:, :, k].T
-        mism = np.nonzero((fol != o["follows"]).any(axis=1))[0]
-        if precision == "f64":
-            assert mism.size == 0, f"follower history differs first at step {mism[:1]}"
-        else:
-            # FP32 positions can only flip a decision whose Float64 margin is below FP32 resolution
-            assert mism.size == 0 or o["min_margin"] < 1e-5, (mism[:3], o["min_margin"])
-        if mism.size == 0:
-            per_step = np.abs(xs - o["xs"]).max(axis=(1, 2)) / np.abs(o["xs"]).max()
-            assert per_step.max() < rtol, per_step.max()
-            assert relerr(np.transpose(out["infs"][:, :, :, k], (2, 0, 1)), o["infs"]) < rtol
-            assert relerr(np.transpose(out["meds"][:, :, :, k], (2, 0, 1)), o["meds"]) < rtol
+        # Float64: bit-exact.  FP32: bit-exact except at counted, isolated near-ties of the oracle's own decision
+        # (parity_util.check_history); positions / influencers / media are compared per step up to that point
+        upto = check_history(fol, o, exact=precision == "f64", label=f"injected {precision} r{k}", rtol=rtol)
+        per_step = np.abs(xs[:upto] - o["xs"][:upto]).max(axis=(1, 2)) / np.abs(o["xs"]).max()
+        assert per_step.max() < rtol, per_step.max()
+        assert relerr(np.transpose(out["infs"][:, :, :, k], (2, 0, 1))[:upto], o["infs"][:upto]) < rtol
+        assert relerr(np.transpose(out["meds"][:, :, :, k], (2, 0, 1))[:upto], o["meds"][:upto]) < rtol
         nswitch += (np.diff(o["follows"], axis=0) != 0).sum()
     assert nswitch > 100                                            # the test exercises switching
     # follower numbers (plotting.jl:284-307), summed over realizations
@@ -168,9 +165,8 @@ def test_abm_sparse_network_dense_kernel(precision, rtol):
     init, inj = stack_inputs([r])
     out = smm.abm_solve_raw(NT, p=p, q=q, precision=precision, init_state=init, injected=inj, network=net)
     o = oracle_solve(r, NT, p, q, net)
-    if precision == "f64" or o["min_margin"] > 1e-5:
-        np.testing.assert_array_equal(out["follows"][:, :, 0].T, o["follows"])
-        assert relerr(np.transpose(out["xs"][:, :, :, 0], (2, 0, 1)), o["xs"]) < rtol
+    check_history(out["follows"][:, :, 0].T, o, exact=precision == "f64", label=f"csr-dense {precision}",
+                  xs=np.transpose(out["xs"][:, :, :, 0], (2, 0, 1)), rtol=rtol)
 
 
 @pytest.mark.parametrize("precision,rtol", [("f64", RTOL_F64), ("f32", RTOL_F32)])
@@ -199,16 +195,24 @@ def test_population_kernel_parity(precision, rtol, L):
         pop.step_injected(xi, u1, u2)
         x, inf, media, follow, margin = A.abm_step(x, inf, media, follow, state, xi, u1, u2, pp, qq, net)
         got = pop.read()
-        if precision == "f32" and not np.array_equal(got["follow"], follow):
-            assert np.nanmin(margin) < 1e-5
+        bad = np.nonzero(got["follow"] != follow)[0]
+        if precision == "f32" and bad.size:
+            # counted near-tie: at most 2 agents, each within 1e-5 of its Float64 threshold; the positions of this
+            # step do not depend on this step's decisions and are still compared below
+            assert bad.size <= 2 and np.all(margin[bad] < 1e-5), (k, bad[:5], margin[bad][:5])
+            LEDGER["cases"] += 1; LEDGER["diverged"] += 1; LEDGER["flips"] += int(bad.size)
+            LEDGER["log"].append((f"population L={L}", k + 1, bad.tolist(), margin[bad].tolist()))
             ok = False
-            break
-        np.testing.assert_array_equal(got["follow"], follow)
+        else:
+            np.testing.assert_array_equal(got["follow"], follow)
         assert relerr(got["x"], x) < rtol
         assert relerr(got["inf"], inf) < max(rtol, 1e-9)
         assert relerr(got["media"], media) < max(rtol, 1e-9)
+        if not ok:
+            break
         ref_numbers = np.array([[np.sum((follow == j) & (state == s)) for j in range(L)] for s in (-1, 1)])
         np.testing.assert_array_equal(got["numbers"], ref_numbers)
+    LEDGER["cases"] += int(ok)
     pop.close()
 
 
@@ -333,8 +337,11 @@ def test_abm_against_golden_fixtures(name):
     init, inj = stack_inputs([r])
     for precision, rtol in (("f64", RTOL_F64), ("f32", RTOL_F32)):
         out = smm.abm_solve_raw(NT, p=p, q=q, precision=precision, init_state=init, injected=inj, network=net)
-        same = np.array_equal(out["follows"][:, :, 0].T, g["follows"])
-        assert same or (precision == "f32" and float(g["min_margin"]) < 1e-5)
+        o = oracle_solve(r, NT, p, q, net)                 # per-step margins are not part of the fixture
+        np.testing.assert_array_equal(o["follows"], g["follows"])
+        upto = check_history(out["follows"][:, :, 0].T, o, exact=precision == "f64", label=f"golden {name} {precision}",
+                             xs=np.transpose(out["xs"][:, :, :, 0], (2, 0, 1)), rtol=rtol)
+        same = upto == NT + 1
         if same:
             assert relerr(np.transpose(out["xs"][:, :, :, 0], (2, 0, 1)), g["xs"]) < rtol
         ens = smm.abm_ensemble_raw(NT, 1, p=p, q=q, savesteps=g["savesteps"], precision=precision, init_state=init,
@@ -362,13 +369,9 @@ def test_dense_kernel_symmetric_pair_schedule(n):
     for k, r in enumerate(runs):
         o = oracle_solve(r, NT, p, q)
         for out in (sym, ordered):
-            fol = out["follows"][:, :, k].T
-            same = np.array_equal(fol, o["follows"])
-            assert same or o["min_margin"] < 1e-5
-            if same:
-                xs = np.transpose(out["xs"][:, :, :, k], (2, 0, 1))
-                assert relerr(xs, o["xs"]) < RTOL_F32
-                assert relerr(np.transpose(out["infs"][:, :, :, k], (2, 0, 1)), o["infs"]) < RTOL_F32
+            check_history(out["follows"][:, :, k].T, o, exact=False, label=f"sym-schedule n={n} r{k}",
+                          xs=np.transpose(out["xs"][:, :, :, k], (2, 0, 1)),
+                          infs=np.transpose(out["infs"][:, :, :, k], (2, 0, 1)), rtol=RTOL_F32)
     assert relerr(sym["xs"], ordered["xs"]) < 5e-6
 
 
@@ -390,3 +393,67 @@ def test_c99_program_calls_the_abi(tmp_path):
     assert abs(float(s_us) - ref["us"].sum()) <= 1e-9 * abs(ref["us"].sum())
     assert abs(float(s_ys) - ref["sum_ys"].sum()) <= 1e-12 * max(1.0, abs(ref["sum_ys"].sum()))
     assert int(launches) > 0
+
+
+def test_ensemble_float32_densities_and_means_only():
+    """Keyword extensions of ABMsolveensemble for callers that do not need 2 GB of Float64 densities
+    (smm_abm_ensemble_f32, us = NULL): the Float32 array holds exactly the values the Float64 array holds, and the
+    means-only call returns the same sums."""
+    p, q = smm.ABMconstruct(dx=0.2), smm.parameters(n=60)
+    st = smm.savetimes_abm(20, 3)
+    ref = smm.abm_ensemble_raw(20, 6, p=p, q=q, savesteps=st, first_realization=1, precision="f32")
+    f32 = smm.abm_ensemble_raw(20, 6, p=p, q=q, savesteps=st, first_realization=1, precision="f32", us_dtype=np.float32)
+    assert f32["us"].dtype == np.float32 and f32["us"].shape == ref["us"].shape
+    np.testing.assert_array_equal(f32["us"].astype(np.float64), ref["us"])
+    np.testing.assert_array_equal(f32["ys"], ref["ys"])
+    means = smm.abm_ensemble_raw(20, 6, p=p, q=q, savesteps=st, first_realization=1, precision="f32", want=("sums", "numbers"))
+    assert "us" not in means
+    np.testing.assert_array_equal(means["sum_us"], ref["sum_us"])
+    np.testing.assert_array_equal(means["numbers"], ref["numbers"])
+
+
+def test_multi_gpu_context_shards_inside_one_call():
+    """smm_ctx_create_multi: every visible GPU behind one context; the ensemble call shards the realizations over them
+    (seed = global realization index, ensemble.jl:25) and reduces the sums (NCCL when more than one GPU).  Same numbers as
+    the single-GPU context, per realization bit for bit."""
+    from socialmediamodel_b200 import _lib
+    ndev = _lib.load().smm_device_count()
+    p, q = smm.ABMconstruct(dx=0.2), smm.parameters(n=60)
+    st = smm.savetimes_abm(20, 3)
+    R = 2 * ndev + 1
+    ref = smm.abm_ensemble_raw(20, R, p=p, q=q, savesteps=st, first_realization=1, precision="f32")
+    ctx = _lib.Context(devices="all")
+    try:
+        assert ctx.gpu_count == ndev and (ctx.nccl_active or ndev == 1)
+        for dt in (np.float64, np.float32):
+            out = smm.abm_ensemble_raw(20, R, p=p, q=q, savesteps=st, first_realization=1, precision="f32", ctx=ctx, us_dtype=dt)
+            np.testing.assert_array_equal(out["us"].astype(np.float64), ref["us"])
+            np.testing.assert_array_equal(out["ys"], ref["ys"]); np.testing.assert_array_equal(out["zs"], ref["zs"])
+            np.testing.assert_allclose(out["sum_us"], ref["sum_us"], rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(out["sum_ys"], ref["sum_ys"], rtol=1e-12)
+            np.testing.assert_array_equal(out["numbers"], ref["numbers"])
+        us, zs, ys, _ = smm.ABMsolveensemble(20, R, savepoints=3, p=p, q=q, save=False, ctx=ctx)
+        np.testing.assert_array_equal(us, ref["us"])
+        # PDE ensemble through the same context: instances sharded, sums added on the host
+        from oracle import pde_oracle  # noqa: F401  (fixtures only)
+        pc = smm.PDEconstructcoarse()
+        qs = [smm.parameters(a=a) for a in (0.5, 1.0, 1.5)]
+        inits = [smm.constructinitial("4inf", (pc, qq)) for qq in qs]
+        U = np.stack([uz.x[0] for uz, _ in inits], axis=-1); Z = np.stack([uz.x[1] for uz, _ in inits], axis=-1)
+        Y = np.stack([uz.x[2] for uz, _ in inits], axis=-1)
+        ql = [qq for _, qq in inits]
+        a = smm.pde_solve_raw(pc, ql, U, Z, Y, dt=1e-3, nsteps=6, savesteps=[0, 6], precision="f64", want_sums=True)
+        b = smm.pde_solve_raw(pc, ql, U, Z, Y, dt=1e-3, nsteps=6, savesteps=[0, 6], precision="f64", want_sums=True, ctx=ctx)
+        np.testing.assert_array_equal(a["us"], b["us"])
+        np.testing.assert_allclose(a["sum_us"], b["sum_us"], rtol=1e-13, atol=1e-15)
+    finally:
+        ctx.close()
+
+
+def test_fp32_divergence_budget():
+    """Runs last in this module: how often an FP32 follower history left the Float64 oracle's (always at a near-tie
+    of the oracle's own decision, at most two agents, positions compared up to that step — parity_util).  A kernel
+    that flipped decisions systematically would exhaust this budget."""
+    print("FP32 follower-history ledger:", {k: v for k, v in LEDGER.items() if k != "log"}, LEDGER["log"])
+    assert LEDGER["cases"] >= 20
+    assert LEDGER["diverged"] <= max(1, LEDGER["cases"] // 20), LEDGER["log"]

@@ -230,6 +230,30 @@ def test_c3_full_horizon_fp32_drift():
     assert abs(o64["us"][..., 1, 0].sum() * p.dV - 1.0113) < 2e-3     # the scheme is not mass-conserving (SURVEY hard part 7)
 
 
+def test_c4_grid_fp32_drift_500_steps():
+    """C4 as bench.py times it (SURVEY hard part 5): 353x353 grid, RK4 with the sweep's dt = 5e-5 (D/dx^2 up to 3 200),
+    500 steps, two lattice corners of the parameter sweep (weak / strong diffusion).  FP32 state vs the Float64 run of
+    the same scheme (the Float64 path is oracle-exact per evaluation and per step, see above): <= 1e-5 of max|u|."""
+    p = smm.PDEconstruct(dx=0.0125)
+    assert p.N_x == 353
+    qs = [smm.parameters(a=0.5, b=1.0, c=1.0, eta=1.0, sigma=0.25), smm.parameters(a=3.0, b=6.0, c=4.0, eta=15.0, sigma=1.0)]
+    inits = [smm.constructinitial("4inf", (p, q)) for q in qs]
+    qlist = [qq for _, qq in inits]
+    U = np.stack([uz.x[0] for uz, _ in inits], axis=-1)
+    Z = np.stack([uz.x[1] for uz, _ in inits], axis=-1)
+    Y = np.stack([uz.x[2] for uz, _ in inits], axis=-1)
+    dt = min(smm.default_dt(p, q) for q in qlist)
+    assert abs(dt - 5e-5) < 1e-12
+    o32 = smm.pde_solve_raw(p, qlist, U, Z, Y, dt=dt, nsteps=500, savesteps=[100, 500], precision="f32")
+    o64 = smm.pde_solve_raw(p, qlist, U, Z, Y, dt=dt, nsteps=500, savesteps=[100, 500], precision="f64")
+    for b in range(2):
+        for m in range(2):
+            e = rel(o32["us"][..., m, b], o64["us"][..., m, b])
+            assert e < TOL32, (b, m, e)
+            assert np.abs(o32["ys"][..., m, b] - o64["ys"][..., m, b]).max() < 1e-6
+    assert np.isfinite(o64["us"]).all() and rel(o64["us"][..., 1, 0], o64["us"][..., 0, 0]) > 1e-3   # the state moved
+
+
 def test_pde_against_golden_fixtures():
     """Committed golden vectors (tests/golden/pde_coarse.npz, oracle-generated)."""
     import os
