@@ -38,8 +38,16 @@ struct FftDims { int P, m, a, r3; };
 // [0, P) for every P = r3 * 2^a, a >= 5.
 __device__ __forceinline__ int swz(int i) { return i ^ ((i >> 2) & 15); }
 
-__device__ __forceinline__ int brev_a(int i, int a) { return a ? (int)(__brev((unsigned)i) >> (32 - a)) : 0; }
-__device__ __forceinline__ int pos_of_freq(int k, FftDims d) {
+__host__ __device__ __forceinline__ int brev_a(int i, int a) {
+#if defined(__CUDA_ARCH__)
+  return a ? (int)(__brev((unsigned)i) >> (32 - a)) : 0;
+#else
+  int r = 0;
+  for (int b = 0; b < a; b++) r |= ((i >> b) & 1) << (a - 1 - b);
+  return r;
+#endif
+}
+__host__ __device__ __forceinline__ int pos_of_freq(int k, FftDims d) {
   return d.r3 == 3 ? (k % 3) * d.m + brev_a(k / 3, d.a) : brev_a(k, d.a);
 }
 __device__ __forceinline__ int freq_of_pos(int p, FftDims d) {
@@ -350,6 +358,7 @@ template <typename real> int cols_for(int P) {
 
 struct smm_fft_plan {
   int Nx, Ny, Pw, P, B, precision;  // Pw: row pitch of rhosum / Fx / Fy
+  smm_fft_fast* fast;               // register-resident FP32 path (fft_fast.cu); null = the kernels of this file
   FftDims dims;
   void* tw;    // real2 [P], stage-major
   void* khat;  // real2 [3][P/2+1][P]
@@ -361,6 +370,7 @@ void smm_fft_plan_destroy(smm_fft_plan* p) {
   if (!p) return;
   void* ptrs[] = {p->tw, p->khat, p->ahat, p->g};
   for (void* q : ptrs) if (q) cudaFree(q);
+  smm_fft_fast_destroy(p->fast);
   delete p;
 }
 
@@ -397,8 +407,13 @@ int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, int Pw, double hx, double 
   smm_fft_plan* p = new smm_fft_plan();
   p->Nx = Nx; p->Ny = Ny; p->Pw = Pw; p->P = P; p->dims = d; p->B = B; p->precision = precision;
   p->tw = p->khat = p->ahat = p->g = nullptr;
+  p->fast = nullptr;
   const size_t c2 = precision == SMM_PREC_F64 ? 16 : 8;
   const int hp1 = P / 2 + 1;
+  // FP32 and P = 96 / 192 / 384 / 768 (the grids 47, 89, 177, 353): the register-resident path of fft_fast.cu
+  // (SMM_FFT_FAST=0 keeps the kernels of this file, which also serve Float64 and every other length)
+  bool want_fast = precision != SMM_PREC_F64 && smm_fft_fast_supported(P);
+  { const char* ev = getenv("SMM_FFT_FAST"); if (ev && ev[0] == '0') want_fast = false; }
 #define PL_CUDA(expr)                                                                                    \
   do {                                                                                                   \
     cudaError_t e__ = (expr);                                                                            \
@@ -412,8 +427,10 @@ int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, int Pw, double hx, double 
   void* tmp[4] = {nullptr, nullptr, nullptr, nullptr};  // img, twd, ahat_d, khat_d
   PL_CUDA(cudaMalloc(&p->tw, (size_t)P * c2));
   PL_CUDA(cudaMalloc(&p->khat, (size_t)3 * hp1 * P * c2));
-  PL_CUDA(cudaMalloc(&p->ahat, (size_t)B * Ny * hp1 * c2));
-  PL_CUDA(cudaMalloc(&p->g, (size_t)3 * B * Ny * hp1 * c2));
+  if (!want_fast) {
+    PL_CUDA(cudaMalloc(&p->ahat, (size_t)B * Ny * hp1 * c2));
+    PL_CUDA(cudaMalloc(&p->g, (size_t)3 * B * Ny * hp1 * c2));
+  }
   PL_CUDA(cudaMalloc(&tmp[0], (size_t)3 * P * P * 8));
   PL_CUDA(cudaMalloc(&tmp[1], (size_t)P * 16));
   PL_CUDA(cudaMalloc(&tmp[2], (size_t)3 * P * hp1 * 16));
@@ -440,6 +457,21 @@ int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, int Pw, double hx, double 
     PL_CUDA(cudaGetLastError());
     if (precision != SMM_PREC_F64) {
       int rc = smm_launch_convert_f64_to_real(ctx, (const double*)tmp[3], p->khat, (size_t)3 * hp1 * P * 2, precision);
+      if (rc != SMM_OK) { smm_fft_plan_destroy(p); for (void* t : tmp) if (t) cudaFree(t); return rc; }
+    }
+    if (want_fast) {  // the same Float64 spectra, re-ordered for the fast path
+      std::vector<int> slot(P);
+      for (int k = 0; k < P; k++) slot[k] = pos_of_freq(k, d);
+      int* dslot = nullptr;
+      PL_CUDA(cudaMalloc((void**)&dslot, (size_t)P * sizeof(int)));
+      cudaError_t e = cudaMemcpyAsync(dslot, slot.data(), (size_t)P * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+      int rc = e == cudaSuccess ? smm_fft_fast_create(ctx, P, Nx, Ny, Pw, B, tmp[3], dslot, &p->fast) : SMM_ERR_CUDA;
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(dslot);
+      // the fast path keeps one real number per spectrum point (even kernel image: real spectrum; odd ones: imaginary);
+      // the dropped parts must be rounding noise of the Float64 transform
+      if (rc == SMM_OK && !(smm_fft_fast_residual(p->fast) < 1e-10))
+        rc = smm_fail(ctx, SMM_ERR_UNSUPPORTED, "FFT convolution: kernel spectra are not real / imaginary (residual %g)", smm_fft_fast_residual(p->fast));
       if (rc != SMM_OK) { smm_fft_plan_destroy(p); for (void* t : tmp) if (t) cudaFree(t); return rc; }
     }
   }
@@ -479,6 +511,7 @@ static int fft_conv_launch(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, vo
 }
 
 int smm_fft_conv(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, void* Fx, void* Fy) {
+  if (p->fast) return smm_fft_fast_conv(ctx, p->fast, rhosum, Fx, Fy);
   return p->precision == SMM_PREC_F64 ? fft_conv_launch<double>(ctx, p, rhosum, Fx, Fy)
                                       : fft_conv_launch<float>(ctx, p, rhosum, Fx, Fy);
 }

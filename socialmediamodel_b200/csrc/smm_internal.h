@@ -104,6 +104,13 @@ struct smm_fft_plan;
 int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, int Pw, double hx, double hy, int B, int precision, smm_fft_plan** out);
 int smm_fft_conv(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, void* Fx, void* Fy);
 void smm_fft_plan_destroy(smm_fft_plan* p);
+// register-resident FP32 path for P = 96 / 192 / 384 / 768 (fft_fast.cu)
+struct smm_fft_fast;
+bool smm_fft_fast_supported(int P);
+int smm_fft_fast_create(smm_ctx* ctx, int P, int Nx, int Ny, int Pw, int B, const void* khat64, const int* slot_of_freq_dev, smm_fft_fast** out);
+int smm_fft_fast_conv(smm_ctx* ctx, smm_fft_fast* f, const void* rhosum, void* Fx, void* Fy);
+void smm_fft_fast_destroy(smm_fft_fast* f);
+double smm_fft_fast_residual(const smm_fft_fast* f);
 
 // several GPUs behind one context (multi.cu)
 struct smm_multi;

@@ -230,6 +230,38 @@ def test_c3_full_horizon_fp32_drift():
     assert abs(o64["us"][..., 1, 0].sum() * p.dV - 1.0113) < 2e-3     # the scheme is not mass-conserving (SURVEY hard part 7)
 
 
+@pytest.mark.parametrize("dx,N", [(0.1, 47), (0.05, 89), (0.025, 177), (0.0125, 353)])
+def test_fast_fft_path_against_generic_path_and_oracle(dx, N, monkeypatch):
+    """FP32 interaction force by the register-resident FFT kernels (fft_fast.cu: P = 96 / 192 / 384 / 768, both CTA
+    shapes) against the generic shared-memory FFT kernels (fft_conv.cu) on a non-symmetric state, several instances
+    (ragged last row / column groups), and against the Float64 oracle."""
+    p = smm.PDEconstructcoarse() if N == 47 else smm.PDEconstruct(dx=dx)
+    assert p.N_x == N
+    rng = np.random.default_rng(N)
+    B = 3
+    qs = [smm.parameters(a=a) for a in (0.5, 1.0, 2.0)]
+    uzy0, _ = smm.constructinitial("4inf", (p, qs[0]))
+    u = np.stack([uzy0.x[0] * (1 + 0.3 * rng.random(uzy0.x[0].shape)) for _ in range(B)], axis=-1)
+    z = np.stack([uzy0.x[1]] * B, axis=-1)
+    y = np.stack([uzy0.x[2] + 0.05 * rng.standard_normal(uzy0.x[2].shape) for _ in range(B)], axis=-1)
+    ql = [smm.constructinitial("4inf", (p, q))[1] for q in qs]
+    res = {}
+    for name, env in (("generic", {"SMM_FFT_FAST": "0"}), ("fast4", {"SMM_FFT_PAIRS": "4"}), ("fast8", {"SMM_FFT_PAIRS": "8"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        res[name] = smm.pde_rhs(u, z, y, p=p, q=ql, precision="f32")
+        for k in env:
+            monkeypatch.delenv(k)
+    ref = res["generic"][0]
+    for name in ("fast4", "fast8"):
+        assert rel(res[name][0], ref) < 2e-6, (name, rel(res[name][0], ref))
+        assert np.abs(res[name][2] - res["generic"][2]).max() < 1e-6
+    if N <= 177:
+        for b in range(B):
+            dur, _, _ = P.rhs(u[..., b], z[..., b], y[..., b], oracle_p(p), dict(ql[b]))
+            assert rel(res["fast4"][0][..., b], dur) < TOL32
+
+
 def test_c4_grid_fp32_drift_500_steps():
     """C4 as bench.py times it (SURVEY hard part 5): 353x353 grid, RK4 with the sweep's dt = 5e-5 (D/dx^2 up to 3 200),
     500 steps, two lattice corners of the parameter sweep (weak / strong diffusion).  FP32 state vs the Float64 run of
