@@ -410,10 +410,17 @@ int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, int Pw, double hx, double 
   p->fast = nullptr;
   const size_t c2 = precision == SMM_PREC_F64 ? 16 : 8;
   const int hp1 = P / 2 + 1;
-  // FP32 and P = 96 / 192 / 384 / 768 (the grids 47, 89, 177, 353): the register-resident path of fft_fast.cu
-  // (SMM_FFT_FAST=0 keeps the kernels of this file, which also serve Float64 and every other length)
-  bool want_fast = precision != SMM_PREC_F64 && smm_fft_fast_supported(P);
-  { const char* ev = getenv("SMM_FFT_FAST"); if (ev && ev[0] == '0') want_fast = false; }
+  // FP32 and P = 96 / 192 / 384 / 768 (the grids 47, 89, 177, 353): the register-resident path of fft_fast.cu for
+  // batches with enough rows to fill the GPU (measured on B200: 16 x 177^2 0.415 -> 0.336 ms, 64 x 353^2 5.48 -> 3.80 ms per
+  // RK4 step; a single 89^2 instance, 13 column CTAs, is latency-bound and 40 % slower than the kernels of this file,
+  // which spread one instance over 129 CTAs).  SMM_FFT_FAST=1 / 0 forces the choice; the kernels of this file also serve
+  // Float64 and every other length.
+  bool want_fast = precision != SMM_PREC_F64 && smm_fft_fast_supported(P) && (size_t)B * Ny >= 1024;
+  {
+    const char* ev = getenv("SMM_FFT_FAST");
+    if (ev && ev[0] == '0') want_fast = false;
+    if (ev && ev[0] == '1') want_fast = precision != SMM_PREC_F64 && smm_fft_fast_supported(P);
+  }
 #define PL_CUDA(expr)                                                                                    \
   do {                                                                                                   \
     cudaError_t e__ = (expr);                                                                            \

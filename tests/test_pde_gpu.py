@@ -246,14 +246,15 @@ def test_fast_fft_path_against_generic_path_and_oracle(dx, N, monkeypatch):
     y = np.stack([uzy0.x[2] + 0.05 * rng.standard_normal(uzy0.x[2].shape) for _ in range(B)], axis=-1)
     ql = [smm.constructinitial("4inf", (p, q))[1] for q in qs]
     res = {}
-    for name, env in (("generic", {"SMM_FFT_FAST": "0"}), ("fast4", {"SMM_FFT_PAIRS": "4"}), ("fast8", {"SMM_FFT_PAIRS": "8"})):
+    for name, env in (("generic", {"SMM_FFT_FAST": "0"}), ("fast4", {"SMM_FFT_FAST": "1", "SMM_FFT_PAIRS": "4"}),
+                      ("fast8", {"SMM_FFT_FAST": "1", "SMM_FFT_PAIRS": "8"}), ("fast4c", {"SMM_FFT_FAST": "1", "SMM_FFT_CHUNK_MB": "1"})):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         res[name] = smm.pde_rhs(u, z, y, p=p, q=ql, precision="f32")
         for k in env:
             monkeypatch.delenv(k)
     ref = res["generic"][0]
-    for name in ("fast4", "fast8"):
+    for name in ("fast4", "fast8", "fast4c"):   # fast4c: one instance per chunk
         assert rel(res[name][0], ref) < 2e-6, (name, rel(res[name][0], ref))
         assert np.abs(res[name][2] - res["generic"][2]).max() < 1e-6
     if N <= 177:
