@@ -6,12 +6,14 @@
 // Replaces the loop body abm.jl:166-213 (attraction :47-67, influence :69-88, Euler-Maruyama
 // :173, influencer/media update :175-198, reflection :139-150, changeinfluencer :90-137).
 // Bound: MUFU (2 per ordered pair: sqrt.approx + ex2.approx), not HBM -- see DESIGN.md.
+#include <algorithm>
+
 #include "abm_device.cuh"
 #include "smm_internal.h"
 
 namespace {
 
-constexpr int kThreads = 128;
+constexpr int kThreads = 128;  // CTA width of the full-GPU configuration (and of the init kernel)
 
 // 2^(-sqrt(r2)) for coordinates pre-scaled by log2(e): exp(-|x_i - x_j|) with two MUFU ops and nothing else
 __device__ __forceinline__ float w_of_scaled_r2(float r2) {
@@ -26,9 +28,13 @@ constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 constexpr int kSymMaxGroups = 16;  // n <= 512: the per-offset partial sums must fit shared memory
 constexpr float kPadPos = 1e15f;   // padding agents of the last 32-group: exp(-|x - pad|) = 0 exactly
 
-template <typename real, bool SYM>
-__global__ void __launch_bounds__(kThreads, SYM ? 7 : 8) abm_dense_kernel(AbmDenseArgs A) {
+// THREADS = CTA width: 128 when the ensemble alone fills the GPU (1 024 realizations: 7 CTAs per SM, all resident);
+// 256 / 512 for small ensembles (configs[1] at 8 GPUs = 128 realizations per GPU; C1 = one realization), where one
+// realization is spread over 8 / 16 warps instead of leaving most of the SMs' issue slots idle.
+template <typename real, bool SYM, int THREADS>
+__global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THREADS == 256 ? 3 : 1)) abm_dense_kernel(AbmDenseArgs A) {
   using real2 = typename vec2<real>::type;
+  constexpr int kThreads = THREADS;  // shadows the namespace constant inside this kernel
   const AbmConst& K = A.k;
   const int n = K.n, L = K.L, M = K.M, NT = A.NT;
   const int r = blockIdx.x;
@@ -56,7 +62,8 @@ __global__ void __launch_bounds__(kThreads, SYM ? 7 : 8) abm_dense_kernel(AbmDen
   float* ffr = finy + L;
   signed char* st = reinterpret_cast<signed char*>(ffr + L);  // [npad]
   // SYM: positions once more, every 32-group stored twice in a row ([G][64]) so that the rotated partner
-  // index lane +- s needs no wrap-around arithmetic, and the partial sums [1 + D][G*32] x (ws, ax, ay)
+  // index lane +- s needs no wrap-around arithmetic, and the partial sums: slot d = 0..D: row sums of tile (g, g+d),
+  // slot D + d, d = 1..D: column sums of tile (h-d, h); each [G*32] x (ws, ax, ay)
   const int G = (n + 31) >> 5, D = G >> 1, NG = G * 32;
   // xy2[g][i] = log2(e) * (x_a, x_b, y_a, y_b) of the agents a = g*32 + (i & 31), b = g*32 + ((i + 16) & 31), i < 64
   float4* xy2 = reinterpret_cast<float4*>(smem + ((reinterpret_cast<unsigned char*>(st + npad) - smem + 15) & ~(size_t)15));
@@ -246,22 +253,32 @@ __global__ void __launch_bounds__(kThreads, SYM ? 7 : 8) abm_dense_kernel(AbmDen
       // pair exactly once (for even G the offset G/2 only from the lower half); the diagonal tile (g, g) is
       // evaluated in ordered form and contains the self pair (abm.jl:42).  Every partial sum has its own
       // shared-memory slot and is added in a fixed order: results are deterministic.
-      for (int g = warp; g < G; g += nwarps) {
+      // Work items = tiles: NO off-diagonal tiles (d = 1..D; for even G the offset G/2 only from the lower half of the
+      // groups) and G diagonal ones.  Off-diagonal tiles cost ~1.7x a diagonal one, so they are dealt first and in
+      // snake order over the warps (longest-processing-time rule): 36 tiles at n = 250 balance to within 6 % over 16
+      // warps.  Every tile owns its partial-sum slots, so any assignment gives bit-identical results.
+      const int NO = (G & 1) ? D * G : (D > 0 ? (D - 1) * G + D : 0), NI = NO + G;
+      for (int round = 0;; round++) {
+        const int it = (round & 1) ? (round + 1) * nwarps - 1 - warp : round * nwarps + warp;
+        if (round * nwarps >= NI) break;
+        if (it >= NI) continue;
+        const int d = it < NO ? it / G + 1 : 0;
+        const int g = it < NO ? it - (d - 1) * G : it - NO;
         const float4* rowp = xy2 + g * 64 + lane;
         const float rx = rowp[0].x, ry = rowp[0].z;
         const float2 nrx = make_float2(-rx, -rx), nry = make_float2(-ry, -ry);
         float2 ws2 = make_float2(0.f, 0.f), ax2 = ws2, ay2 = ws2;
-        // diagonal tile: lane l against all 32 agents of its own group, two partners per step
+        if (d == 0) {
+          // diagonal tile: lane l against all 32 agents of its own group, two partners per step
 #pragma unroll 8
-        for (int t = 0; t < 16; t++) {
-          const float4 p = rowp[t];
-          const float2 dx = add2(make_float2(p.x, p.y), nrx), dy = add2(make_float2(p.z, p.w), nry);
-          const float2 r2 = fma2(dx, dx, mul2(dy, dy));
-          const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
-          ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
-        }
-        for (int d = 1; d <= D; d++) {
-          if (2 * d == G && g >= D) break;
+          for (int t = 0; t < 16; t++) {
+            const float4 p = rowp[t];
+            const float2 dx = add2(make_float2(p.x, p.y), nrx), dy = add2(make_float2(p.z, p.w), nry);
+            const float2 r2 = fma2(dx, dx, mul2(dy, dy));
+            const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
+            ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
+          }
+        } else {
           int h = g + d;
           if (h >= G) h -= G;
           const float4* colp = xy2 + h * 64 + lane;
@@ -285,19 +302,24 @@ __global__ void __launch_bounds__(kThreads, SYM ? 7 : 8) abm_dense_kernel(AbmDen
             const float2 ex = add2(make_float2(q.x, q.y), ncx), ey = add2(make_float2(q.z, q.w), ncy);
             cws2 = add2(cws2, wv); cax2 = fma2(wv, ex, cax2); cay2 = fma2(wv, ey, cay2);
           }
-          float* o = part + (size_t)d * 3 * NG + h * 32 + lane;
+          float* o = part + (size_t)(D + d) * 3 * NG + h * 32 + lane;
           o[0] = cws2.x + cws2.y; o[NG] = (cax2.x + cax2.y) * kLn2; o[2 * NG] = (cay2.x + cay2.y) * kLn2;
         }
-        float* o = part + g * 32 + lane;
+        float* o = part + (size_t)d * 3 * NG + g * 32 + lane;
         o[0] = ws2.x + ws2.y; o[NG] = (ax2.x + ax2.y) * kLn2; o[2 * NG] = (ay2.x + ay2.y) * kLn2;
       }
       __syncthreads();
       for (int j = tid; j < n; j += kThreads) {
         real ws = part[j], ax = part[NG + j], ay = part[2 * NG + j];
         const int hg = j >> 5;
-        for (int d = 1; d <= D; d++) {
-          if (2 * d == G && hg < D) break;  // that slot is only written for the upper half of the groups
+        for (int d = 1; d <= D; d++) {  // fixed order: row sums d = 1..D, then column sums d = 1..D
+          if (2 * d == G && hg >= D) break;  // tile (hg, hg + G/2) belongs to the lower half of the groups
           const real* o = part + (size_t)d * 3 * NG + j;
+          ws += o[0]; ax += o[NG]; ay += o[2 * NG];
+        }
+        for (int d = 1; d <= D; d++) {
+          if (2 * d == G && hg < D) break;   // column sums of offset G/2 exist only for the upper half
+          const real* o = part + (size_t)(D + d) * 3 * NG + j;
           ws += o[0]; ax += o[NG]; ay += o[2 * NG];
         }
         finish(j, xc[j], ax, ay, ws);
@@ -409,12 +431,25 @@ size_t dense_smem_bytes(int n, int L, int M, size_t real_size, bool sym) {
              sizeof(int) * (4 * (L + M) + npad) + sizeof(float) * 3 * L + npad + 16;
   if (sym) {
     const size_t G = (n + 31) / 32, D = G / 2;
-    b += 16 + 2 * G * 64 * 8 + (1 + D) * 3 * G * 32 * 4;
+    b += 16 + 2 * G * 64 * 8 + (1 + 2 * D) * 3 * G * 32 * 4;
   }
   return b;
 }
 
 }  // namespace
+
+template <typename real, bool SYM, int THREADS>
+static int launch_dense_t(smm_ctx* ctx, const AbmDenseArgs& A, size_t sm) {
+  SMM_CUDA(ctx, cudaFuncSetAttribute(abm_dense_kernel<real, SYM, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  abm_dense_kernel<real, SYM, THREADS><<<A.R, THREADS, sm, ctx->stream>>>(A);
+  return SMM_OK;
+}
+template <typename real, bool SYM>
+static int launch_dense_w(smm_ctx* ctx, const AbmDenseArgs& A, size_t sm, int threads) {
+  if (threads == 512) return launch_dense_t<real, SYM, 512>(ctx, A, sm);
+  if (threads == 256) return launch_dense_t<real, SYM, 256>(ctx, A, sm);
+  return launch_dense_t<real, SYM, 128>(ctx, A, sm);
+}
 
 int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
   // FP32 all-to-all populations of up to 512 agents take the symmetric-pair path (SMM_ABM_SYM=0: ordered pairs)
@@ -423,16 +458,21 @@ int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
   size_t sm = dense_smem_bytes(A.k.n, A.k.L, A.k.M, precision == SMM_PREC_F64 ? 8 : 4, sym);
   SMM_REQUIRE(ctx, sm <= 227 * 1024, "dense ABM kernel: n=%d does not fit shared memory (%zu B); pass a CSR network", A.k.n, sm);
   SMM_REQUIRE(ctx, A.k.L + A.k.M <= kThreads && A.k.L * A.k.M <= kThreads, "dense ABM kernel: L+M and L*M must be <= %d", kThreads);
-  if (precision == SMM_PREC_F64) {
-    SMM_CUDA(ctx, cudaFuncSetAttribute(abm_dense_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    abm_dense_kernel<double, false><<<A.R, kThreads, sm, ctx->stream>>>(A);
-  } else if (sym) {
-    SMM_CUDA(ctx, cudaFuncSetAttribute(abm_dense_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    abm_dense_kernel<float, true><<<A.R, kThreads, sm, ctx->stream>>>(A);
-  } else {
-    SMM_CUDA(ctx, cudaFuncSetAttribute(abm_dense_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    abm_dense_kernel<float, false><<<A.R, kThreads, sm, ctx->stream>>>(A);
+  // CTA width from the ensemble size: the widest CTA for which all R realizations are still resident at once (one
+  // 512-thread CTA or three 256-thread CTAs per SM at their register counts), but never wider than the tile count
+  // of the population can feed (n = 250: 8 row groups, 36 tiles)
+  int threads = 128;
+  {
+    const int groups = (A.k.n + 31) / 32;
+    if (A.R <= ctx->sm_count && groups >= 8) threads = 512;
+    else if (A.R <= 3 * ctx->sm_count && groups >= 4) threads = 256;
+    if (const char* tv = getenv("SMM_ABM_THREADS")) { const int t = atoi(tv); if (t == 128 || t == 256 || t == 512) threads = t; }
   }
+  int rc;
+  if (precision == SMM_PREC_F64) rc = launch_dense_w<double, false>(ctx, A, sm, threads);
+  else if (sym) rc = launch_dense_w<float, true>(ctx, A, sm, threads);
+  else rc = launch_dense_w<float, false>(ctx, A, sm, threads);
+  SMM_TRY(rc);
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;

@@ -395,6 +395,39 @@ def test_c99_program_calls_the_abi(tmp_path):
     assert int(launches) > 0
 
 
+@pytest.mark.parametrize("n", [250, 90, 300])
+def test_dense_kernel_cta_widths_are_bit_identical(n, monkeypatch):
+    """Small ensembles run one realization on 256 / 512 threads (tiles dealt over 8 / 16 warps) instead of 128: every
+    tile owns its partial-sum slots and the final sums have a fixed order, so the three widths give the same bits, in
+    both arithmetic modes; and they match the oracle."""
+    NT = 25
+    p, q = smm.ABMconstruct(), smm.parameters(n=n)
+    runs = make_run(300 + n, n=n, NT=NT, R=2)
+    init, inj = stack_inputs(runs)
+    for precision in ("f32", "f64"):
+        outs = {}
+        for th in ("128", "256", "512"):
+            monkeypatch.setenv("SMM_ABM_THREADS", th)
+            outs[th] = smm.abm_solve_raw(NT, p=p, q=q, R=2, precision=precision, init_state=init, injected=inj)
+        monkeypatch.delenv("SMM_ABM_THREADS")
+        for th in ("256", "512"):
+            np.testing.assert_array_equal(outs[th]["xs"], outs["128"]["xs"])
+            np.testing.assert_array_equal(outs[th]["follows"], outs["128"]["follows"])
+            np.testing.assert_array_equal(outs[th]["infs"], outs["128"]["infs"])
+            np.testing.assert_array_equal(outs[th]["numbers"], outs["128"]["numbers"])
+        for k, r in enumerate(runs):
+            o = oracle_solve(r, NT, p, q)
+            check_history(outs["512"]["follows"][:, :, k].T, o, exact=precision == "f64", label=f"cta-width n={n} {precision} r{k}",
+                          xs=np.transpose(outs["512"]["xs"][:, :, :, k], (2, 0, 1)), rtol=RTOL_F32 if precision == "f32" else RTOL_F64)
+    # automatic choice: one realization (C1) and a 128-member ensemble take the wide CTAs and still agree with 128 threads
+    auto = smm.abm_solve_raw(NT, p=p, q=q, R=2, precision="f32", init_state=init, injected=inj)
+    np.testing.assert_array_equal(auto["xs"], outs["128"]["xs"]) if precision == "f32" else None
+    monkeypatch.setenv("SMM_ABM_THREADS", "128")
+    ref = smm.abm_solve_raw(NT, p=p, q=q, R=2, precision="f32", init_state=init, injected=inj)
+    monkeypatch.delenv("SMM_ABM_THREADS")
+    np.testing.assert_array_equal(auto["xs"], ref["xs"])
+
+
 def test_ensemble_float32_densities_and_means_only():
     """Keyword extensions of ABMsolveensemble for callers that do not need 2 GB of Float64 densities
     (smm_abm_ensemble_f32, us = NULL): the Float32 array holds exactly the values the Float64 array holds, and the
