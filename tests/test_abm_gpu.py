@@ -421,7 +421,6 @@ def test_dense_kernel_cta_widths_are_bit_identical(n, monkeypatch):
                           xs=np.transpose(outs["512"]["xs"][:, :, :, k], (2, 0, 1)), rtol=RTOL_F32 if precision == "f32" else RTOL_F64)
     # automatic choice: one realization (C1) and a 128-member ensemble take the wide CTAs and still agree with 128 threads
     auto = smm.abm_solve_raw(NT, p=p, q=q, R=2, precision="f32", init_state=init, injected=inj)
-    np.testing.assert_array_equal(auto["xs"], outs["128"]["xs"]) if precision == "f32" else None
     monkeypatch.setenv("SMM_ABM_THREADS", "128")
     ref = smm.abm_solve_raw(NT, p=p, q=q, R=2, precision="f32", init_state=init, injected=inj)
     monkeypatch.delenv("SMM_ABM_THREADS")
