@@ -253,6 +253,65 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
       // pair exactly once (for even G the offset G/2 only from the lower half); the diagonal tile (g, g) is
       // evaluated in ordered form and contains the self pair (abm.jl:42).  Every partial sum has its own
       // shared-memory slot and is added in a fixed order: results are deterministic.
+      if constexpr (THREADS == 128) {
+      // full-GPU configuration: a warp owns whole row groups and keeps their sums in registers across the offsets
+      for (int g = warp; g < G; g += nwarps) {
+        const float4* rowp = xy2 + g * 64 + lane;
+        const float rx = rowp[0].x, ry = rowp[0].z;
+        const float2 nrx = make_float2(-rx, -rx), nry = make_float2(-ry, -ry);
+        float2 ws2 = make_float2(0.f, 0.f), ax2 = ws2, ay2 = ws2;
+        // diagonal tile: lane l against all 32 agents of its own group, two partners per step
+#pragma unroll 8
+        for (int t = 0; t < 16; t++) {
+          const float4 p = rowp[t];
+          const float2 dx = add2(make_float2(p.x, p.y), nrx), dy = add2(make_float2(p.z, p.w), nry);
+          const float2 r2 = fma2(dx, dx, mul2(dy, dy));
+          const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
+          ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
+        }
+        for (int d = 1; d <= D; d++) {
+          if (2 * d == G && g >= D) break;
+          int h = g + d;
+          if (h >= G) h -= G;
+          const float4* colp = xy2 + h * 64 + lane;
+          const float cx = colp[0].x, cy = colp[0].z;
+          const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy);
+          float2 cws2 = make_float2(0.f, 0.f), cax2 = cws2, cay2 = cws2;
+          // step t: row agent l with the column agents (l + t) & 31 and (l + t + 16) & 31; their weights go
+          // to the lanes that own those column agents, which pair them with the rows (l - t) & 31 and
+          // (l - t - 16) & 31 — stored next to each other at index l - t + 32
+#pragma unroll 16
+          for (int t = 0; t < 16; t++) {
+            const float4 p = colp[t];
+            const float2 dx = add2(make_float2(p.x, p.y), nrx), dy = add2(make_float2(p.z, p.w), nry);
+            const float2 r2 = fma2(dx, dx, mul2(dy, dy));
+            const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
+            ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
+            float2 wv;
+            wv.x = __shfl_sync(0xffffffffu, w.x, lane - t);
+            wv.y = __shfl_sync(0xffffffffu, w.y, lane - t - 16);
+            const float4 q = rowp[32 - t];
+            const float2 ex = add2(make_float2(q.x, q.y), ncx), ey = add2(make_float2(q.z, q.w), ncy);
+            cws2 = add2(cws2, wv); cax2 = fma2(wv, ex, cax2); cay2 = fma2(wv, ey, cay2);
+          }
+          float* o = part + (size_t)d * 3 * NG + h * 32 + lane;
+          o[0] = cws2.x + cws2.y; o[NG] = (cax2.x + cax2.y) * kLn2; o[2 * NG] = (cay2.x + cay2.y) * kLn2;
+        }
+        float* o = part + g * 32 + lane;
+        o[0] = ws2.x + ws2.y; o[NG] = (ax2.x + ax2.y) * kLn2; o[2 * NG] = (ay2.x + ay2.y) * kLn2;
+      }
+      __syncthreads();
+      for (int j = tid; j < n; j += kThreads) {
+        real ws = part[j], ax = part[NG + j], ay = part[2 * NG + j];
+        const int hg = j >> 5;
+        for (int d = 1; d <= D; d++) {
+          if (2 * d == G && hg < D) break;  // that slot is only written for the upper half of the groups
+          const real* o = part + (size_t)d * 3 * NG + j;
+          ws += o[0]; ax += o[NG]; ay += o[2 * NG];
+        }
+        finish(j, xc[j], ax, ay, ws);
+      }
+      } else {
       // Work items = tiles: NO off-diagonal tiles (d = 1..D; for even G the offset G/2 only from the lower half of the
       // groups) and G diagonal ones.  Off-diagonal tiles cost ~1.7x a diagonal one, so they are dealt first and in
       // snake order over the warps (longest-processing-time rule): 36 tiles at n = 250 balance to within 6 % over 16
@@ -323,6 +382,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
           ws += o[0]; ax += o[NG]; ay += o[2 * NG];
         }
         finish(j, xc[j], ax, ay, ws);
+      }
       }
     } else
     for (int j0 = tid; j0 < n; j0 += 2 * kThreads) {
