@@ -424,7 +424,8 @@ def test_dense_kernel_cta_widths(n, monkeypatch):
                               xs=np.transpose(outs[th]["xs"][:, :, :, k], (2, 0, 1)), rtol=RTOL_F32 if precision == "f32" else RTOL_F64)
     # automatic choice: a 2-member ensemble takes the widest CTA the population can feed
     auto = smm.abm_solve_raw(NT, p=p, q=q, R=2, precision="f32", init_state=init, injected=inj)
-    monkeypatch.setenv("SMM_ABM_THREADS", "512" if n >= 225 else "256")
+    groups = (n + 31) // 32
+    monkeypatch.setenv("SMM_ABM_THREADS", "512" if groups >= 8 else "256" if groups >= 4 else "128")
     ref = smm.abm_solve_raw(NT, p=p, q=q, R=2, precision="f32", init_state=init, injected=inj)
     monkeypatch.delenv("SMM_ABM_THREADS")
     np.testing.assert_array_equal(auto["xs"], ref["xs"])
