@@ -485,13 +485,15 @@ __global__ void abm_draws_kernel(int n, uint64_t seed, uint32_t realization, int
   u2[t] = d;
 }
 
-size_t dense_smem_bytes(int n, int L, int M, size_t real_size, bool sym) {
+size_t dense_smem_bytes(int n, int L, int M, size_t real_size, bool sym, int threads) {
   int npad = (n + 3) & ~3;
   size_t b = 2 * (size_t)npad * 2 * real_size + sizeof(double) * (4 * L + 4 * M + L + 4 * (L + M)) +
              sizeof(int) * (4 * (L + M) + npad) + sizeof(float) * 3 * L + npad + 16;
   if (sym) {
     const size_t G = (n + 31) / 32, D = G / 2;
-    b += 16 + 2 * G * 64 * 8 + (1 + 2 * D) * 3 * G * 32 * 4;
+    // 128-thread CTAs keep row sums in registers (slots 0..D); wider CTAs deal single tiles (row + column slots).
+    // The difference decides whether 7 CTAs (all 1 024 realizations of C2) fit one SM's shared memory.
+    b += 16 + 2 * G * 64 * 8 + (1 + (threads == 128 ? 1 : 2) * D) * 3 * G * 32 * 4;
   }
   return b;
 }
@@ -515,8 +517,6 @@ int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
   // FP32 all-to-all populations of up to 512 agents take the symmetric-pair path (SMM_ABM_SYM=0: ordered pairs)
   const char* ev = getenv("SMM_ABM_SYM");
   const bool sym = precision == SMM_PREC_F32 && A.rowptr == nullptr && (A.k.n + 31) / 32 <= kSymMaxGroups && !(ev && ev[0] == '0');
-  size_t sm = dense_smem_bytes(A.k.n, A.k.L, A.k.M, precision == SMM_PREC_F64 ? 8 : 4, sym);
-  SMM_REQUIRE(ctx, sm <= 227 * 1024, "dense ABM kernel: n=%d does not fit shared memory (%zu B); pass a CSR network", A.k.n, sm);
   SMM_REQUIRE(ctx, A.k.L + A.k.M <= kThreads && A.k.L * A.k.M <= kThreads, "dense ABM kernel: L+M and L*M must be <= %d", kThreads);
   // CTA width from the ensemble size: the widest CTA for which all R realizations are still resident at once (one
   // 512-thread CTA or three 256-thread CTAs per SM at their register counts), but never wider than the tile count
@@ -528,6 +528,8 @@ int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
     else if (A.R <= 3 * ctx->sm_count && groups >= 4) threads = 256;
     if (const char* tv = getenv("SMM_ABM_THREADS")) { const int t = atoi(tv); if (t == 128 || t == 256 || t == 512) threads = t; }
   }
+  size_t sm = dense_smem_bytes(A.k.n, A.k.L, A.k.M, precision == SMM_PREC_F64 ? 8 : 4, sym, threads);
+  SMM_REQUIRE(ctx, sm <= 227 * 1024, "dense ABM kernel: n=%d does not fit shared memory (%zu B); pass a CSR network", A.k.n, sm);
   int rc;
   if (precision == SMM_PREC_F64) rc = launch_dense_w<double, false>(ctx, A, sm, threads);
   else if (sym) rc = launch_dense_w<float, true>(ctx, A, sm, threads);

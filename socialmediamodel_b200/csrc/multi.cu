@@ -12,13 +12,67 @@
 #include <nccl.h>  // types only; every entry point goes through dlsym
 
 #include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
 #include "smm_internal.h"
 
+// One persistent host thread per member GPU (a fresh std::thread per call pays the CUDA runtime's per-thread
+// device binding again every time: measured 14 ms per 2-GPU call).
+struct smm_worker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<void()> job;
+  bool has_job = false, done = true, quit = false;
+  void loop() {
+    for (;;) {
+      std::function<void()> j;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return has_job || quit; });
+        if (quit) return;
+        j = std::move(job);
+        has_job = false;
+      }
+      j();
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        done = true;
+      }
+      cv.notify_all();
+    }
+  }
+  void start() { th = std::thread([this] { loop(); }); }
+  void submit(std::function<void()> j) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      job = std::move(j);
+      has_job = true;
+      done = false;
+    }
+    cv.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return done; });
+  }
+  void stop() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      quit = true;
+    }
+    cv.notify_all();
+    if (th.joinable()) th.join();
+  }
+};
+
 struct smm_multi {
   int n = 0;
+  std::vector<smm_worker*> workers;  // workers[g] drives member g, g >= 1 (member 0 runs on the calling thread)
   std::vector<int> devices;
   std::vector<smm_ctx*> member;
   // NCCL (single process, one communicator per member GPU)
@@ -36,6 +90,7 @@ struct smm_multi {
 
 static void multi_free(smm_multi* m) {
   if (!m) return;
+  for (smm_worker* w : m->workers) if (w) { w->stop(); delete w; }
   if (m->nccl)
     for (ncclComm_t c : m->comms) if (c) m->CommDestroy(c);
   for (smm_ctx* c : m->member) smm_ctx_destroy(c);
@@ -93,6 +148,8 @@ extern "C" int smm_ctx_create_multi(int ngpus, const int* device_ids, smm_ctx** 
     c->shard_mode = true;
     m->member.push_back(c);
   }
+  m->workers.assign(ngpus, nullptr);
+  for (int g = 1; g < ngpus; g++) { m->workers[g] = new smm_worker(); m->workers[g]->start(); }
   m->nccl = ngpus > 1 && multi_init_nccl(m);
   smm_ctx* lead = nullptr;
   int rc = smm_ctx_create(m->devices[0], &lead);
@@ -189,12 +246,9 @@ int smm_multi_abm_ensemble(smm_ctx* lead, const smm_params* q, int32_t precision
         us ? (char*)us + (size_t)r0 * per_real * us_elem : nullptr, us_f32, zs ? zs + (size_t)r0 * nsave * M * 2 : nullptr,
         ys ? ys + (size_t)r0 * nsave * L * 2 : nullptr, su, sz, sy, nu);
   };
-  {
-    std::vector<std::thread> th;
-    for (int g = 1; g < G; g++) th.emplace_back(work, g);
-    work(0);
-    for (auto& t : th) t.join();
-  }
+  for (int g = 1; g < G; g++) m->workers[g]->submit([&work, g] { work(g); });
+  work(0);
+  for (int g = 1; g < G; g++) m->workers[g]->wait();
   for (int g = 0; g < G; g++)
     if (rcs[g] != SMM_OK) return smm_fail(lead, rcs[g], "GPU %d: %s", m->devices[g], m->member[g]->err.c_str());
   lead->launches = smm_multi_launches(m);
@@ -272,12 +326,9 @@ int smm_multi_pde_solve(smm_ctx* lead, const smm_grid* grid, const smm_params* q
                            zs ? zs + (size_t)b0 * nsave * 4 : nullptr, ys ? ys + (size_t)b0 * nsave * 2 * L : nullptr,
                            sum_us ? h_us[g].data() : nullptr, sum_zs ? h_zs[g].data() : nullptr, sum_ys ? h_ys[g].data() : nullptr);
   };
-  {
-    std::vector<std::thread> th;
-    for (int g = 1; g < G; g++) th.emplace_back(work, g);
-    work(0);
-    for (auto& t : th) t.join();
-  }
+  for (int g = 1; g < G; g++) m->workers[g]->submit([&work, g] { work(g); });
+  work(0);
+  for (int g = 1; g < G; g++) m->workers[g]->wait();
   for (int g = 0; g < G; g++)
     if (rcs[g] != SMM_OK) return smm_fail(lead, rcs[g], "GPU %d: %s", m->devices[g], m->member[g]->err.c_str());
   lead->launches = smm_multi_launches(m);
