@@ -621,6 +621,203 @@ __global__ void __launch_bounds__(BX* BY, sizeof(real) == 4 ? 3 : 1) pde_stage_k
   moments_ticket(A, b, sm, FIN_STAGE);
 }
 
+// K7, throughput form (FP32, fixed-step schemes, compile-time L): the same right-hand side and RK update as
+// pde_stage_kernel, two grid points (ix, ix + 1) per thread in the halves of packed FP32x2 registers.  The two points
+// share every per-plane scalar (influencer / medium positions, rate factors, RK weights), so the y-direction fluxes, the
+// reaction terms, the RK update and the accumulator traffic are FADD2 / FMUL2 / FFMA2 on pairs, the centre / upper / lower
+// neighbours are 8-byte shared-memory loads, and the step-start state, accumulator and result move as 8-byte global
+// accesses; only the x-direction differences, which couple the two points, stay scalar (and share the flux at the
+// common face).  CTA = 32 x 8 threads = 64 x 8 grid points; the tile (2L planes x 10 x 72, one-cell halo) and the two
+// force tiles arrive by TMA.  Boundary formulas (pde.jl:231-234, one-sided rows of C and MassM) are compiled only
+// into CTAs that touch the domain edge.
+constexpr int BX2 = 2 * BX, TW2 = BX2 + 8;
+
+template <int LT, bool EDGE>
+__device__ __forceinline__ void stage2_planes(const StageArgs& A, const float* tile, const float* s_yx, const float* s_yy, const float (*s_R)[LMAX],
+                                              const float* s_zx, const float* s_zy, int tx, int ty, int ix, int iy, bool in0, bool in1,
+                                              float pa, float pb, float pc, float D, float2 X2, float Y, const float* sFx, const float* sFy,
+                                              const float2* unv, const float2* accv, float* un_unused, float* acc, float* Uout, size_t plane,
+                                              size_t o_c, float dtA, float dtB, float dtC, float dtw, float2& rs_out, float* mom0, float* momx) {
+  constexpr int L = LT, NP = 2 * LT;
+  const int Nx = A.Nx, Ny = A.Ny;
+  const float h = (float)A.dx, ih = (float)(1.0 / A.dx), hih = 0.5f * ih, ih2 = (float)(1.0 / (A.dx * A.dx));
+  const float Ddx = (float)((double)D / A.dx), Ddy = (float)((double)D / A.dy);  // pde.jl:231-234 (Q12)
+  const float bcv = pb + pc;
+  // plane-independent parts of the velocity a F + b (y_j - x) + c (z_i - x)   (pde.jl:214)
+  const float* fxr = sFx + ty * TW2 + XO + 2 * tx;
+  const float2 fxc2 = *reinterpret_cast<const float2*>(fxr);
+  const float2 vxc0 = fma2(bc2(pa), fxc2, mul2(bc2(-bcv), X2));
+  const float vl0 = pa * fxr[-1] - bcv * (X2.x - h), vr0 = pa * fxr[2] - bcv * (X2.y + h);
+  const float* fyr = sFy + ty * BX2 + 2 * tx;
+  const float2 vym0 = fma2(bc2(pa), *reinterpret_cast<const float2*>(fyr), bc2(-bcv * (Y - h)));
+  const float2 vyc0 = fma2(bc2(pa), *reinterpret_cast<const float2*>(fyr + BX2), bc2(-bcv * Y));
+  const float2 vyp0 = fma2(bc2(pa), *reinterpret_cast<const float2*>(fyr + 2 * BX2), bc2(-bcv * (Y + h)));
+  const bool x_lo0 = EDGE && ix == 0, x_hi0 = EDGE && ix == Nx - 1, x_hi1 = EDGE && ix + 1 == Nx - 1;
+  const bool y_lo = EDGE && iy == 0, y_hi = EDGE && iy == Ny - 1;
+  const float* tc = tile + (ty + 1) * TW2 + XO + 2 * tx;  // centre pair of plane 0
+
+  float2 rsum[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)}, gsum[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  float2 E[L];
+#pragma unroll
+  for (int j = 0; j < L; j++) {
+    const float dyj = Y - s_yy[j];
+    E[j] = make_float2(fast_exp_neg_dist(X2.x - s_yx[j], dyj), fast_exp_neg_dist(X2.y - s_yx[j], dyj));
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      rsum[i] = add2(rsum[i], *reinterpret_cast<const float2*>(tc + (j * 2 + i) * TH * TW2));
+      gsum[i] = fma2(E[j], bc2(s_R[i][j]), gsum[i]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < L; j++) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int p = j * 2 + i;
+      const float* t = tc + p * TH * TW2;
+      const float2 c = *reinterpret_cast<const float2*>(t);
+      const float2 up = *reinterpret_cast<const float2*>(t - TW2), dn = *reinterpret_cast<const float2*>(t + TW2);
+      const float l = t[-1], r = t[2];
+      const float bxv = pb * s_yx[j] + pc * s_zx[i], byv = pb * s_yy[j] + pc * s_zy[i];
+      // x direction: the flux at the face between the two points is shared; everything else scalar
+      const float2 fxc = mul2(c, add2(vxc0, bc2(bxv)));
+      const float fl = l * (vl0 + bxv), fr = r * (vr0 + bxv);
+      float ddx0 = (fxc.y - fl) * hih, ddx1 = (fr - fxc.x) * hih;
+      float lapx0 = l - 2.f * c.x + c.y, lapx1 = c.x - 2.f * c.y + r;
+      // y direction: packed
+      const float2 fym = mul2(up, add2(vym0, bc2(byv))), fyp = mul2(dn, add2(vyp0, bc2(byv)));
+      float2 ddy = mul2(sub2(fyp, fym), bc2(hih));
+      float2 lapy = add2(fma2(bc2(-2.f), c, up), dn);
+      float2 bnd = make_float2(0.f, 0.f);
+      if (EDGE) {  // one-sided rows of C / MassM and the boundary flux terms (pde.jl:68-87, 231-234)
+        const float2 fyc = mul2(c, add2(vyc0, bc2(byv)));
+        if (x_lo0) { ddx0 = (fxc.y - fxc.x) * ih; lapx0 = c.y - c.x; bnd.x -= Ddx * fxc.x; }
+        if (x_hi0) { ddx0 = (fxc.x - fl) * ih; lapx0 = l - c.x; bnd.x += Ddx * fxc.x; }
+        if (x_hi1) { ddx1 = (fxc.y - fxc.x) * ih; lapx1 = c.x - c.y; bnd.y += Ddx * fxc.y; }
+        if (y_lo) { ddy = mul2(sub2(fyp, fyc), bc2(ih)); lapy = sub2(dn, c); bnd = fma2(bc2(-Ddy), fyc, bnd); }
+        if (y_hi) { ddy = mul2(sub2(fyc, fym), bc2(ih)); lapy = sub2(up, c); bnd = fma2(bc2(Ddy), fyc, bnd); }
+      }
+      const float2 G = mul2(E[j], bc2(s_R[i][j]));
+      // reac = -c (gsum - G) + G (rsum - c)   (pde.jl:220-225)
+      const float2 reac = fma2(G, sub2(rsum[i], c), mul2(c, sub2(G, gsum[i])));
+      const float2 lap = add2(make_float2(lapx0, lapx1), lapy), dive = add2(make_float2(ddx0, ddx1), ddy);
+      const float2 k = add2(sub2(fma2(bc2(D * ih2), lap, bnd), dive), reac);  // pde.jl:236
+      const size_t po = (size_t)p * plane + o_c;
+      float2 out = mul2(bc2(dtC), k);
+      if (dtA != 0.f) out = fma2(bc2(dtA), unv[p], out);
+      if (dtB != 0.f) out = fma2(bc2(dtB), c, out);
+      float2 accn = make_float2(0.f, 0.f);
+      if (A.acc_mode == ACC_INIT) accn = fma2(bc2(dtw), k, unv[p]);
+      else if (A.acc_mode == ACC_ADD) accn = fma2(bc2(dtw), k, accv[p]);
+      else if (A.acc_mode == ACC_FINAL) out = fma2(bc2(dtw), k, accv[p]);
+      if (in1) {
+        if (A.acc_mode == ACC_INIT || A.acc_mode == ACC_ADD) *reinterpret_cast<float2*>(acc + po) = accn;
+        *reinterpret_cast<float2*>(Uout + po) = out;
+      } else if (in0) {
+        if (A.acc_mode == ACC_INIT || A.acc_mode == ACC_ADD) acc[po] = accn.x;
+        Uout[po] = out.x;
+      }
+      const float v0 = in0 ? out.x : 0.f, v1 = in1 ? out.y : 0.f;
+      rs_out = add2(rs_out, make_float2(v0, v1));
+      mom0[(ty * NP + p) * 32 + tx] = v0 + v1;
+      momx[(ty * NP + p) * 32 + tx] = v0 * X2.x + v1 * X2.y;
+    }
+  }
+}
+
+template <int LT>
+__global__ void __launch_bounds__(BX* BY, 2) pde_stage2_kernel(const __grid_constant__ StageArgs A) {
+  constexpr int L = LT, NP = 2 * LT;
+  const int Nx = A.Nx, Ny = A.Ny, b = blockIdx.z;
+  const int bx0 = blockIdx.x * BX2, by0 = blockIdx.y * BY;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int ix = bx0 + 2 * tx, iy = by0 + ty;
+  const int tid = ty * BX + tx;
+  const bool in0 = ix < Nx && iy < Ny, in1 = ix + 1 < Nx && iy < Ny;
+  pdl_wait();
+  pdl_launch_dependents();
+  extern __shared__ __align__(128) unsigned char smem_stage[];
+  float* tile = reinterpret_cast<float*>(smem_stage);                                                         // [NP][TH][TW2]
+  float* sFx = reinterpret_cast<float*>(smem_stage + align128(sizeof(float) * NP * TH * TW2));                 // [BY][TW2]
+  float* sFy = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sFx) + align128(sizeof(float) * BY * TW2));   // [TH][BX2]
+  float* mom0 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sFy) + align128(sizeof(float) * TH * BX2));  // [BY][NP][32]
+  float* momx = mom0 + BY * NP * 32;
+  __shared__ __align__(8) unsigned long long tma_bar;
+  __shared__ double sm[2 * LMAX * 3];
+  __shared__ float s_yx[LMAX], s_yy[LMAX], s_R[2][LMAX], s_zx[2], s_zy[2];
+  __shared__ float s_par[4];
+  if (tid < L) {
+    s_yx[tid] = (float)A.coef[b].y[tid][0]; s_yy[tid] = (float)A.coef[b].y[tid][1];
+    s_R[0][tid] = (float)A.coef[b].R[0][tid]; s_R[1][tid] = (float)A.coef[b].R[1][tid];
+  }
+  if (tid < 2) { s_zx[tid] = (float)A.coef[b].z[tid][0]; s_zy[tid] = (float)A.coef[b].z[tid][1]; }
+  if (tid == 0) {
+    s_par[0] = (float)A.inst[b].a; s_par[1] = (float)A.inst[b].b; s_par[2] = (float)A.inst[b].c; s_par[3] = (float)A.inst[b].D;
+    mbar_init(&tma_bar, 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&tma_bar, (unsigned)(sizeof(float) * (NP * TH * TW2 + BY * TW2 + TH * BX2)));
+    tma_load_3d(tile, &A.tmU, bx0 - XO, by0 - 1, b * NP, &tma_bar);
+    tma_load_3d(sFx, &A.tmFx, bx0 - XO, by0, b, &tma_bar);
+    tma_load_3d(sFy, &A.tmFy, bx0, by0 - 1, b, &tma_bar);
+  }
+  const int Pw = A.Pw;
+  const size_t plane = (size_t)Pw * Ny;
+  const float* un = static_cast<const float*>(A.un) + (size_t)b * NP * plane;
+  float* Uout = static_cast<float*>(A.Uout) + (size_t)b * NP * plane;
+  float* acc = A.acc ? static_cast<float*>(A.acc) + (size_t)b * NP * plane : nullptr;
+  // pair offset: even column, clamped into the row (the pad columns up to Pw hold zeros and are never written)
+  const size_t o_c = (size_t)min(iy, Ny - 1) * Pw + min(ix, (Nx - 1) & ~1);
+  const float dtA = (float)A.A, dtB = (float)A.Bc, dtC = (float)(A.C * A.dt), dtw = (float)(A.bw * A.dt);
+  // step-start state and accumulator of the two grid points for all planes: issued before the TMA wait
+  float2 unv[NP], accv[NP];
+  const bool need_un = dtA != 0.f || A.acc_mode == ACC_INIT;
+  const bool need_acc = A.acc_mode == ACC_ADD || A.acc_mode == ACC_FINAL;
+#pragma unroll
+  for (int p = 0; p < NP; p++) {
+    unv[p] = need_un ? *reinterpret_cast<const float2*>(un + (size_t)p * plane + o_c) : make_float2(0.f, 0.f);
+    accv[p] = need_acc ? *reinterpret_cast<const float2*>(acc + (size_t)p * plane + o_c) : make_float2(0.f, 0.f);
+  }
+  mbar_wait(&tma_bar, 0);
+  const float pa = s_par[0], pb = s_par[1], pc = s_par[2], D = s_par[3];
+  const float2 X2 = make_float2((float)(A.gx0 + min(ix, Nx - 1) * A.dx), (float)(A.gx0 + min(ix + 1, Nx - 1) * A.dx));
+  const float Y = (float)(A.gy0 + min(iy, Ny - 1) * A.dy);
+  float2 rs_out = make_float2(0.f, 0.f);
+  const bool edge = bx0 == 0 || bx0 + BX2 >= Nx || by0 == 0 || by0 + BY >= Ny;  // CTA-uniform
+  if (edge)
+    stage2_planes<LT, true>(A, tile, s_yx, s_yy, s_R, s_zx, s_zy, tx, ty, ix, iy, in0, in1, pa, pb, pc, D, X2, Y, sFx, sFy, unv, accv, nullptr, acc,
+                            Uout, plane, o_c, dtA, dtB, dtC, dtw, rs_out, mom0, momx);
+  else
+    stage2_planes<LT, false>(A, tile, s_yx, s_yy, s_R, s_zx, s_zy, tx, ty, ix, iy, in0, in1, pa, pb, pc, D, X2, Y, sFx, sFy, unv, accv, nullptr, acc,
+                             Uout, plane, o_c, dtA, dtB, dtC, dtw, rs_out, mom0, momx);
+  if (!A.do_moments) return;
+  {
+    float* ro = static_cast<float*>(A.rhosum_out) + (size_t)b * plane + o_c;
+    if (in1) *reinterpret_cast<float2*>(ro) = rs_out;
+    else if (in0) ro[0] = rs_out.x;
+  }
+  __syncthreads();
+  {  // block-level moments, fixed order (deterministic): warp w reduces planes w, w + 8, ..
+    const int nblk = gridDim.x * gridDim.y, blk = blockIdx.y * gridDim.x + blockIdx.x;
+    for (int p = ty; p < NP; p += BY) {
+      float s0 = 0, sx = 0, sy = 0;
+#pragma unroll
+      for (int w = 0; w < BY; w++) {
+        const float v = mom0[(w * NP + p) * 32 + tx];
+        s0 += v;
+        sx += momx[(w * NP + p) * 32 + tx];
+        sy += v * (float)(A.gy0 + min(by0 + w, Ny - 1) * A.dy);
+      }
+      s0 = warp_sum(s0); sx = warp_sum(sx); sy = warp_sum(sy);
+      if (tx == 0) {
+        double* o = A.partials + ((size_t)b * nblk + blk) * (NP * 3) + p * 3;
+        o[0] = (double)s0; o[1] = (double)sx; o[2] = (double)sy;
+      }
+    }
+  }
+  moments_ticket(A, b, sm, FIN_STAGE);
+}
+
 // K6 direct Toeplitz correlation.  CTA = 8x8 output points x NS input slices; wext[ady][d + Nx-1]
 // = exp(-h sqrt(d^2 + ady^2)) for d in -(Nx-1)..Nx-1 (row-extended so the index is monotone in jx).
 constexpr int CT = 8, NS = 16;
@@ -730,7 +927,10 @@ struct smm_pde_batch {
   int64_t steps_taken;
   smm_fft_plan* fft;  // null = direct Toeplitz kernel
   CUtensorMap tm_u, tm_ua, tm_ub, tm_fx, tm_fy;  // TMA descriptors (stage kernel tile loads)
+  CUtensorMap tm_u2, tm_ua2, tm_ub2, tm_fx2, tm_fy2;  // the 64-wide boxes of pde_stage2_kernel
   bool use_tma;
+  bool stage2;        // FP32 fixed-step stages run the packed two-points-per-thread kernel
+  int nbx2;
   bool no_graph;      // stream capture unavailable on the caller's stream: launch kernels directly
   // adaptive integrator (allocated by the first smm_pde_batch_advance)
   double time;        // batch clock
@@ -791,6 +991,22 @@ static int launch_conv(smm_ctx* ctx, smm_pde_batch* pb) {
   return SMM_OK;
 }
 
+static size_t stage2_smem(int L) {
+  return align128(4 * (size_t)2 * L * TH * TW2) + align128(4 * (size_t)BY * TW2) + align128(4 * (size_t)TH * BX2) + 2 * 4 * (size_t)BY * 2 * L * 32;
+}
+
+template <int LT>
+static int launch_stage2_t(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
+  dim3 grid(pb->nbx2, pb->nby, pb->B), block(BX, BY);
+  const size_t sm = stage2_smem(pb->L);
+  SMM_CUDA(ctx, cudaFuncSetAttribute(pde_stage2_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 48 * 1024)));
+  static const bool pdl = !(getenv("SMM_PDE_PDL") && getenv("SMM_PDE_PDL")[0] == '0');
+  SMM_CUDA(ctx, smm_launch_pdl(pdl ? ctx->sm_count : 0, pde_stage2_kernel<LT>, grid, block, sm, ctx->stream, A));
+  ctx->launches++;
+  SMM_CUDA(ctx, cudaGetLastError());
+  return SMM_OK;
+}
+
 static size_t stage_smem(int L, size_t rs) {
   return align128(rs * 2 * L * TH * TW) + align128(rs * BY * TW) + align128(rs * TH * BX) + rs * (size_t)BY * 2 * L * 32;
 }
@@ -819,8 +1035,18 @@ static int launch_stage_ad(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) 
   }
 }
 
-static int launch_stage(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
-  return A.ctl ? launch_stage_ad<true>(ctx, pb, A) : launch_stage_ad<false>(ctx, pb, A);
+static int launch_stage(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A0) {
+  if (pb->stage2 && !A0.ctl) {  // FP32, fixed step, L in {4, 5, 6}: packed kernel with its own (64-wide) TMA boxes
+    StageArgs A = A0;
+    A.tmU = A0.U == pb->u ? pb->tm_u2 : (A0.U == pb->Ua ? pb->tm_ua2 : pb->tm_ub2);
+    A.tmFx = pb->tm_fx2; A.tmFy = pb->tm_fy2;
+    switch (pb->L) {
+      case 4: return launch_stage2_t<4>(ctx, pb, A);
+      case 5: return launch_stage2_t<5>(ctx, pb, A);
+      default: return launch_stage2_t<6>(ctx, pb, A);
+    }
+  }
+  return A0.ctl ? launch_stage_ad<true>(ctx, pb, A0) : launch_stage_ad<false>(ctx, pb, A0);
 }
 
 // one RK step = nstages x (conv, stage).  Buffer roles: u = step start / result, Ua/Ub stage states.
@@ -953,6 +1179,8 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
   pb->fft = nullptr;
   pb->no_graph = false;
   pb->use_tma = false;
+  pb->stage2 = false;
+  pb->nbx2 = 0;
   pb->rs = precision == SMM_PREC_F64 ? 8 : 4;
   pb->Pw = (grid->Nx + 3) & ~3;  // 16-byte row pitch in both precisions (TMA global strides)
   pb->plane = (size_t)pb->Pw * grid->Ny;
@@ -1007,6 +1235,20 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
                 make_map3(&pb->tm_fx, pb->Fx, precision, grid->Nx, grid->Ny, pb->Pw, (size_t)B, TW, BY, 1) &&
                 make_map3(&pb->tm_fy, pb->Fy, precision, grid->Nx, grid->Ny, pb->Pw, (size_t)B, BX, TH, 1);
       if (!ok) pb->use_tma = false;
+    }
+    // packed stage kernel (two grid points per thread, 64 x 8 tiles): FP32, L = 4..6, and enough tiles to fill the GPU
+    // (a single 89 x 89 instance has 24 of them: the 32-wide kernel spreads it over 36 CTAs and stays)
+    pb->nbx2 = (grid->Nx + BX2 - 1) / BX2;
+    pb->stage2 = pb->use_tma && precision == SMM_PREC_F32 && L >= 4 && L <= 6 && (size_t)B * pb->nbx2 * pb->nby >= (size_t)2 * ctx->sm_count;
+    { const char* e2 = getenv("SMM_PDE_STAGE2"); if (e2 && e2[0] == '0') pb->stage2 = false; if (e2 && e2[0] == '1') pb->stage2 = pb->use_tma && precision == SMM_PREC_F32 && L >= 4 && L <= 6; }
+    if (pb->stage2) {
+      const size_t nz = (size_t)2 * L * B;
+      bool ok = make_map3(&pb->tm_u2, pb->u, precision, grid->Nx, grid->Ny, pb->Pw, nz, TW2, TH, 2 * L) &&
+                make_map3(&pb->tm_ua2, pb->Ua, precision, grid->Nx, grid->Ny, pb->Pw, nz, TW2, TH, 2 * L) &&
+                make_map3(&pb->tm_ub2, pb->Ub, precision, grid->Nx, grid->Ny, pb->Pw, nz, TW2, TH, 2 * L) &&
+                make_map3(&pb->tm_fx2, pb->Fx, precision, grid->Nx, grid->Ny, pb->Pw, (size_t)B, TW2, BY, 1) &&
+                make_map3(&pb->tm_fy2, pb->Fy, precision, grid->Nx, grid->Ny, pb->Pw, (size_t)B, BX2, TH, 1);
+      if (!ok) pb->stage2 = false;
     }
   }
   // interaction force: FFT correlation (default), or the direct O(N^2) kernel when SMM_PDE_CONV=direct

@@ -131,6 +131,13 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
       : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
   return d;
 }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  float2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }  // scalar broadcast (folds into the operand)
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) {
   float2 d;
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))

@@ -8,6 +8,7 @@ import pytest
 import socialmediamodel_b200 as smm
 from oracle import abm_oracle as A
 from oracle import pde_oracle as P
+from oracle.abm_oracle import default_q as A_default_q
 
 pytestmark = pytest.mark.gpu
 
@@ -261,6 +262,50 @@ def test_fast_fft_path_against_generic_path_and_oracle(dx, N, monkeypatch):
         for b in range(B):
             dur, _, _ = P.rhs(u[..., b], z[..., b], y[..., b], oracle_p(p), dict(ql[b]))
             assert rel(res["fast4"][0][..., b], dur) < TOL32
+
+
+@pytest.mark.parametrize("N", [47, 89, 177])
+@pytest.mark.parametrize("scheme", ["rk4", "ssprk3", "heun", "euler"])
+def test_packed_stage_kernel_against_generic_and_f64(N, scheme, monkeypatch):
+    """pde_stage2_kernel (two grid points per thread, FP32x2; edge-only tiles at 47, interior tiles at 177) against the
+    one-point-per-thread kernel and the Float64 path (oracle-exact, see above): right-hand side and 6 steps of every
+    scheme (all RK accumulator modes), batch of 2 with different parameters, L = 4."""
+    p = smm.PDEconstructcoarse() if N == 47 else smm.PDEconstruct(dx={89: 0.05, 177: 0.025}[N])
+    assert p.N_x == N
+    rng = np.random.default_rng(N)
+    qs = [smm.parameters(a=0.7, sigma=0.4), smm.parameters(a=2.0, eta=5.0)]
+    inits = [smm.constructinitial("4inf", (p, q)) for q in qs]
+    ql = [qq for _, qq in inits]
+    U = np.stack([uz.x[0] * (1 + 0.3 * rng.random(uz.x[0].shape)) for uz, _ in inits], axis=-1)
+    Z = np.stack([uz.x[1] for uz, _ in inits], axis=-1); Y = np.stack([uz.x[2] for uz, _ in inits], axis=-1)
+    dt = min(smm.default_dt(p, q) for q in ql)
+    run = lambda prec: (smm.pde_rhs(U, Z, Y, p=p, q=ql, precision=prec),
+                        smm.pde_solve_raw(p, ql, U, Z, Y, dt=dt, nsteps=6, savesteps=[3, 6], scheme=scheme, precision=prec))
+    monkeypatch.setenv("SMM_PDE_STAGE2", "0")
+    rhs1, sol1 = run("f32")
+    monkeypatch.setenv("SMM_PDE_STAGE2", "1")
+    rhs2, sol2 = run("f32")
+    monkeypatch.delenv("SMM_PDE_STAGE2")
+    rhs64, sol64 = run("f64")
+    assert rel(rhs2[0], rhs1[0]) < 2e-6 and rel(rhs2[0], rhs64[0]) < TOL32
+    assert rel(sol2["us"], sol1["us"]) < 2e-6 and rel(sol2["us"], sol64["us"]) < TOL32
+    assert np.abs(sol2["ys"] - sol64["ys"]).max() < 1e-6 and np.abs(sol2["zs"] - sol64["zs"]).max() < 1e-6
+
+
+def test_packed_stage_kernel_controlled_L5(monkeypatch):
+    """L = 5 with a controlled, zero-mass influencer (controlstrategies.jl:16-30; r(NaN) = 0.1, pde.jl:26-32)."""
+    from oracle import control_oracle as CO
+    p = smm.PDEconstructcoarse()
+    q = smm.parameters(eta=1.0)
+    po, qo = oracle_p(p), A_default_q(eta=1.0)
+    uzy0, sl, q2, ci, cm, slm = CO.prep(0.01, po, qo, start="zero", savedt=0.01, dt=1e-3, countercontrol="no")
+    u, z, y = uzy0
+    qq = q.merge(L=5, controlled_inf=ci, controlled_med=cm)
+    monkeypatch.setenv("SMM_PDE_STAGE2", "1")
+    du, dz, dy = smm.pde_rhs(u, z, y, p=p, q=qq, precision="f32")
+    monkeypatch.delenv("SMM_PDE_STAGE2")
+    dur, dzr, dyr = P.rhs(u, z, y, po, dict(q2), ci, cm)
+    assert rel(du, dur) < TOL32 and np.abs(dy - dyr).max() < 1e-6
 
 
 def test_c4_grid_fp32_drift_500_steps():
