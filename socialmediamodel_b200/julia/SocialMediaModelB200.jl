@@ -50,63 +50,129 @@ grid(p) = SmmGrid(size(p.X, 1), size(p.X, 2), p.domain[1, 1], p.domain[2, 1], p.
 
 mutable struct Ctx
     h::Ptr{Cvoid}
+    devices::Any
 end
 const CTX = Ref{Union{Nothing,Ctx}}(nothing)
 
-function ctx()
-    if CTX[] === nothing
-        h = Ref{Ptr{Cvoid}}(C_NULL)
+"""
+    use_devices!(devices)
+
+Select the GPUs behind the library context of this Julia process: `nothing` = one GPU (`LOCAL_RANK`, default 0),
+`:all` = every visible GPU, or a vector of device ids.  With several GPUs the ensemble calls below shard their
+realizations / instances over them INSIDE the one `ccall` (smm_ctx_create_multi: one host thread per GPU, NCCL
+all-reduce of the ensemble sums), so the unchanged `ABMsolveensemble(200, 1024)` uses the whole box from one task.
+The environment variable SMM_B200_DEVICES ("all" or "0,1,2,3") sets the default.
+"""
+function use_devices!(devices)
+    if CTX[] !== nothing
+        ccall((:smm_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), CTX[].h)
+        CTX[] = nothing
+    end
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    if devices === nothing
         dev = parse(Int, get(ENV, "LOCAL_RANK", "0"))
         rc = ccall((:smm_ctx_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), dev, h)
-        rc == 0 || error("smm_ctx_create failed [$rc]: ", unsafe_string(ccall((:smm_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
-        CTX[] = Ctx(h[])
+    elseif devices === :all
+        rc = ccall((:smm_ctx_create_multi, LIB), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), 0, C_NULL, h)
+    else
+        ids = Cint.(collect(devices))
+        rc = ccall((:smm_ctx_create_multi, LIB), Cint, (Cint, Ptr{Cint}, Ref{Ptr{Cvoid}}), length(ids), ids, h)
+    end
+    rc == 0 || error("smm_ctx_create failed [$rc]: ", unsafe_string(ccall((:smm_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+    CTX[] = Ctx(h[], devices)
+    return nothing
+end
+
+function ctx(; devices = :default)
+    if CTX[] === nothing || (devices !== :default && devices != CTX[].devices)
+        if devices === :default
+            e = get(ENV, "SMM_B200_DEVICES", "")
+            devices = e == "" ? nothing : (e == "all" ? :all : parse.(Int, split(e, ",")))
+        end
+        use_devices!(devices)
     end
     return CTX[].h
 end
+
+gpu_count() = Int(ccall((:smm_ctx_gpu_count, LIB), Cint, (Ptr{Cvoid},), ctx()))
 
 check(rc, what) = rc == 0 || error("$what failed [$rc]: ", unsafe_string(ccall((:smm_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx())))
 
 # ---- ABMsolve (abm.jl:154-217) ---------------------------------------------------------------------
 # Same signature and return value; `precision` is an added keyword (reference behaviour = Float64).
-function ABMsolve(NT = 100; p = ABMconstruct(), q = parameters(), init = "4inf", chosenseed = 0, precision = PREC_F32)
+# Keyword extensions (reference defaults reproduce the reference call): `network = (rowptr, colidx)` a 0-based CSR follower
+# network (row j = the agents i with IndNet[j,i] == 1, abm.jl:51; list j itself to keep the self-loop of abm.jl:42) instead of
+# the all-to-all IndNet; L may be any square number g^2 (influencers initialised on a g x g partition of the domain,
+# generalising abm.jl:21-24); `save_stride` thins the returned history (every save_stride-th step and the last).
+function ABMsolve(NT = 100; p = ABMconstruct(), q = parameters(), init = "4inf", chosenseed = 0, precision = PREC_F32,
+                  network = nothing, save_stride = 1)
     n, L, M = q.n, q.L, q.M
     sp = params(q, p)
     x0 = zeros(n, 2, 1); state = zeros(Int32, n, 1); follow0 = zeros(Int32, n, 1); inf0 = zeros(L, 2, 1); media0 = zeros(M, 2, 1)
     check(ccall((:smm_abm_init, LIB), Cint,
                 (Ptr{Cvoid}, Ref{SmmParams}, UInt64, Int64, Int32, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
                 ctx(), sp, chosenseed, 0, 1, x0, state, follow0, inf0, media0), "smm_abm_init")
-    savesteps = Int32.(0:NT)
-    xs = zeros(n, 2, NT + 1, 1); fol = zeros(Int32, n, NT + 1, 1); infs = zeros(L, 2, NT + 1, 1); meds = zeros(M, 2, NT + 1, 1)
+    savesteps = Int32.(unique(vcat(collect(0:save_stride:NT), NT)))
+    ns = length(savesteps)
+    xs = zeros(n, 2, ns, 1); fol = zeros(Int32, n, ns, 1); infs = zeros(L, 2, NT + 1, 1); meds = zeros(M, 2, NT + 1, 1)
+    rowptr = network === nothing ? Ptr{Int32}(C_NULL) : Int32.(network[1])
+    colidx = network === nothing ? Ptr{Int32}(C_NULL) : Int32.(network[2])
     noise = SmmNoise(0, chosenseed, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)
     check(ccall((:smm_abm_solve, LIB), Cint,
                 (Ptr{Cvoid}, Ref{SmmParams}, Int32, Int32, Int32, Int64,
                  Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ref{SmmNoise},
                  Int32, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
-                ctx(), sp, precision, NT, 1, 0, x0, state, follow0, inf0, media0, C_NULL, C_NULL, noise,
-                NT + 1, savesteps, xs, fol, infs, meds, C_NULL), "smm_abm_solve")
-    xs_l = [xs[:, :, k, 1] for k in 1:NT+1]
-    stateinfs = [Float64.(fol[:, k, 1]) .+ 1.0 for k in 1:NT+1]     # abm.jl:164,212: Float64 ids 1.0..L
-    infs_l = [infs[:, :, k, 1] for k in 1:NT+1]
-    meds_l = [meds[:, :, k, 1] for k in 1:NT+1]
+                ctx(), sp, precision, NT, 1, 0, x0, state, follow0, inf0, media0, rowptr, colidx, noise,
+                ns, savesteps, xs, fol, infs, meds, C_NULL), "smm_abm_solve")
+    xs_l = [xs[:, :, k, 1] for k in 1:ns]
+    stateinfs = [Float64.(fol[:, k, 1]) .+ 1.0 for k in 1:ns]       # abm.jl:164,212: Float64 ids 1.0..L
+    infs_l = [infs[:, :, Int(k) + 1, 1] for k in savesteps]
+    meds_l = [meds[:, :, Int(k) + 1, 1] for k in savesteps]
     return xs_l, stateinfs, infs_l, meds_l, Int.(state[:, 1]), (p, q)
 end
 
 # ---- ABMsolveensemble (ensemble.jl:11-55) -------------------------------------------------------------
+# Keyword extensions (defaults = the reference call): `devices` (see use_devices!), `us_type = Float32` returns the
+# densities as Float32 (smm_abm_ensemble_f32: half the PCIe and host bytes), `want_us = false` returns the ensemble MEANS
+# (av_u, av_z, av_y of plotting.jl:361-363) instead of the per-realization arrays: 1 MB instead of 2 GB.
 function ABMsolveensemble(NT = 200, N = 10; savepoints = 4, init = "4inf", p = ABMconstruct(), q = parameters(),
-                          sigma = 0.1, save = true, precision = PREC_F32)
+                          sigma = 0.1, save = true, precision = PREC_F32, devices = :default, us_type = Float64, want_us = true)
     L = q.L
     g = grid(p)
-    zs = zeros(2, 2, savepoints, N); ys = zeros(2, L, savepoints, N); us = zeros(g.Nx, g.Ny, 2, L, savepoints, N)
+    h = ctx(; devices = devices)
     savesteps = Int32.(Int.(round.(LinRange(1, NT, savepoints))) .- 1)   # ensemble.jl:21, 0-based
     noise = SmmNoise(0, 0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL)
-    check(ccall((:smm_abm_ensemble, LIB), Cint,
-                (Ptr{Cvoid}, Ref{SmmParams}, Int32, Int32, Int32, Int64,
-                 Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ref{SmmNoise},
-                 Int32, Ptr{Int32}, Float64, Ref{SmmGrid},
-                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
-                ctx(), params(q, p), precision, NT, N, 1,                      # realizations k = 1..N (ensemble.jl:25)
-                C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, noise,
-                savepoints, savesteps, sigma, g, us, zs, ys, C_NULL, C_NULL, C_NULL, C_NULL), "smm_abm_ensemble")
+    zs = Array{Float64}(undef, 2, 2, savepoints, N); ys = Array{Float64}(undef, 2, L, savepoints, N)
+    if !want_us
+        su = Array{Float64}(undef, g.Nx, g.Ny, 2, L, savepoints); sz = Array{Float64}(undef, 2, 2, savepoints); sy = Array{Float64}(undef, 2, L, savepoints)
+        check(ccall((:smm_abm_ensemble, LIB), Cint,
+                    (Ptr{Cvoid}, Ref{SmmParams}, Int32, Int32, Int32, Int64,
+                     Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ref{SmmNoise},
+                     Int32, Ptr{Int32}, Float64, Ref{SmmGrid},
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                    h, params(q, p), precision, NT, N, 1, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, noise,
+                    savepoints, savesteps, sigma, g, C_NULL, C_NULL, C_NULL, su, sz, sy, C_NULL), "smm_abm_ensemble")
+        return su ./ N, sz ./ N, sy ./ N, (p, q)
+    end
+    us = Array{us_type}(undef, g.Nx, g.Ny, 2, L, savepoints, N)          # every element is written by the library
+    if us_type === Float32
+        check(ccall((:smm_abm_ensemble_f32, LIB), Cint,
+                    (Ptr{Cvoid}, Ref{SmmParams}, Int32, Int32, Int64,
+                     Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ref{SmmNoise},
+                     Int32, Ptr{Int32}, Float64, Ref{SmmGrid},
+                     Ptr{Float32}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                    h, params(q, p), NT, N, 1, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, noise,
+                    savepoints, savesteps, sigma, g, us, zs, ys, C_NULL, C_NULL, C_NULL, C_NULL), "smm_abm_ensemble_f32")
+    else
+        check(ccall((:smm_abm_ensemble, LIB), Cint,
+                    (Ptr{Cvoid}, Ref{SmmParams}, Int32, Int32, Int32, Int64,
+                     Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ref{SmmNoise},
+                     Int32, Ptr{Int32}, Float64, Ref{SmmGrid},
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                    h, params(q, p), precision, NT, N, 1,                      # realizations k = 1..N (ensemble.jl:25)
+                    C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL, noise,
+                    savepoints, savesteps, sigma, g, us, zs, ys, C_NULL, C_NULL, C_NULL, C_NULL), "smm_abm_ensemble")
+    end
     if save
         us2 = us; zs2 = zs; ys2 = ys; p2 = p; q2 = q
         @eval Main using JLD2
@@ -163,23 +229,26 @@ function PDEsolve(tmax = 0.1; alg = nothing, init = "4inf", p = PDEconstruct(), 
 end
 
 # ---- PDEsolveensemble (ensemble.jl:58-85): all N instances advance as ONE device-resident batch -------
+# Keyword extensions: `qs` = a vector of N parameter sets (the reference runs N identical solves unless init = "random",
+# ensemble.jl:70; with `qs` the call is a parameter sweep, instance k integrates with qs[k]); `devices` as above.
 function PDEsolveensemble(tmax = 0.1, N = 10; savepoints = 4, alg = nothing, init = "4inf", p = PDEconstruct(),
-                          q = parameters(), save = true, dt = nothing, precision = PREC_F32)
-    inits = [constructinitial(init, (p, q)) for _ in 1:N]
+                          q = parameters(), save = true, dt = nothing, precision = PREC_F32, qs = nothing, devices = :default)
+    qs !== nothing && (N = length(qs))
+    inits = [constructinitial(init, (p, qs === nothing ? q : qs[k])) for k in 1:N]
     qa = inits[1][2]; L = qa.L
-    D = 0.5 * q.sigma^2
+    D = maximum(0.5 * i[2].sigma^2 for i in inits)
     dt === nothing && (dt = min(1e-3, 0.16 * p.dx^2 / D))
     per = max(1, ceil(Int, tmax / (savepoints - 1) / dt - 1e-9)); nsteps = per * (savepoints - 1); dt = tmax / nsteps
     savesteps = Int32.((0:savepoints-1) .* per)                       # LinRange(0, tmax, savepoints) (ensemble.jl:65)
     u0 = cat([i[1].x[1] for i in inits]...; dims = 5); z0 = cat([i[1].x[2] for i in inits]...; dims = 3)
     y0 = cat([i[1].x[3] for i in inits]...; dims = 3)
     us = zeros(p.N_x, p.N_y, 2, L, savepoints, N); zs = zeros(2, 2, savepoints, N); ys = zeros(2, L, savepoints, N)
-    ci = repeat(Float64.(collect(qa.controlled_inf)), 1, N); cm = repeat(Float64.(collect(qa.controlled_med)), 1, N)
+    ci = hcat([Float64.(collect(i[2].controlled_inf)) for i in inits]...); cm = hcat([Float64.(collect(i[2].controlled_med)) for i in inits]...)
     check(ccall((:smm_pde_solve, LIB), Cint,
                 (Ptr{Cvoid}, Ref{SmmGrid}, Ptr{SmmParams}, Int32, Int32, Int32, Ptr{Float64}, Ptr{Float64},
                  Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Int32, Int32, Int32, Ptr{Int32},
                  Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                ctx(), grid(p), [params(qa, p) for _ in 1:N], N, L, precision, ci, cm, u0, z0, y0, dt, nsteps, RK4,
+                ctx(; devices = devices), grid(p), [params(i[2], p) for i in inits], N, L, precision, ci, cm, u0, z0, y0, dt, nsteps, RK4,
                 savepoints, savesteps, us, zs, ys, C_NULL, C_NULL, C_NULL), "smm_pde_solve")
     P = (p, qa)
     if save
@@ -213,6 +282,33 @@ function PDEsolveadaptive(tmax = 0.1; init = "4inf", p = PDEconstruct(), q = par
                 us, zs, ys, C_NULL, C_NULL, C_NULL, nacc, nrej), "smm_pde_solve_adaptive")
     states = [ArrayPartition(us[:, :, :, :, m, 1], zs[:, :, m, 1], ys[:, :, m, 1]) for m in 1:ns]
     return FixedStepSolution(times, states), (p, qa)
+end
+
+# ---- one large population kept on the GPU between calls (config C5: n = 1e7 agents, CSR follower network, L = 64) -----
+# Not part of the reference's API (abm.jl:42 builds a dense n x n IndNet and abm.jl:12-13 asserts L == 4): a handle
+# around smm_abm_pop_*.  x0 [n,2], state [n] (+-1), follow0 [n] (0-based), inf0 [L,2], media0 [2,2], network = (rowptr, colidx).
+mutable struct ABMPopulation
+    h::Ptr{Cvoid}
+    n::Int; L::Int
+end
+function ABMPopulation(q, p, x0, state, follow0, inf0, media0, network; seed = 0, precision = PREC_F32)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:smm_abm_pop_create, LIB), Cint,
+                (Ptr{Cvoid}, Ref{SmmParams}, Int32, UInt64, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64},
+                 Ptr{Int32}, Ptr{Int32}, Ref{Ptr{Cvoid}}),
+                ctx(), params(q, p), precision, seed, Float64.(x0), Int32.(state), Int32.(follow0), Float64.(inf0), Float64.(media0),
+                Int32.(network[1]), Int32.(network[2]), out), "smm_abm_pop_create")
+    pop = ABMPopulation(out[], q.n, q.L)
+    finalizer(x -> ccall((:smm_abm_pop_destroy, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), ctx(), x.h), pop)
+    return pop
+end
+step!(pop::ABMPopulation, nsteps = 1) = check(ccall((:smm_abm_pop_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Int32), ctx(), pop.h, nsteps), "smm_abm_pop_step")
+function Base.read(pop::ABMPopulation; positions = true)
+    x = positions ? zeros(pop.n, 2) : zeros(0, 2); follow = zeros(Int32, pop.n); inf = zeros(pop.L, 2); media = zeros(2, 2)
+    numbers = zeros(Int64, 2, pop.L)
+    check(ccall((:smm_abm_pop_read, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}),
+                ctx(), pop.h, positions ? x : C_NULL, follow, inf, media, numbers), "smm_abm_pop_read")
+    return (x = x, follow = follow .+ 1, inf = inf, media = media, numbers = numbers)
 end
 
 end # module
