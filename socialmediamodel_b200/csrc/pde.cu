@@ -724,8 +724,8 @@ __device__ __forceinline__ void stage2_planes(const StageArgs& A, const float* t
   }
 }
 
-template <int LT>
-__global__ void __launch_bounds__(BX* BY, 2) pde_stage2_kernel(const __grid_constant__ StageArgs A) {
+template <int LT, int OCC>
+__global__ void __launch_bounds__(BX* BY, OCC) pde_stage2_kernel(const __grid_constant__ StageArgs A) {
   constexpr int L = LT, NP = 2 * LT;
   const int Nx = A.Nx, Ny = A.Ny, b = blockIdx.z;
   const int bx0 = blockIdx.x * BX2, by0 = blockIdx.y * BY;
@@ -742,25 +742,25 @@ __global__ void __launch_bounds__(BX* BY, 2) pde_stage2_kernel(const __grid_cons
   float* mom0 = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(sFy) + align128(sizeof(float) * TH * BX2));  // [BY][NP][32]
   float* momx = mom0 + BY * NP * 32;
   __shared__ __align__(8) unsigned long long tma_bar;
-  __shared__ double sm[2 * LMAX * 3];
   __shared__ float s_yx[LMAX], s_yy[LMAX], s_R[2][LMAX], s_zx[2], s_zy[2];
   __shared__ float s_par[4];
-  if (tid < L) {
-    s_yx[tid] = (float)A.coef[b].y[tid][0]; s_yy[tid] = (float)A.coef[b].y[tid][1];
-    s_R[0][tid] = (float)A.coef[b].R[0][tid]; s_R[1][tid] = (float)A.coef[b].R[1][tid];
-  }
-  if (tid < 2) { s_zx[tid] = (float)A.coef[b].z[tid][0]; s_zy[tid] = (float)A.coef[b].z[tid][1]; }
+  // the elected thread initialises the barrier and issues the three bulk tensor copies before anything else: their
+  // latency overlaps the loads of the per-instance coefficients and of the step-start state below
   if (tid == 0) {
-    s_par[0] = (float)A.inst[b].a; s_par[1] = (float)A.inst[b].b; s_par[2] = (float)A.inst[b].c; s_par[3] = (float)A.inst[b].D;
     mbar_init(&tma_bar, 1);
-  }
-  __syncthreads();
-  if (tid == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     mbar_expect_tx(&tma_bar, (unsigned)(sizeof(float) * (NP * TH * TW2 + BY * TW2 + TH * BX2)));
     tma_load_3d(tile, &A.tmU, bx0 - XO, by0 - 1, b * NP, &tma_bar);
     tma_load_3d(sFx, &A.tmFx, bx0 - XO, by0, b, &tma_bar);
     tma_load_3d(sFy, &A.tmFy, bx0, by0 - 1, b, &tma_bar);
+    s_par[0] = (float)A.inst[b].a; s_par[1] = (float)A.inst[b].b; s_par[2] = (float)A.inst[b].c; s_par[3] = (float)A.inst[b].D;
   }
+  if (tid >= 32 && tid < 32 + L) {
+    const int j = tid - 32;
+    s_yx[j] = (float)A.coef[b].y[j][0]; s_yy[j] = (float)A.coef[b].y[j][1];
+    s_R[0][j] = (float)A.coef[b].R[0][j]; s_R[1][j] = (float)A.coef[b].R[1][j];
+  }
+  if (tid >= 64 && tid < 66) { s_zx[tid - 64] = (float)A.coef[b].z[tid - 64][0]; s_zy[tid - 64] = (float)A.coef[b].z[tid - 64][1]; }
   const int Pw = A.Pw;
   const size_t plane = (size_t)Pw * Ny;
   const float* un = static_cast<const float*>(A.un) + (size_t)b * NP * plane;
@@ -778,6 +778,7 @@ __global__ void __launch_bounds__(BX* BY, 2) pde_stage2_kernel(const __grid_cons
     unv[p] = need_un ? *reinterpret_cast<const float2*>(un + (size_t)p * plane + o_c) : make_float2(0.f, 0.f);
     accv[p] = need_acc ? *reinterpret_cast<const float2*>(acc + (size_t)p * plane + o_c) : make_float2(0.f, 0.f);
   }
+  __syncthreads();  // coefficients in shared memory; barrier initialisation visible to every waiter
   mbar_wait(&tma_bar, 0);
   const float pa = s_par[0], pb = s_par[1], pc = s_par[2], D = s_par[3];
   const float2 X2 = make_float2((float)(A.gx0 + min(ix, Nx - 1) * A.dx), (float)(A.gx0 + min(ix + 1, Nx - 1) * A.dx));
@@ -815,7 +816,17 @@ __global__ void __launch_bounds__(BX* BY, 2) pde_stage2_kernel(const __grid_cons
       }
     }
   }
-  moments_ticket(A, b, sm, FIN_STAGE);
+  // no last-CTA ticket here: pde_finalize_kernel (one small CTA per instance, next in the stream) reduces the partials
+}
+
+// Reduction of the per-CTA partial moments of pde_stage2_kernel and the ODE update of the instance (what the last CTA of an
+// instance does inside pde_stage_kernel).  A separate launch costs a few microseconds per stage, which large batches do not
+// notice, and takes two barriers, a fence (with its L1 invalidation) and a global atomic round trip out of every tile CTA.
+__global__ void __launch_bounds__(BX* BY) pde_finalize_kernel(StageArgs A, int nblk) {
+  __shared__ double sm[2 * LMAX * 3];
+  pdl_wait();
+  pdl_launch_dependents();
+  finalize_instance(A, blockIdx.x, nblk, FIN_STAGE, sm);
 }
 
 // K6 direct Toeplitz correlation.  CTA = 8x8 output points x NS input slices; wext[ady][d + Nx-1]
@@ -923,7 +934,8 @@ struct smm_pde_batch {
   int nbx, nby;
   bool table_in_smem;
   size_t conv_smem;
-  std::map<std::pair<int, double>, cudaGraphExec_t> graphs;
+  struct StepGraph { cudaGraphExec_t exec; int64_t launches; };
+  std::map<std::pair<int, double>, StepGraph> graphs;  // one RK step per (scheme, dt), with its kernel count
   int64_t steps_taken;
   smm_fft_plan* fft;  // null = direct Toeplitz kernel
   CUtensorMap tm_u, tm_ua, tm_ub, tm_fx, tm_fy;  // TMA descriptors (stage kernel tile loads)
@@ -947,7 +959,7 @@ static void pde_free(smm_pde_batch* pb) {
                   pb->err, pb->errpart, pb->ctl};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (pb->adapt_graph) cudaGraphExecDestroy(pb->adapt_graph);
-  for (auto& g : pb->graphs) cudaGraphExecDestroy(g.second);
+  for (auto& g : pb->graphs) cudaGraphExecDestroy(g.second.exec);
   smm_fft_plan_destroy(pb->fft);
   delete pb;
 }
@@ -995,16 +1007,26 @@ static size_t stage2_smem(int L) {
   return align128(4 * (size_t)2 * L * TH * TW2) + align128(4 * (size_t)BY * TW2) + align128(4 * (size_t)TH * BX2) + 2 * 4 * (size_t)BY * 2 * L * 32;
 }
 
-template <int LT>
-static int launch_stage2_t(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
+template <int LT, int OCC>
+static int launch_stage2_o(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
   dim3 grid(pb->nbx2, pb->nby, pb->B), block(BX, BY);
   const size_t sm = stage2_smem(pb->L);
-  SMM_CUDA(ctx, cudaFuncSetAttribute(pde_stage2_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 48 * 1024)));
+  SMM_CUDA(ctx, cudaFuncSetAttribute(pde_stage2_kernel<LT, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sm, 48 * 1024)));
   static const bool pdl = !(getenv("SMM_PDE_PDL") && getenv("SMM_PDE_PDL")[0] == '0');
-  SMM_CUDA(ctx, smm_launch_pdl(pdl ? ctx->sm_count : 0, pde_stage2_kernel<LT>, grid, block, sm, ctx->stream, A));
+  SMM_CUDA(ctx, smm_launch_pdl(pdl ? ctx->sm_count : 0, pde_stage2_kernel<LT, OCC>, grid, block, sm, ctx->stream, A));
   ctx->launches++;
+  if (A.do_moments) {
+    SMM_CUDA(ctx, smm_launch_pdl(pdl ? ctx->sm_count : 0, pde_finalize_kernel, dim3(pb->B), dim3(BX, BY), 0, ctx->stream, A, pb->nbx2 * pb->nby));
+    ctx->launches++;
+  }
   SMM_CUDA(ctx, cudaGetLastError());
   return SMM_OK;
+}
+template <int LT>
+static int launch_stage2_t(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A) {
+  // resident CTAs per SM: 2 (126 registers, no spills) or 3 (80 registers, ~30 spilled words); SMM_PDE_STAGE2_OCC selects
+  static const int occ = getenv("SMM_PDE_STAGE2_OCC") ? atoi(getenv("SMM_PDE_STAGE2_OCC")) : 3;
+  return occ == 3 ? launch_stage2_o<LT, 3>(ctx, pb, A) : launch_stage2_o<LT, 2>(ctx, pb, A);
 }
 
 static size_t stage_smem(int L, size_t rs) {
@@ -1315,6 +1337,7 @@ extern "C" int smm_pde_batch_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, in
     } else {
       int64_t l0 = ctx->launches;
       int rc = enqueue_step(ctx, pb, dt, scheme);
+      const int64_t captured = ctx->launches - l0;
       ctx->launches = l0;
       cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
       if (rc != SMM_OK) { if (e == cudaSuccess) cudaGraphDestroy(graph); return rc; }
@@ -1322,7 +1345,7 @@ extern "C" int smm_pde_batch_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, in
       cudaGraphExec_t exec;
       SMM_CUDA(ctx, cudaGraphInstantiate(&exec, graph, 0));
       cudaGraphDestroy(graph);
-      it = pb->graphs.emplace(key, exec).first;
+      it = pb->graphs.emplace(key, smm_pde_batch::StepGraph{exec, captured}).first;
     }
   }
   if (!use_graph) {
@@ -1333,11 +1356,10 @@ extern "C" int smm_pde_batch_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, in
     pb->time += dt * nsteps;
     return SMM_OK;
   }
-  const int per_step = (scheme == SMM_RK_EULER ? 1 : scheme == SMM_RK_HEUN ? 2 : scheme == SMM_RK_SSPRK3 ? 3 : 4) * 2;
   smm_tic(ctx, SMM_K_STENCIL);
-  for (int s = 0; s < nsteps; s++) SMM_CUDA(ctx, cudaGraphLaunch(it->second, ctx->stream));
+  for (int s = 0; s < nsteps; s++) SMM_CUDA(ctx, cudaGraphLaunch(it->second.exec, ctx->stream));
   smm_toc(ctx, SMM_K_STENCIL);
-  ctx->launches += (int64_t)per_step * nsteps;
+  ctx->launches += it->second.launches * nsteps;
   pb->steps_taken += nsteps;
   pb->time += dt * nsteps;
   return SMM_OK;
