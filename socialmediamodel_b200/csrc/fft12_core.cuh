@@ -223,21 +223,43 @@ template <int P> F12_HD int pos_r2(int t, int s) { return 2 * (t + Plan<P>::T * 
 // position of slot s after the LAST forward pass (= before the first inverse pass)
 template <int P> F12_HD int pos_last(int t, int s) { return Plan<P>::R2 ? pos_r2<P>(t, s) : pos_r4<P>(t, 1, s); }
 
+// ---- twiddle table, pass-major: every pass reads consecutive entries for consecutive threads --------------------
+//   [0, 11 T)                 radix-12 pass:  entry (k1 - 1) T + t        = exp(-2 pi i t k1 / P),  k1 = 1..11
+//   then per radix-4 pass with quarter distance q > 1 (in pass order):  entry off + (k - 1) q + j = exp(-2 pi i j k / (4 q)), k = 1..3
+template <int P> F12_HD constexpr int tw_r4_offset(int pass) {  // pass = 1..NR4
+  int off = 11 * Plan<P>::T;
+  for (int ps = 1; ps < pass; ps++) { const int q = Plan<P>::T >> (2 * ps); if (q > 1) off += 3 * q; }
+  return off;
+}
+template <int P> F12_HD constexpr int tw_size() { return tw_r4_offset<P>(Plan<P>::NR4 + 1); }
+// exponent of entry e as a fraction num / den of a full turn (for the table generators on host and device)
+template <int P> F12_HD void tw_exponent(int e, int& num, int& den) {
+  constexpr int T = Plan<P>::T;
+  if (e < 11 * T) { const int k1 = e / T + 1, t = e - (k1 - 1) * T; num = t * k1; den = P; return; }
+  for (int ps = 1; ps <= Plan<P>::NR4; ps++) {
+    const int q = T >> (2 * ps);
+    if (q <= 1) continue;
+    const int off = tw_r4_offset<P>(ps);
+    if (e < off + 3 * q) { const int k = (e - off) / q + 1, j = (e - off) - (k - 1) * q; num = j * k; den = 4 * q; return; }
+  }
+  num = 0; den = 1;
+}
+
 // ---- passes on registers -------------------------------------------------------------------------------------
-// tw[j] = exp(-2 pi i j / P), j < P (float2 = (cos, sin)); SGN as above.
+// SGN as above; tw = the pass-major table.
 template <int P, int SGN> F12_HD void twiddle_r12_out(C2 (&a)[12], int t, const float2* tw) {  // a[k1] *= W^(SGN: conj)(t k1)
 #pragma unroll
   for (int k1 = 1; k1 < 12; k1++) {
-    const float2 w = tw[t * k1];  // t k1 < 64 * 11 < P
+    const float2 w = tw[(k1 - 1) * Plan<P>::T + t];
     a[k1] = cmul_s<SGN>(a[k1], w.x, w.y);
   }
 }
 // DIF radix-4 pass on the thread's three butterflies: y_k = (sum_m a_m W4^(mk)) * W_{4q}^(j k)
-template <int P, int SGN> F12_HD void r4_dif(C2 (&a)[12], int t, int q, const float2* tw) {
+template <int P, int SGN> F12_HD void r4_dif(C2 (&a)[12], int t, int pass, const float2* tw) {
+  const int q = Plan<P>::T >> (2 * pass);
   const int j = t & (q - 1);  // T is a multiple of q
-  const int stride = P / (4 * q);
   float2 w1 = make_float2(1.f, 0.f), w2 = w1, w3 = w1;
-  if (q > 1) { w1 = tw[stride * j]; w2 = tw[2 * stride * j]; w3 = tw[3 * stride * j]; }
+  if (q > 1) { const float2* tq = tw + tw_r4_offset<P>(pass) + j; w1 = tq[0]; w2 = tq[q]; w3 = tq[2 * q]; }
 #pragma unroll
   for (int u = 0; u < 3; u++) {
     dft4<SGN>(a[4 * u], a[4 * u + 1], a[4 * u + 2], a[4 * u + 3]);
@@ -249,11 +271,11 @@ template <int P, int SGN> F12_HD void r4_dif(C2 (&a)[12], int t, int q, const fl
   }
 }
 // DIT radix-4 pass (transpose of r4_dif with the opposite sign): twiddle first, then the butterfly
-template <int P, int SGN> F12_HD void r4_dit(C2 (&a)[12], int t, int q, const float2* tw) {
+template <int P, int SGN> F12_HD void r4_dit(C2 (&a)[12], int t, int pass, const float2* tw) {
+  const int q = Plan<P>::T >> (2 * pass);
   const int j = t & (q - 1);
-  const int stride = P / (4 * q);
   float2 w1 = make_float2(1.f, 0.f), w2 = w1, w3 = w1;
-  if (q > 1) { w1 = tw[stride * j]; w2 = tw[2 * stride * j]; w3 = tw[3 * stride * j]; }
+  if (q > 1) { const float2* tq = tw + tw_r4_offset<P>(pass) + j; w1 = tq[0]; w2 = tq[q]; w3 = tq[2 * q]; }
 #pragma unroll
   for (int u = 0; u < 3; u++) {
     if (q > 1) {
@@ -281,21 +303,59 @@ template <int P> F12_HD int pass_pos(int pass, int t, int s) {
 }
 template <int P, int SGN> F12_HD void pass_dif(int pass, C2 (&a)[12], int t, const float2* tw) {
   if (pass == 0) { dft12_dif<SGN>(a); twiddle_r12_out<P, SGN>(a, t, tw); }
-  else if (pass <= Plan<P>::NR4) r4_dif<P, SGN>(a, t, Plan<P>::T >> (2 * pass), tw);
+  else if (pass <= Plan<P>::NR4) r4_dif<P, SGN>(a, t, pass, tw);
   else r2_pass(a);
 }
 template <int P, int SGN> F12_HD void pass_dit(int pass, C2 (&a)[12], int t, const float2* tw) {
   if (pass == 0) { twiddle_r12_out<P, SGN>(a, t, tw); dft12_dit<SGN>(a); }
-  else if (pass <= Plan<P>::NR4) r4_dit<P, SGN>(a, t, Plan<P>::T >> (2 * pass), tw);
+  else if (pass <= Plan<P>::NR4) r4_dit<P, SGN>(a, t, pass, tw);
   else r2_pass(a);
 }
+// Shared-memory word of slot s in a pass = (one of two per-thread bases) + (compile-time offset).  The swizzle bit of a
+// position depends either on thread bits only or on slot bits only in every pass (pos = thread part + slot part, and
+// the two never carry into bits 0..2 of each other), so the XOR of swz() reduces to a choice between the thread part
+// with bit 0 as is / flipped: no per-access address arithmetic (the generic form cost 30 registers of spills).
+// tools/fft12_check.cpp checks slot_word == word(pass_pos) for every thread, slot and pass.
+struct PassAddr { int a, b; };
+template <int P, int PAIRS> F12_HD PassAddr pass_bases(int pass, int t, int p) {
+  constexpr int T = Plan<P>::T, NR4 = Plan<P>::NR4;
+  int tp, fa = 0, fb = 0;
+  if (pass == 0) { tp = t; fa = fb = ((t >> 1) ^ (t >> 2)) & 1; }
+  else if (pass <= NR4) {
+    const int q = T >> (2 * pass);
+    tp = (t / q) * 4 * q + (t & (q - 1));
+    if (q >= 8) fa = fb = ((t >> 1) ^ (t >> 2)) & 1;
+    else if (q == 4) { fa = (t >> 1) & 1; fb = fa ^ 1; }
+    else if (q == 2) { fa = 0; fb = 1; }
+    else { fa = t & 1; fb = fa ^ 1; }      // q == 1: tp = 4 t
+  } else { tp = 2 * t; fa = (t ^ (t >> 1)) & 1; fb = fa ^ 1; }
+  if (PAIRS == 8) fa = fb = 0;
+  return PassAddr{(tp ^ fa) * PAIRS + p, (tp ^ fb) * PAIRS + p};
+}
+template <int P, int PAIRS> F12_HD int slot_word(int pass, int s, PassAddr ad) {
+  constexpr int T = Plan<P>::T, NR4 = Plan<P>::NR4;
+  if (pass == 0) return ad.a + T * s * PAIRS;
+  if (pass <= NR4) {
+    const int q = T >> (2 * pass), u = s >> 2, m = s & 3, cp = 4 * T * u + q * m;
+    if (PAIRS == 8 || q >= 8) return ad.a + cp * PAIRS;
+    if (q == 4) return ((m & 1) ? ad.b : ad.a) + cp * PAIRS;
+    if (q == 2) return ((((m & 1) ^ (m >> 1)) & 1) ? ad.b : ad.a) + cp * PAIRS;
+    // q == 1: positions tp + 4 T u + (m ^ s), s = (m >> 1) ^ (t & 1): m = 0 -> A, 1 -> B, 2 -> B + 2, 3 -> A + 2
+    return ((m == 0 || m == 3) ? ad.a : ad.b) + (4 * T * u + (m & 2)) * PAIRS;
+  }
+  const int u = s >> 1, m = s & 1;
+  if (PAIRS == 8) return ad.a + (2 * T * u + m) * PAIRS;
+  return (m ? ad.b : ad.a) + 2 * T * u * PAIRS;
+}
 template <int P, int PAIRS> F12_HD void store_pass(int pass, const C2 (&a)[12], int t, int p, float4* buf) {
+  const PassAddr ad = pass_bases<P, PAIRS>(pass, t, p);
 #pragma unroll
-  for (int s = 0; s < 12; s++) buf[word<PAIRS>(pass_pos<P>(pass, t, s), p)] = pack(a[s]);
+  for (int s = 0; s < 12; s++) buf[slot_word<P, PAIRS>(pass, s, ad)] = pack(a[s]);
 }
 template <int P, int PAIRS> F12_HD void load_pass(int pass, C2 (&a)[12], int t, int p, const float4* buf) {
+  const PassAddr ad = pass_bases<P, PAIRS>(pass, t, p);
 #pragma unroll
-  for (int s = 0; s < 12; s++) a[s] = unpack(buf[word<PAIRS>(pass_pos<P>(pass, t, s), p)]);
+  for (int s = 0; s < 12; s++) a[s] = unpack(buf[slot_word<P, PAIRS>(pass, s, ad)]);
 }
 
 }  // namespace f12

@@ -9,7 +9,7 @@
 //   fast_cols      CTA = 2 PAIRS adjacent spectrum columns of one instance; forward transform, the spectrum stays in
 //                  registers, and for each of the three kernel spectra: scale (the spectra of the even / odd kernel
 //                  images are purely real / purely imaginary: one real factor per point), transposed inverse whose
-//                  first pass is thread-local, rows iy < Ny stored from registers            A -> G[k][row][kx]
+//                  first pass is thread-local, rows iy < Ny stored from registers   A -> G[k][row quad][kx][row mod 4]
 //   fast_rows_inv  CTA = 4 PAIRS grid rows; Hermitian extension while loading pass-1 operands, inverse in
 //                  decimation-in-frequency form (digit-reversed output read back through a position table), k = 0 first
 //                  so that 1/(w*rho) waits in registers for the two force components            G -> Fx, Fy
@@ -71,7 +71,7 @@ __device__ __forceinline__ void transform(C2 (&a)[12], int t, int p, const Smem<
 template <int P, int PAIRS>
 __device__ __forceinline__ void load_tables(const Smem<P, PAIRS>& sm, const float2* __restrict__ twg, bool want_postab) {
   for (int i = threadIdx.x; i < P; i += Cfg<P, PAIRS>::THREADS) {
-    sm.tw[i] = twg[i];
+    if (i < tw_size<P>()) sm.tw[i] = twg[i];
     if (want_postab) sm.postab[i] = (unsigned short)pos_of_freq<P>(i);
   }
 }
@@ -160,11 +160,17 @@ fast_cols(int Ny, int kxp, int ngroups, const float2* __restrict__ A, const floa
       else w[s] = C2{pmul(r[s].im, make_float2(-h.x, -h.y)), pmul(r[s].re, h)};
     }
     transform<P, PAIRS, +1, true>(w, t, p, sm, x);  // natural order: w[e] <-> iy = t + T e
-    float2* Gb = G + (size_t)k * gstride + (size_t)b * Ny * kxp + col;
+    // G[k][row quad][kx][row mod 4]: the four rows a thread of fast_rows_inv combines sit in one 32-byte sector
+    float2* Gk = G + (size_t)k * gstride;
 #pragma unroll
     for (int e = 0; e < 12; e++) {
       const int iy = t + C::T * e;
-      if (iy < Ny) *reinterpret_cast<float4*>(Gb + (size_t)iy * kxp) = make_float4(w[e].re.x, w[e].im.x, w[e].re.y, w[e].im.y);
+      if (iy < Ny) {
+        const size_t r = (size_t)b * Ny + iy;
+        float2* o = Gk + ((r >> 2) * kxp + col) * 4 + (r & 3);
+        o[0] = make_float2(w[e].re.x, w[e].im.x);
+        o[4] = make_float2(w[e].re.y, w[e].im.y);
+      }
     }
   }
 }
@@ -199,8 +205,12 @@ fast_rows_inv(int nrows, int Nx, int Pw, int kxp, const float2* __restrict__ G, 
       const int src = up ? P - kx : kx;
       const float sg = up ? -1.f : 1.f;
       float2 g4[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) g4[j] = ok[j] ? Gk[(size_t)(r0 + j) * kxp + src] : make_float2(0.f, 0.f);
+      {  // the block's rows are quad-aligned (r0 = 4 (block PAIRS + p)): two 16-byte loads fetch the four rows at column src
+        const float4* q4 = reinterpret_cast<const float4*>(Gk + ((size_t)(r0 >> 2) * kxp + src) * 4);
+        const float4 lo = ok[0] ? q4[0] : make_float4(0.f, 0.f, 0.f, 0.f), hi = ok[2] ? q4[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        g4[0] = make_float2(lo.x, lo.y); g4[1] = ok[1] ? make_float2(lo.z, lo.w) : make_float2(0.f, 0.f);
+        g4[2] = make_float2(hi.x, hi.y); g4[3] = ok[3] ? make_float2(hi.z, hi.w) : make_float2(0.f, 0.f);
+      }
       // rows (0, 1) -> transform .x, rows (2, 3) -> transform .y;  S = A + i B with A, B conjugated when `up`
       a[e] = C2{make_float2(g4[0].x - sg * g4[1].y, g4[2].x - sg * g4[3].y), make_float2(sg * g4[0].y + g4[1].x, sg * g4[2].y + g4[3].x)};
     }
@@ -252,12 +262,15 @@ __global__ void fast_hk_kernel(int hp1, int cols, int ngroups, const double2* __
   }
 }
 
-__global__ void fast_tw_kernel(int P, float2* tw) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= P) return;
+template <int P>
+__global__ void fast_tw_kernel(float2* tw) {  // pass-major twiddle table (fft12_core.cuh)
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P) return;
+  int num = 0, den = 1;
+  if (e < tw_size<P>()) tw_exponent<P>(e, num, den);
   double s, c;
-  sincospi(-2.0 * (double)j / (double)P, &s, &c);
-  tw[j] = make_float2((float)c, (float)s);
+  sincospi(-2.0 * (double)num / (double)den, &s, &c);
+  tw[e] = make_float2((float)c, (float)s);
 }
 
 }  // namespace
@@ -297,7 +310,7 @@ static int fast_launch(smm_ctx* ctx, smm_fft_fast* f, const float* rho, float* F
     const int bc = std::min(f->chunk, f->B - b0);
     const int nrows = bc * f->Ny;
     const size_t off = (size_t)b0 * f->Ny * f->Pw;
-    const size_t gstride = (size_t)f->chunk * f->Ny * f->kxp;
+    const size_t gstride = (((size_t)f->chunk * f->Ny + 3) & ~(size_t)3) * f->kxp;
     const dim3 rgrid((nrows + C::ROWS - 1) / C::ROWS);
     SMM_CUDA(ctx, smm_launch_pdl(sms, fast_rows_fwd<P, PAIRS>, rgrid, dim3(C::THREADS), C::SMEM, ctx->stream, nrows, f->Nx, f->Pw, f->kxp,
                                  rho + off, f->a, (const float2*)f->tw));
@@ -355,7 +368,7 @@ int smm_fft_fast_create(smm_ctx* ctx, int P, int Nx, int Ny, int Pw, int B, cons
     if (const char* ev = getenv("SMM_FFT_CHUNK_MB"))
       f->chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, ((size_t)std::max(1, atoi(ev)) << 20) / per_inst));
   }
-  const size_t arow = (size_t)f->chunk * Ny * f->kxp;
+  const size_t arow = (((size_t)f->chunk * Ny + 3) & ~(size_t)3) * f->kxp;  // rows rounded up to whole quads (G layout)
 #define FF_CUDA(expr)                                                                                                   \
   do {                                                                                                                  \
     cudaError_t e__ = (expr);                                                                                           \
@@ -374,7 +387,12 @@ int smm_fft_fast_create(smm_ctx* ctx, int P, int Nx, int Ny, int Pw, int B, cons
   double* resid = nullptr;
   FF_CUDA(cudaMalloc((void**)&resid, sizeof(double)));
   cudaMemsetAsync(resid, 0, sizeof(double), ctx->stream);
-  fast_tw_kernel<<<(P + 255) / 256, 256, 0, ctx->stream>>>(P, f->tw);
+  switch (P) {
+    case 96: fast_tw_kernel<96><<<(P + 255) / 256, 256, 0, ctx->stream>>>(f->tw); break;
+    case 192: fast_tw_kernel<192><<<(P + 255) / 256, 256, 0, ctx->stream>>>(f->tw); break;
+    case 384: fast_tw_kernel<384><<<(P + 255) / 256, 256, 0, ctx->stream>>>(f->tw); break;
+    default: fast_tw_kernel<768><<<(P + 255) / 256, 256, 0, ctx->stream>>>(f->tw); break;
+  }
   const size_t total = (size_t)3 * f->ngroups * P * cols;
   const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)ctx->sm_count * 8);
   switch (P) {

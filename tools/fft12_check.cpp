@@ -28,10 +28,34 @@ static void account(const std::vector<int>& words) {
   }
 }
 
+template <int P> static std::vector<float2> make_tw() {  // the pass-major table, as fast_tw_kernel builds it on the device
+  std::vector<float2> tw(tw_size<P>());
+  for (int e = 0; e < (int)tw.size(); e++) {
+    int num, den;
+    tw_exponent<P>(e, num, den);
+    tw[e] = make_float2((float)cos(-2 * M_PI * num / den), (float)sin(-2 * M_PI * num / den));
+  }
+  return tw;
+}
+
+// closed-form shared-memory words == the generic swizzle of the positions, for every thread, slot and pass
+template <int P, int PAIRS> static int check_slot_words() {
+  constexpr int T = Plan<P>::T, NEX = Plan<P>::NEX;
+  int bad = 0;
+  for (int pass = 0; pass <= NEX; pass++)
+    for (int t = 0; t < T; t++)
+      for (int p = 0; p < PAIRS; p++) {
+        const PassAddr ad = pass_bases<P, PAIRS>(pass, t, p);
+        for (int s = 0; s < 12; s++)
+          if (slot_word<P, PAIRS>(pass, s, ad) != word<PAIRS>(pass_pos<P>(pass, t, s), p)) bad++;
+      }
+  if (bad) printf("P=%d PAIRS=%d: %d closed-form addresses differ from the generic swizzle\n", P, PAIRS, bad);
+  return bad;
+}
+
 template <int P, int PAIRS> static double run(bool inverse_dit) {
   constexpr int T = Plan<P>::T, NEX = Plan<P>::NEX, NT = T * PAIRS;
-  std::vector<float2> tw(P);
-  for (int j = 0; j < P; j++) tw[j] = make_float2((float)cos(-2 * M_PI * j / P), (float)sin(-2 * M_PI * j / P));
+  std::vector<float2> tw = make_tw<P>();
   // input: 2 * PAIRS independent sequences
   std::vector<std::vector<cd>> x(2 * PAIRS, std::vector<cd>(P));
   srand(1 + P + PAIRS);
@@ -124,8 +148,7 @@ template <int P, int PAIRS> static double run(bool inverse_dit) {
 // inverse in DIF form (rows_inv): natural in -> permuted out with SGN = +1
 template <int P, int PAIRS> static double run_dif_inv() {
   constexpr int T = Plan<P>::T, NEX = Plan<P>::NEX, NT = T * PAIRS;
-  std::vector<float2> tw(P);
-  for (int j = 0; j < P; j++) tw[j] = make_float2((float)cos(-2 * M_PI * j / P), (float)sin(-2 * M_PI * j / P));
+  std::vector<float2> tw = make_tw<P>();
   std::vector<cd> x(P);
   srand(7 + P);
   for (auto& e : x) e = cd(rand() / (double)RAND_MAX - 0.5, rand() / (double)RAND_MAX - 0.5);
@@ -161,6 +184,7 @@ template <int P, int PAIRS> static double run_dif_inv() {
 
 template <int P, int PAIRS> static int check() {
   g_conflicts = g_wavefronts = 0;
+  if (check_slot_words<P, PAIRS>()) return 1;
   const double e1 = run<P, PAIRS>(false), e2 = run<P, PAIRS>(true), e3 = run_dif_inv<P, PAIRS>();
   const double scale = sqrt((double)P);  // rms magnitude of the spectrum of O(1) inputs
   printf("P=%4d PAIRS=%d: fwd err %.2e  inv(DIT) err %.2e  inv(DIF) err %.2e  (scale %.1f)  bank conflicts %ld / %ld wavefronts\n", P, PAIRS, e1, e2, e3,
