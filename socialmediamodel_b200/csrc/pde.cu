@@ -101,7 +101,7 @@ __device__ __forceinline__ double r_fun(double x) { return x > 0.1 ? x : 0.1; } 
 // unknowns by the stage formula, and produce the coefficients of the next right-hand side.
 __device__ void adaptive_controller(const StageArgs& A, int b, int nblk, const double* s_err);
 
-__device__ void finalize_instance(const StageArgs& A, int b, int nblk, int mode, double* sm /* [2L][3] */) {
+__device__ void finalize_instance(const StageArgs& A, int b, int nblk, int mode, double* sm /* [2L][3] */, const double* presum = nullptr) {
   const int L = A.L, tid = threadIdx.y * blockDim.x + threadIdx.x;
   const double dV = A.dx * A.dy;
   PdeCoef& cf = A.coef[b];
@@ -112,8 +112,11 @@ __device__ void finalize_instance(const StageArgs& A, int b, int nblk, int mode,
   __shared__ double s_err[LMAX + 2];  // adaptive: scaled squared error of each ODE unknown pair
   if (tid < 2 * L * 3) {
     double s = 0.0;
-    const double* p = A.partials + ((size_t)b * nblk) * (2 * L * 3) + tid;
-    for (int k = 0; k < nblk; k++) s += p[(size_t)k * (2 * L * 3)];
+    if (presum) s = presum[tid];  // already reduced over the CTAs (pde_finalize_kernel)
+    else {
+      const double* p = A.partials + ((size_t)b * nblk) * (2 * L * 3) + tid;
+      for (int k = 0; k < nblk; k++) s += p[(size_t)k * (2 * L * 3)];
+    }
     sm[tid] = s * dV;  // plane index = j*2+i; entries (mass, x-moment, y-moment)
   }
   __syncthreads();
@@ -824,9 +827,30 @@ __global__ void __launch_bounds__(BX* BY, OCC) pde_stage2_kernel(const __grid_co
 // notice, and takes two barriers, a fence (with its L1 invalidation) and a global atomic round trip out of every tile CTA.
 __global__ void __launch_bounds__(BX* BY) pde_finalize_kernel(StageArgs A, int nblk) {
   __shared__ double sm[2 * LMAX * 3];
+  __shared__ double part[8][2 * LMAX * 3];
+  __shared__ double pre[2 * LMAX * 3];
   pdl_wait();
   pdl_launch_dependents();
-  finalize_instance(A, blockIdx.x, nblk, FIN_STAGE, sm);
+  // partial moments of the instance's CTAs: 8 interleaved slices summed by independent threads (the loads overlap: one
+  // thread per value walking all CTAs serially took 24 us at 270 CTAs), then added in a fixed order (deterministic)
+  const int nv = 2 * A.L * 3, b = blockIdx.x, tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const int v = tid % 32, slice = tid / 32;  // 8 warps = 8 slices, lane = value (nv <= 32 for L <= 5; looped otherwise)
+  for (int v0 = 0; v0 < nv; v0 += 32) {
+    if (v0 + v < nv) {
+      double s = 0.0;
+      const double* p = A.partials + ((size_t)b * nblk) * nv + v0 + v;
+      for (int k = slice; k < nblk; k += 8) s += p[(size_t)k * nv];
+      part[slice][v0 + v] = s;
+    }
+  }
+  __syncthreads();
+  if (tid < nv) {
+    double s = 0.0;
+    for (int sl = 0; sl < 8; sl++) s += part[sl][tid];
+    pre[tid] = s;
+  }
+  __syncthreads();
+  finalize_instance(A, b, nblk, FIN_STAGE, sm, pre);
 }
 
 // K6 direct Toeplitz correlation.  CTA = 8x8 output points x NS input slices; wext[ady][d + Nx-1]
