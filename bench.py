@@ -623,8 +623,16 @@ def main():
             attempt("abm_population_C5", lambda: run_abm_pop(args, ctx))
             attempt(None, lambda: run_pde_workloads(ctx))
         else:
+            # rank 0 drives every GPU of the job from one process; the other ranks must leave their GPUs idle meanwhile.
+            # They wait on a gloo (CPU) barrier: an NCCL barrier would park a spinning kernel on their GPU and the two
+            # processes' contexts would time-slice it with the measured work
+            import torch
+            import torch.distributed as dist
+            cpu_group = dist.new_group(backend="gloo")
             barrier(world)
+            torch.cuda.synchronize()
             attempt("abm_C2_one_call", lambda: abm_one_call_multi_gpu(args, ens, world), everyone=False)
+            dist.barrier(group=cpu_group)
         res["workloads"] = extra
         res["cpu_baseline"] = cpu
     if world > 1:
