@@ -291,8 +291,10 @@ def rk_solve(u0, z0, y0, nsteps, dt, p, q, ci=None, cm=None, scheme="rk4", save_
     return (u, z, y) if not save_every else saved
 
 
-def adaptive_solve(u0, z0, y0, tmax, p, q, ci=None, cm=None, rtol=1e-8, atol=1e-10):
-    """Tight-tolerance adaptive reference (SciPy DOP853) to show the fixed step is converged."""
+def adaptive_solve(u0, z0, y0, tmax, p, q, ci=None, cm=None, rtol=1e-8, atol=1e-10, method="DOP853", stats=None):
+    """Independent adaptive integrators on the oracle right-hand side (SciPy): DOP853 at a tight tolerance shows that a
+    fixed step is converged; method="RK23" is SciPy's own Bogacki-Shampine 3(2) pair (4 stages, FSAL, its own step
+    controller) -- an implementation of the same family that shares no code or controller with csrc/pde.cu."""
     from scipy.integrate import solve_ivp
     shp = u0.shape
     nu = u0.size
@@ -303,7 +305,9 @@ def adaptive_solve(u0, z0, y0, tmax, p, q, ci=None, cm=None, rtol=1e-8, atol=1e-
         return np.concatenate([du.ravel(), dz.ravel(), dy.ravel()])
 
     v0 = np.concatenate([u0.ravel(), z0.ravel(), y0.ravel()])
-    sol = solve_ivp(fun, (0, tmax), v0, method="DOP853", rtol=rtol, atol=atol)
+    sol = solve_ivp(fun, (0, tmax), v0, method=method, rtol=rtol, atol=atol)
+    if stats is not None:
+        stats.update(nfev=int(sol.nfev), steps=int(sol.t.size - 1))
     v = sol.y[:, -1]
     return v[:nu].reshape(shp), v[nu:nu + 4].reshape(2, 2), v[nu + 4:].reshape(2, shp[3])
 

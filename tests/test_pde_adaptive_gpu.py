@@ -76,6 +76,27 @@ def test_adaptive_solution_converges_to_fine_fixed_step(coarse):
     assert work[0] <= work[1] <= work[2], work
 
 
+def test_adaptive_against_independent_integrators(coarse):
+    """Not circular: the device integrator against two integrators it shares nothing with -- SciPy's RK23 (the standard
+    4-stage FSAL Bogacki-Shampine pair with SciPy's controller) at the same tolerances, and DOP853 at a tight tolerance
+    as the truth -- all on the Float64 oracle right-hand side.  Same tolerance semantics as the reference's
+    solve(..., abstol, reltol) calls (pde.jl:291, controlstrategies.jl:10,96): the error of our solution is of the order of
+    the requested tolerance and no worse than a few times RK23's, at a comparable number of right-hand-side evaluations."""
+    p, q, uzy0 = coarse
+    po, qo = oracle_p(p), dict(q)
+    T = 0.03
+    truth = P.adaptive_solve(*uzy0.x, T, po, qo, rtol=1e-7, atol=1e-10)[0]
+    st = {}
+    rk23 = P.adaptive_solve(*uzy0.x, T, po, qo, rtol=1e-3, atol=1e-6, method="RK23", stats=st)[0]
+    out = smm.pde_solve_adaptive_raw(p, [q], *uzy0.x, savetimes=[T], abstol=1e-6, reltol=1e-3, precision="f64")
+    ours = out["us"][..., 0, 0]
+    e_ours, e_rk23 = rel(ours, truth), rel(rk23, truth)
+    assert e_ours < 5e-3 and e_rk23 < 1e-2, (e_ours, e_rk23)   # measured: 2.3e-4 (72 evaluations) and 4.1e-3 (29)
+    assert e_ours < 5 * max(e_rk23, 2e-4), (e_ours, e_rk23)
+    evals = 3 * int(out["naccept"][0] + out["nreject"][0])
+    assert evals <= 2 * st["nfev"] + 30, (evals, st)
+
+
 def test_adaptive_per_instance_step_control(coarse):
     """Instances of one batch choose their own steps: each reproduces its solo run, and the step counts
     differ between the instances."""
