@@ -110,14 +110,30 @@ __device__ void finalize_instance(const StageArgs& A, int b, int nblk, int mode,
   const bool adaptive = A.ctl != nullptr;
   const double dt = adaptive ? A.ctl[b].dt_try : A.dt;
   __shared__ double s_err[LMAX + 2];  // adaptive: scaled squared error of each ODE unknown pair
-  if (tid < 2 * L * 3) {
-    double s = 0.0;
-    if (presum) s = presum[tid];  // already reduced over the CTAs (pde_finalize_kernel)
-    else {
-      const double* p = A.partials + ((size_t)b * nblk) * (2 * L * 3) + tid;
-      for (int k = 0; k < nblk; k++) s += p[(size_t)k * (2 * L * 3)];
+  // Partial moments of the instance's CTAs.  Eight interleaved slices are summed by different warps (independent loads in
+  // flight: one thread per value walking all CTAs was ~10 us of dependent L2 round trips on the critical path of every stage
+  // of a single 89 x 89 instance) and then added in a fixed order: deterministic.
+  __shared__ double s_part[8][2 * LMAX * 3];
+  const int nv = 2 * L * 3, nthr = blockDim.x * blockDim.y;
+  if (!presum) {
+    const int nsl = nthr >= 256 ? 8 : 1, lanes = nthr / nsl;
+    const int v = tid % lanes, slice = tid / lanes;
+    for (int v0 = 0; v0 < nv; v0 += lanes) {
+      if (v0 + v < nv && slice < nsl) {
+        double s = 0.0;
+        const double* p = A.partials + ((size_t)b * nblk) * nv + v0 + v;
+        for (int k = slice; k < nblk; k += nsl) s += p[(size_t)k * nv];
+        s_part[slice][v0 + v] = s;
+      }
     }
-    sm[tid] = s * dV;  // plane index = j*2+i; entries (mass, x-moment, y-moment)
+    __syncthreads();
+    if (tid < nv) {
+      double s = 0.0;
+      for (int sl = 0; sl < nsl; sl++) s += s_part[sl][tid];
+      sm[tid] = s * dV;  // plane index = j*2+i; entries (mass, x-moment, y-moment)
+    }
+  } else if (tid < nv) {
+    sm[tid] = presum[tid] * dV;  // already reduced over the CTAs (pde_finalize_kernel)
   }
   __syncthreads();
   if (tid < L + 2) {

@@ -20,6 +20,9 @@ def main(which):
     elif which == "pde_sweep353":
         import bench_pde
         print(bench_pde.run_pde_sweep(ctx, dx=0.0125, B=16, steps=2))
+    elif which == "pde_sweep353x64":
+        import bench_pde
+        print(bench_pde.run_pde_sweep(ctx, dx=0.0125, B=64, steps=2))
     elif which == "pop_long":
         import bench
         print(bench.run_abm_pop(None, ctx, n=10_000_000, steps=20, warmup=3))
