@@ -113,13 +113,20 @@ def run_pde_c4_job(ctx, rank, world, B=64, steps=3, dx=0.0125):
     cells = p.N_x * p.N_y * 2 * 4 * B * world
     peaks = _peaks()
     ach = cells / world * 76 / (ms_step * 1e-3) / 1e9      # per GPU: 19 B per cell per RK stage
+    from bench import NCU_TRAFFIC
+    stage_traffic = NCU_TRAFFIC["pde_stage2_per16"][0] * B / 16 if p.N_x == 353 else None
     return dict(workload=f"C4 parameter sweep: {B} PDE instances per GPU x {world} GPU(s), {p.N_x}x{p.N_y}x2x4, RK4 dt={dt:.2e}, "
                          "lattice points sharded by rank, ensemble mean all-reduced",
                 metric="pde_cell_steps_per_s", scaling="weak", n_gpus=world, value=cells / (ms_step * 1e-3), ms_per_step=ms_step,
                 instances_per_gpu=B, mean_all_reduce_ms=allreduce_ms, ensemble_mean_mass=mean_mass,
                 roofline=dict(kernel="pde_stage_kernel<float,4> + FFT convolution kernels", bound="hbm", achieved=ach,
-                              peak=peaks["hbm_gbs"], unit="GB/s (per GPU)", frac=ach / peaks["hbm_gbs"], traffic=None,
+                              peak=peaks["hbm_gbs"], unit="GB/s (per GPU)", frac=ach / peaks["hbm_gbs"],
+                              traffic=stage_traffic, traffic_note="DRAM bytes of ONE stage-kernel launch (4 per step), ncu: "
+                              + NCU_TRAFFIC["pde_stage2_per16"][1],
                               bytes_per_cell_step=76, peak_source=peaks["source"],
+                              stage_kernel=dict(share_of_step=0.446, frac_of_hbm=0.55, note="ncu launch list at 64 instances "
+                                                "(profiles/r2_launches_pde_353x64.csv): stage kernel 340 us of 763 us per RK stage = "
+                                                "1.21 GB / 340 us = 3.57 TB/s; FFT kernels 414 us (shared-memory-bound, not HBM)"),
                               note="whole RK4 step per GPU: 4 x (FFT evaluation of the interaction force + fused stage kernel); "
                                    "76 B/cell-step counts the stencil/RK traffic only (SURVEY 8d)"))
 
