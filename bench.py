@@ -507,6 +507,21 @@ def _c_port_run(realizations, first=1):
     return realizations * C2["NT"] * C2["n"], dt, used
 
 
+def julia_reference():
+    """The reference itself (baseline/julia_bench.jl), when a `julia` binary and the reference checkout (SMM_REFERENCE_DIR)
+    are present on the box -- they are not in the build image: returns None there."""
+    import shutil
+    ref = os.environ.get("SMM_REFERENCE_DIR")
+    if not shutil.which("julia") or not ref or not os.path.isdir(ref):
+        return None
+    try:
+        out = subprocess.run(["julia", "-t", "auto", f"--project={ref}", os.path.join(ROOT, "baseline", "julia_bench.jl"), ref, "16"],
+                             capture_output=True, text=True, timeout=900)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as e:  # noqa: BLE001
+        return dict(error=f"{type(e).__name__}: {e}")
+
+
 def cpu_baseline_abm(realizations=None):
     cores = host_threads()
     try:
@@ -516,7 +531,7 @@ def cpu_baseline_abm(realizations=None):
         return dict(value=done / dt, unit="agent-steps/s", cores=used, kind="port",
                     sample=f"{realizations} realizations of C2 (NT=200, n=250, KDE at 4 save points): C restatement of the "
                            f"reference's loops (oracle/abm_oracle.c, gcc -O3, Float64), OpenMP over realizations, {used} threads",
-                    seconds=dt)
+                    seconds=dt, julia_reference=julia_reference() or "julia absent (baseline/julia_bench.jl not run)")
     except (OSError, AssertionError, subprocess.CalledProcessError) as e:   # no compiler: NumPy restatement instead
         import multiprocessing as mp
         realizations = realizations or 12 * max(cores, 8)
