@@ -79,19 +79,23 @@ __device__ __forceinline__ void load_tables(const Smem<P, PAIRS>& sm, const floa
 // ---- rows forward ----------------------------------------------------------------------------------------------
 template <int P, int PAIRS>
 __global__ void __launch_bounds__(Cfg<P, PAIRS>::THREADS, Cfg<P, PAIRS>::MINB)
-fast_rows_fwd(int nrows, int Nx, int Pw, int kxp, const float* __restrict__ rho, float2* __restrict__ A, const float2* __restrict__ twg) {
+fast_rows_fwd(int nrows, int Ny, int Nyp, int Nx, int Pw, int kxp, const float* __restrict__ rho, float2* __restrict__ A, const float2* __restrict__ twg) {
   using C = Cfg<P, PAIRS>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Smem<P, PAIRS> sm(smem_raw);
   const int tid = threadIdx.x, p = tid % PAIRS, t = tid / PAIRS;
+  // virtual rows: every instance owns Nyp = Ny rounded up to 4 rows, so that the four rows of a thread (two packed
+  // transforms of two real rows each) always belong to ONE instance: an instance's result does not depend on what else
+  // is in the batch, bit for bit
   const int r0 = blockIdx.x * C::ROWS + 4 * p;
+  const int inst = r0 / Nyp, iy0 = r0 - inst * Nyp;
   load_tables<P, PAIRS>(sm, twg, true);
   pdl_wait();
   pdl_launch_dependents();
   const float* row[4];
   bool ok[4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) { ok[j] = r0 + j < nrows; row[j] = rho + (size_t)(ok[j] ? r0 + j : 0) * Pw; }
+  for (int j = 0; j < 4; j++) { ok[j] = r0 + j < nrows && iy0 + j < Ny; row[j] = rho + (size_t)(ok[j] ? inst * Ny + iy0 + j : 0) * Pw; }
   C2 a[12];
 #pragma unroll
   for (int e = 0; e < 12; e++) {
@@ -126,7 +130,7 @@ fast_rows_fwd(int nrows, int Nx, int Pw, int kxp, const float* __restrict__ rho,
 // ---- columns: forward, x 3 kernel spectra, inverse --------------------------------------------------------------
 template <int P, int PAIRS>
 __global__ void __launch_bounds__(Cfg<P, PAIRS>::THREADS, Cfg<P, PAIRS>::MINB)
-fast_cols(int Ny, int kxp, int ngroups, const float2* __restrict__ A, const float* __restrict__ hk, float2* __restrict__ G, size_t gstride,
+fast_cols(int Ny, int Nyp, int kxp, int ngroups, const float2* __restrict__ A, const float* __restrict__ hk, float2* __restrict__ G, size_t gstride,
           const float2* __restrict__ twg) {
   using C = Cfg<P, PAIRS>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -137,7 +141,7 @@ fast_cols(int Ny, int kxp, int ngroups, const float2* __restrict__ A, const floa
   pdl_wait();
   pdl_launch_dependents();
   const size_t col = (size_t)g * C::COLS + 2 * p;               // first of this thread's two columns
-  const float2* Ab = A + (size_t)b * Ny * kxp + col;
+  const float2* Ab = A + (size_t)b * Nyp * kxp + col;
   C2 r[12];
 #pragma unroll
   for (int e = 0; e < 12; e++) {
@@ -166,7 +170,7 @@ fast_cols(int Ny, int kxp, int ngroups, const float2* __restrict__ A, const floa
     for (int e = 0; e < 12; e++) {
       const int iy = t + C::T * e;
       if (iy < Ny) {
-        const size_t r = (size_t)b * Ny + iy;
+        const size_t r = (size_t)b * Nyp + iy;
         float2* o = Gk + ((r >> 2) * kxp + col) * 4 + (r & 3);
         o[0] = make_float2(w[e].re.x, w[e].im.x);
         o[4] = make_float2(w[e].re.y, w[e].im.y);
@@ -178,19 +182,21 @@ fast_cols(int Ny, int kxp, int ngroups, const float2* __restrict__ A, const floa
 // ---- rows inverse + division -------------------------------------------------------------------------------------
 template <int P, int PAIRS>
 __global__ void __launch_bounds__(Cfg<P, PAIRS>::THREADS, Cfg<P, PAIRS>::MINB)
-fast_rows_inv(int nrows, int Nx, int Pw, int kxp, const float2* __restrict__ G, size_t gstride, float* __restrict__ Fx, float* __restrict__ Fy,
-              const float2* __restrict__ twg) {
+fast_rows_inv(int nrows, int Ny, int Nyp, int Nx, int Pw, int kxp, const float2* __restrict__ G, size_t gstride, float* __restrict__ Fx,
+              float* __restrict__ Fy, const float2* __restrict__ twg) {
   using C = Cfg<P, PAIRS>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Smem<P, PAIRS> sm(smem_raw);
   const int tid = threadIdx.x, p = tid % PAIRS, t = tid / PAIRS;
-  const int r0 = blockIdx.x * C::ROWS + 4 * p;
+  const int r0 = blockIdx.x * C::ROWS + 4 * p;        // virtual row (see fast_rows_fwd): a whole quad of one instance
+  const int inst = r0 / Nyp, iy0 = r0 - inst * Nyp;
+  const size_t frow = (size_t)inst * Ny + iy0;        // row of Fx / Fy
   load_tables<P, PAIRS>(sm, twg, true);
   pdl_wait();
   pdl_launch_dependents();
   bool ok[4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) ok[j] = r0 + j < nrows;
+  for (int j = 0; j < 4; j++) ok[j] = r0 + j < nrows && iy0 + j < Ny;
   constexpr int NE = 6;  // 2 Nx - 1 <= P = 12 T, so Nx <= 6 T: at most 6 output points per thread and row (ix = t + T i)
   float4 inv[NE];
   int x = 0;
@@ -228,10 +234,10 @@ fast_rows_inv(int nrows, int Nx, int Pw, int kxp, const float2* __restrict__ G, 
         if (k == 0) {
           inv[i] = make_float4(1.f / v.x, 1.f / v.z, 1.f / v.y, 1.f / v.w);  // rows 0, 1, 2, 3: 1 / (w * rho)
         } else {  // pde.jl:58 force ./ norms
-          if (ok[0]) F[(size_t)(r0 + 0) * Pw + ix] = v.x * inv[i].x;
-          if (ok[1]) F[(size_t)(r0 + 1) * Pw + ix] = v.z * inv[i].y;
-          if (ok[2]) F[(size_t)(r0 + 2) * Pw + ix] = v.y * inv[i].z;
-          if (ok[3]) F[(size_t)(r0 + 3) * Pw + ix] = v.w * inv[i].w;
+          if (ok[0]) F[(frow + 0) * Pw + ix] = v.x * inv[i].x;
+          if (ok[1]) F[(frow + 1) * Pw + ix] = v.z * inv[i].y;
+          if (ok[2]) F[(frow + 2) * Pw + ix] = v.y * inv[i].z;
+          if (ok[3]) F[(frow + 3) * Pw + ix] = v.w * inv[i].w;
         }
       }
     }
@@ -308,16 +314,17 @@ static int fast_launch(smm_ctx* ctx, smm_fft_fast* f, const float* rho, float* F
   const int sms = pdl ? ctx->sm_count : 0;
   for (int b0 = 0; b0 < f->B; b0 += f->chunk) {
     const int bc = std::min(f->chunk, f->B - b0);
-    const int nrows = bc * f->Ny;
+    const int Nyp = (f->Ny + 3) & ~3;
+    const int nrows = bc * Nyp;                          // virtual rows: Ny rounded up to whole quads per instance
     const size_t off = (size_t)b0 * f->Ny * f->Pw;
-    const size_t gstride = (((size_t)f->chunk * f->Ny + 3) & ~(size_t)3) * f->kxp;
+    const size_t gstride = (size_t)f->chunk * Nyp * f->kxp;
     const dim3 rgrid((nrows + C::ROWS - 1) / C::ROWS);
-    SMM_CUDA(ctx, smm_launch_pdl(sms, fast_rows_fwd<P, PAIRS>, rgrid, dim3(C::THREADS), C::SMEM, ctx->stream, nrows, f->Nx, f->Pw, f->kxp,
-                                 rho + off, f->a, (const float2*)f->tw));
-    SMM_CUDA(ctx, smm_launch_pdl(sms, fast_cols<P, PAIRS>, dim3(f->ngroups, bc), dim3(C::THREADS), C::SMEM, ctx->stream, f->Ny, f->kxp, f->ngroups,
-                                 (const float2*)f->a, (const float*)f->hk, f->g, gstride, (const float2*)f->tw));
-    SMM_CUDA(ctx, smm_launch_pdl(sms, fast_rows_inv<P, PAIRS>, rgrid, dim3(C::THREADS), C::SMEM, ctx->stream, nrows, f->Nx, f->Pw, f->kxp,
-                                 (const float2*)f->g, gstride, Fx + off, Fy + off, (const float2*)f->tw));
+    SMM_CUDA(ctx, smm_launch_pdl(sms, fast_rows_fwd<P, PAIRS>, rgrid, dim3(C::THREADS), C::SMEM, ctx->stream, nrows, f->Ny, Nyp, f->Nx, f->Pw,
+                                 f->kxp, rho + off, f->a, (const float2*)f->tw));
+    SMM_CUDA(ctx, smm_launch_pdl(sms, fast_cols<P, PAIRS>, dim3(f->ngroups, bc), dim3(C::THREADS), C::SMEM, ctx->stream, f->Ny, Nyp, f->kxp,
+                                 f->ngroups, (const float2*)f->a, (const float*)f->hk, f->g, gstride, (const float2*)f->tw));
+    SMM_CUDA(ctx, smm_launch_pdl(sms, fast_rows_inv<P, PAIRS>, rgrid, dim3(C::THREADS), C::SMEM, ctx->stream, nrows, f->Ny, Nyp, f->Nx, f->Pw,
+                                 f->kxp, (const float2*)f->g, gstride, Fx + off, Fy + off, (const float2*)f->tw));
     ctx->launches += 3;
   }
   SMM_CUDA(ctx, cudaGetLastError());
@@ -368,7 +375,7 @@ int smm_fft_fast_create(smm_ctx* ctx, int P, int Nx, int Ny, int Pw, int B, cons
     if (const char* ev = getenv("SMM_FFT_CHUNK_MB"))
       f->chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, ((size_t)std::max(1, atoi(ev)) << 20) / per_inst));
   }
-  const size_t arow = (((size_t)f->chunk * Ny + 3) & ~(size_t)3) * f->kxp;  // rows rounded up to whole quads (G layout)
+  const size_t arow = (size_t)f->chunk * ((Ny + 3) & ~3) * f->kxp;  // virtual rows: Ny rounded up to whole quads per instance
 #define FF_CUDA(expr)                                                                                                   \
   do {                                                                                                                  \
     cudaError_t e__ = (expr);                                                                                           \
