@@ -269,8 +269,13 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
           const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
           ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
         }
+        // running totals in the order of the tile-dealing form below (diagonal, then the row sums of d = 1..D, every tile
+        // summed on its own first; explicit _rn operations: no contraction into an FMA), so that a realization's result
+        // does not depend on the CTA width, i.e. on the size of the ensemble it is part of
+        float totw = __fadd_rn(ws2.x, ws2.y), totx = __fmul_rn(__fadd_rn(ax2.x, ax2.y), kLn2), toty = __fmul_rn(__fadd_rn(ay2.x, ay2.y), kLn2);
         for (int d = 1; d <= D; d++) {
           if (2 * d == G && g >= D) break;
+          ws2 = make_float2(0.f, 0.f); ax2 = ws2; ay2 = ws2;
           int h = g + d;
           if (h >= G) h -= G;
           const float4* colp = xy2 + h * 64 + lane;
@@ -296,9 +301,12 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
           }
           float* o = part + (size_t)d * 3 * NG + h * 32 + lane;
           o[0] = cws2.x + cws2.y; o[NG] = (cax2.x + cax2.y) * kLn2; o[2 * NG] = (cay2.x + cay2.y) * kLn2;
+          totw = __fadd_rn(totw, __fadd_rn(ws2.x, ws2.y));
+          totx = __fadd_rn(totx, __fmul_rn(__fadd_rn(ax2.x, ax2.y), kLn2));
+          toty = __fadd_rn(toty, __fmul_rn(__fadd_rn(ay2.x, ay2.y), kLn2));
         }
         float* o = part + g * 32 + lane;
-        o[0] = ws2.x + ws2.y; o[NG] = (ax2.x + ax2.y) * kLn2; o[2 * NG] = (ay2.x + ay2.y) * kLn2;
+        o[0] = totw; o[NG] = totx; o[2 * NG] = toty;
       }
       __syncthreads();
       for (int j = tid; j < n; j += kThreads) {
