@@ -28,6 +28,64 @@ constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 constexpr int kSymMaxGroups = 16;  // n <= 512: the per-offset partial sums must fit shared memory
 constexpr float kPadPos = 1e15f;   // padding agents of the last 32-group: exp(-|x - pad|) = 0 exactly
 
+// ---- symmetric pair tiles ---------------------------------------------------------------------------------------
+// Table of a 32-group: T[i] = log2(e) * (x_a, x_b, y_a, y_b) of the agents a = i & 31, b = (i + 16) & 31, i < 64
+// (every entry twice, so that the rotated index lane +- t needs no wrap-around arithmetic).
+// Measured and rejected (round 2): a table in which lanes l and l + 16 read the same entry halves the shared-memory
+// wavefronts of the loads (the data pipe is the busiest unit, 75 %), but routing the weights then costs four selects
+// and a mask per step: 21 -> 26 instructions per step, kernel 5.90 -> 6.40 ms.  The loop is bound by issue slots and
+// per-warp latency (0.6 instructions per cycle and scheduler with 5.7 resident warps), so what pays is instructions:
+// the column-side fix-up below (21 -> 19 per step) and the symmetric diagonal tile: 5.90 -> 5.60 ms.
+constexpr int kTab = 64;   // table entries per 32-group
+struct Sums2 { float2 ws, ax, ay; };
+__device__ __forceinline__ void zero(Sums2& s) { s.ws = s.ax = s.ay = make_float2(0.f, 0.f); }
+// (sum of the two halves; forces scaled back by ln 2) -- explicit _rn operations: no contraction into an FMA
+__device__ __forceinline__ float fold_w(const Sums2& s) { return __fadd_rn(s.ws.x, s.ws.y); }
+__device__ __forceinline__ float fold_x(const Sums2& s) { return __fmul_rn(__fadd_rn(s.ax.x, s.ax.y), kLn2); }
+__device__ __forceinline__ float fold_y(const Sums2& s) { return __fmul_rn(__fadd_rn(s.ay.x, s.ay.y), kLn2); }
+
+// ordered step: row agent against the two agents of entry p (no exchange)
+__device__ __forceinline__ void ordered_step(const float4 p, const float2 nrx, const float2 nry, Sums2& R) {
+  const float2 dx = add2(make_float2(p.x, p.y), nrx), dy = add2(make_float2(p.z, p.w), nry);
+  const float2 r2 = fma2(dx, dx, mul2(dy, dy));
+  const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
+  R.ws = add2(R.ws, w); R.ax = fma2(w, dx, R.ax); R.ay = fma2(w, dy, R.ay);
+}
+// symmetric steps T0..T1 of the tile (row group, column group): at step t row agent l (= lane) meets the column agents
+// (l + t) & 31 and (l + t + 16) & 31; the weights go to the row sums R and, through one shuffle each, to the lanes that
+// own those column agents, which pair them with the rows (l - t) & 31 and (l - t - 16) & 31 -- stored next to each other
+// at index l - t + 32.  The column side accumulates sum_r w x_r and subtracts x_c sum_r w once at the end (ncx = -x_c):
+// two instructions fewer per step; the cancellation costs < 1e-6 of the force (|x| <= 3.2 in these units), i.e.
+// < 1e-8 of a position per step.
+template <int T0, int T1>
+__device__ __forceinline__ void sym_steps(const float4* rowp, const float4* colp, const int lane, const float2 nrx, const float2 nry,
+                                          const float2 ncx, const float2 ncy, Sums2& R, Sums2& C) {
+#pragma unroll
+  for (int t = T0; t <= T1; t++) {
+    const float4 p = colp[t];
+    const float2 dx = add2(make_float2(p.x, p.y), nrx), dy = add2(make_float2(p.z, p.w), nry);
+    const float2 r2 = fma2(dx, dx, mul2(dy, dy));
+    const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
+    R.ws = add2(R.ws, w); R.ax = fma2(w, dx, R.ax); R.ay = fma2(w, dy, R.ay);
+    float2 wv;
+    wv.x = __shfl_sync(0xffffffffu, w.x, lane - t);
+    wv.y = __shfl_sync(0xffffffffu, w.y, lane - t - 16);
+    const float4 q = rowp[32 - t];
+    C.ws = add2(C.ws, wv); C.ax = fma2(wv, make_float2(q.x, q.y), C.ax); C.ay = fma2(wv, make_float2(q.z, q.w), C.ay);
+  }
+  C.ax = fma2(C.ws, ncx, C.ax); C.ay = fma2(C.ws, ncy, C.ay);
+}
+// diagonal tile: rotation steps 1..7 symmetric (offsets 1..7 and 17..23 = -15..-9), steps 0 and 8 ordered (step 0 holds
+// the agent itself, abm.jl:42, and its opposite; the pairs at offsets 8 and 24 are met from both sides): 9 steps, not 16
+__device__ __forceinline__ void diag_tile(const float4* rowp, const int lane, const float2 nrx, const float2 nry, Sums2& R) {
+  Sums2 C;
+  zero(R); zero(C);
+  ordered_step(rowp[0], nrx, nry, R);
+  sym_steps<1, 7>(rowp, rowp, lane, nrx, nry, nrx, nry, R, C);
+  ordered_step(rowp[8], nrx, nry, R);
+  R.ws = add2(R.ws, C.ws); R.ax = add2(R.ax, C.ax); R.ay = add2(R.ay, C.ay);
+}
+
 // THREADS = CTA width: 128 when the ensemble alone fills the GPU (1 024 realizations: 7 CTAs per SM, all resident);
 // 256 / 512 for small ensembles (configs[1] at 8 GPUs = 128 realizations per GPU; C1 = one realization), where one
 // realization is spread over 8 / 16 warps instead of leaving most of the SMs' issue slots idle.
@@ -67,7 +125,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
   const int G = (n + 31) >> 5, D = G >> 1, NG = G * 32;
   // xy2[g][i] = log2(e) * (x_a, x_b, y_a, y_b) of the agents a = g*32 + (i & 31), b = g*32 + ((i + 16) & 31), i < 64
   float4* xy2 = reinterpret_cast<float4*>(smem + ((reinterpret_cast<unsigned char*>(st + npad) - smem + 15) & ~(size_t)15));
-  float* part = reinterpret_cast<float*>(xy2 + (SYM ? G * 64 : 0));
+  float* part = reinterpret_cast<float*>(xy2 + (SYM ? G * kTab : 0));
 
   // ---- load the initial condition --------------------------------------------------------
   const real* x0 = static_cast<const real*>(A.x0) + (size_t)r * 2 * n;
@@ -206,7 +264,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
         medx[nxt * M + e] = px; medy[nxt * M + e] = py;
       }
     }
-    __syncthreads();
+    // The symmetric pair loop reads nothing P2 writes (its consumers are the per-agent updates behind the next barrier):
+    // no barrier here, the six P2 threads' latency overlaps the other warps' tiles.
+    if (!SYM) __syncthreads();
 
     // ---- P3: per agent: attraction over all agents, influence, Euler-Maruyama, switch.
     // Two agents per thread (j0, j0 + kThreads): each broadcast partner load feeds two pair
@@ -254,56 +314,29 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
       // evaluated in ordered form and contains the self pair (abm.jl:42).  Every partial sum has its own
       // shared-memory slot and is added in a fixed order: results are deterministic.
       if constexpr (THREADS == 128) {
-      // full-GPU configuration: a warp owns whole row groups and keeps their sums in registers across the offsets
+      // full-GPU configuration: a warp owns whole row groups and keeps their running totals in registers across the
+      // offsets.  The totals are added in the order of the tile-dealing form below (diagonal tile, then the row sums
+      // of d = 1..D, every tile folded on its own first), so that a realization's result does not depend on the CTA
+      // width, i.e. on the size of the ensemble it is part of.
       for (int g = warp; g < G; g += nwarps) {
-        const float4* rowp = xy2 + g * 64 + lane;
+        const float4* rowp = xy2 + g * kTab + lane;
         const float rx = rowp[0].x, ry = rowp[0].z;
         const float2 nrx = make_float2(-rx, -rx), nry = make_float2(-ry, -ry);
-        float2 ws2 = make_float2(0.f, 0.f), ax2 = ws2, ay2 = ws2;
-        // diagonal tile: lane l against all 32 agents of its own group, two partners per step
-#pragma unroll 8
-        for (int t = 0; t < 16; t++) {
-          const float4 p = rowp[t];
-          const float2 dx = add2(make_float2(p.x, p.y), nrx), dy = add2(make_float2(p.z, p.w), nry);
-          const float2 r2 = fma2(dx, dx, mul2(dy, dy));
-          const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
-          ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
-        }
-        // running totals in the order of the tile-dealing form below (diagonal, then the row sums of d = 1..D, every tile
-        // summed on its own first; explicit _rn operations: no contraction into an FMA), so that a realization's result
-        // does not depend on the CTA width, i.e. on the size of the ensemble it is part of
-        float totw = __fadd_rn(ws2.x, ws2.y), totx = __fmul_rn(__fadd_rn(ax2.x, ax2.y), kLn2), toty = __fmul_rn(__fadd_rn(ay2.x, ay2.y), kLn2);
+        Sums2 Rs;
+        diag_tile(rowp, lane, nrx, nry, Rs);
+        float totw = fold_w(Rs), totx = fold_x(Rs), toty = fold_y(Rs);
         for (int d = 1; d <= D; d++) {
           if (2 * d == G && g >= D) break;
-          ws2 = make_float2(0.f, 0.f); ax2 = ws2; ay2 = ws2;
           int h = g + d;
           if (h >= G) h -= G;
-          const float4* colp = xy2 + h * 64 + lane;
+          const float4* colp = xy2 + h * kTab + lane;
           const float cx = colp[0].x, cy = colp[0].z;
-          const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy);
-          float2 cws2 = make_float2(0.f, 0.f), cax2 = cws2, cay2 = cws2;
-          // step t: row agent l with the column agents (l + t) & 31 and (l + t + 16) & 31; their weights go
-          // to the lanes that own those column agents, which pair them with the rows (l - t) & 31 and
-          // (l - t - 16) & 31 — stored next to each other at index l - t + 32
-#pragma unroll 16
-          for (int t = 0; t < 16; t++) {
-            const float4 p = colp[t];
-            const float2 dx = add2(make_float2(p.x, p.y), nrx), dy = add2(make_float2(p.z, p.w), nry);
-            const float2 r2 = fma2(dx, dx, mul2(dy, dy));
-            const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
-            ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
-            float2 wv;
-            wv.x = __shfl_sync(0xffffffffu, w.x, lane - t);
-            wv.y = __shfl_sync(0xffffffffu, w.y, lane - t - 16);
-            const float4 q = rowp[32 - t];
-            const float2 ex = add2(make_float2(q.x, q.y), ncx), ey = add2(make_float2(q.z, q.w), ncy);
-            cws2 = add2(cws2, wv); cax2 = fma2(wv, ex, cax2); cay2 = fma2(wv, ey, cay2);
-          }
+          Sums2 Cs;
+          zero(Rs); zero(Cs);
+          sym_steps<0, 15>(rowp, colp, lane, nrx, nry, make_float2(-cx, -cx), make_float2(-cy, -cy), Rs, Cs);
           float* o = part + (size_t)d * 3 * NG + h * 32 + lane;
-          o[0] = cws2.x + cws2.y; o[NG] = (cax2.x + cax2.y) * kLn2; o[2 * NG] = (cay2.x + cay2.y) * kLn2;
-          totw = __fadd_rn(totw, __fadd_rn(ws2.x, ws2.y));
-          totx = __fadd_rn(totx, __fmul_rn(__fadd_rn(ax2.x, ax2.y), kLn2));
-          toty = __fadd_rn(toty, __fmul_rn(__fadd_rn(ay2.x, ay2.y), kLn2));
+          o[0] = fold_w(Cs); o[NG] = fold_x(Cs); o[2 * NG] = fold_y(Cs);
+          totw = __fadd_rn(totw, fold_w(Rs)); totx = __fadd_rn(totx, fold_x(Rs)); toty = __fadd_rn(toty, fold_y(Rs));
         }
         float* o = part + g * 32 + lane;
         o[0] = totw; o[NG] = totx; o[2 * NG] = toty;
@@ -331,49 +364,25 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
         if (it >= NI) continue;
         const int d = it < NO ? it / G + 1 : 0;
         const int g = it < NO ? it - (d - 1) * G : it - NO;
-        const float4* rowp = xy2 + g * 64 + lane;
+        const float4* rowp = xy2 + g * kTab + lane;
         const float rx = rowp[0].x, ry = rowp[0].z;
         const float2 nrx = make_float2(-rx, -rx), nry = make_float2(-ry, -ry);
-        float2 ws2 = make_float2(0.f, 0.f), ax2 = ws2, ay2 = ws2;
+        Sums2 Rs;
         if (d == 0) {
-          // diagonal tile: lane l against all 32 agents of its own group, two partners per step
-#pragma unroll 8
-          for (int t = 0; t < 16; t++) {
-            const float4 p = rowp[t];
-            const float2 dx = add2(make_float2(p.x, p.y), nrx), dy = add2(make_float2(p.z, p.w), nry);
-            const float2 r2 = fma2(dx, dx, mul2(dy, dy));
-            const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
-            ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
-          }
+          diag_tile(rowp, lane, nrx, nry, Rs);
         } else {
           int h = g + d;
           if (h >= G) h -= G;
-          const float4* colp = xy2 + h * 64 + lane;
+          const float4* colp = xy2 + h * kTab + lane;
           const float cx = colp[0].x, cy = colp[0].z;
-          const float2 ncx = make_float2(-cx, -cx), ncy = make_float2(-cy, -cy);
-          float2 cws2 = make_float2(0.f, 0.f), cax2 = cws2, cay2 = cws2;
-          // step t: row agent l with the column agents (l + t) & 31 and (l + t + 16) & 31; their weights go
-          // to the lanes that own those column agents, which pair them with the rows (l - t) & 31 and
-          // (l - t - 16) & 31 — stored next to each other at index l - t + 32
-#pragma unroll 16
-          for (int t = 0; t < 16; t++) {
-            const float4 p = colp[t];
-            const float2 dx = add2(make_float2(p.x, p.y), nrx), dy = add2(make_float2(p.z, p.w), nry);
-            const float2 r2 = fma2(dx, dx, mul2(dy, dy));
-            const float2 w = make_float2(w_of_scaled_r2(r2.x), w_of_scaled_r2(r2.y));
-            ws2 = add2(ws2, w); ax2 = fma2(w, dx, ax2); ay2 = fma2(w, dy, ay2);
-            float2 wv;
-            wv.x = __shfl_sync(0xffffffffu, w.x, lane - t);
-            wv.y = __shfl_sync(0xffffffffu, w.y, lane - t - 16);
-            const float4 q = rowp[32 - t];
-            const float2 ex = add2(make_float2(q.x, q.y), ncx), ey = add2(make_float2(q.z, q.w), ncy);
-            cws2 = add2(cws2, wv); cax2 = fma2(wv, ex, cax2); cay2 = fma2(wv, ey, cay2);
-          }
+          Sums2 Cs;
+          zero(Rs); zero(Cs);
+          sym_steps<0, 15>(rowp, colp, lane, nrx, nry, make_float2(-cx, -cx), make_float2(-cy, -cy), Rs, Cs);
           float* o = part + (size_t)(D + d) * 3 * NG + h * 32 + lane;
-          o[0] = cws2.x + cws2.y; o[NG] = (cax2.x + cax2.y) * kLn2; o[2 * NG] = (cay2.x + cay2.y) * kLn2;
+          o[0] = fold_w(Cs); o[NG] = fold_x(Cs); o[2 * NG] = fold_y(Cs);
         }
         float* o = part + (size_t)d * 3 * NG + g * 32 + lane;
-        o[0] = ws2.x + ws2.y; o[NG] = (ax2.x + ax2.y) * kLn2; o[2 * NG] = (ay2.x + ay2.y) * kLn2;
+        o[0] = fold_w(Rs); o[NG] = fold_x(Rs); o[2 * NG] = fold_y(Rs);
       }
       __syncthreads();
       for (int j = tid; j < n; j += kThreads) {
@@ -501,7 +510,7 @@ size_t dense_smem_bytes(int n, int L, int M, size_t real_size, bool sym, int thr
     const size_t G = (n + 31) / 32, D = G / 2;
     // 128-thread CTAs keep row sums in registers (slots 0..D); wider CTAs deal single tiles (row + column slots).
     // The difference decides whether 7 CTAs (all 1 024 realizations of C2) fit one SM's shared memory.
-    b += 16 + 2 * G * 64 * 8 + (1 + (threads == 128 ? 1 : 2) * D) * 3 * G * 32 * 4;
+    b += 16 + G * kTab * 16 + (1 + (threads == 128 ? 1 : 2) * D) * 3 * G * 32 * 4;
   }
   return b;
 }
