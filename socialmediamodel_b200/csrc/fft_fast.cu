@@ -107,6 +107,7 @@ fast_rows_fwd(int nrows, int Ny, int Nyp, int Nx, int Pw, int kxp, const float* 
     a[e] = C2{make_float2(v[0], v[2]), make_float2(v[1], v[3])};  // transform .x = rows (0, 1), transform .y = rows (2, 3)
   }
   int x = 0;
+  __syncthreads();  // the twiddle / position tables written by load_tables are read by other threads from the first pass on
   transform<P, PAIRS, -1, false>(a, t, p, sm, x);
   store_pass<P, PAIRS>(C::NEX, a, t, p, sm.buf(x));
   x++;
@@ -151,6 +152,8 @@ fast_cols(int Ny, int Nyp, int kxp, int ngroups, const float2* __restrict__ A, c
     r[e] = C2{make_float2(v.x, v.z), make_float2(v.y, v.w)};
   }
   int x = 0;
+  __syncthreads();  // tables of load_tables (see fast_rows_fwd): without this barrier a late warp's table entries were read
+                    // before they were written -- rare, timing-dependent errors of 1e-7 .. 1e-4 in the force
   transform<P, PAIRS, -1, false>(r, t, p, sm, x);  // r[s] = spectrum at digit-reversed position pass_pos(NEX, t, s)
 #pragma unroll 1
   for (int k = 0; k < 3; k++) {
@@ -200,6 +203,7 @@ fast_rows_inv(int nrows, int Ny, int Nyp, int Nx, int Pw, int kxp, const float2*
   constexpr int NE = 6;  // 2 Nx - 1 <= P = 12 T, so Nx <= 6 T: at most 6 output points per thread and row (ix = t + T i)
   float4 inv[NE];
   int x = 0;
+  __syncthreads();  // tables of load_tables
 #pragma unroll 1
   for (int k = 0; k < 3; k++) {
     const float2* Gk = G + (size_t)k * gstride;

@@ -19,29 +19,12 @@
 #include <algorithm>
 #include <map>
 
+#include "pde_types.cuh"
 #include "smm_internal.h"
 
 namespace {
 
-constexpr int LMAX = 16;
 constexpr int BX = 32, BY = 8;  // stage-kernel CTA = 32 x 8 grid points, one warp per grid row
-
-struct PdeInst {  // per-instance constants
-  double a, b, c, eta, D, frictionI, frictionM, speed1, speed2, tgt1[2], tgt2[2];
-  int cinf[LMAX];
-  int cmed[2];
-};
-
-struct PdeCoef {  // per-instance stage data: written by the finalising CTA, read by the next stage
-  double y[LMAX][2], z[2][2];    // stage values of the ODE unknowns
-  double dy[LMAX][2], dz[2][2];  // their right-hand sides at this stage (pde.jl:239-265)
-  double R[2][LMAX];             // eta * r((m_ij - m_i'j)/(m_ij + m_i'j))  (pde.jl:43)
-};
-
-struct PdeOde {  // RK bookkeeping of the ODE unknowns
-  double yn[LMAX][2], zn[2][2], yacc[LMAX][2], zacc[2][2];
-  double yerr[LMAX][2], zerr[2][2];  // embedded error estimate (adaptive stepping)
-};
 
 // Per-instance step controller of the adaptive integrator (embedded 3(2) pair, see enqueue_adaptive_attempt).
 // Written only by the CTA that finalises the instance in the last stage kernel of an attempt (and by the
@@ -991,6 +974,10 @@ struct smm_pde_batch {
   PdeCtl* ctl;
   std::vector<PdeCtl> h_ctl;
   cudaGraphExec_t adapt_graph;
+  // whole steps inside one thread-block cluster per instance (pde_cluster.cu): small FP32 batches
+  bool cluster_ok;
+  int cl_rpc, cl_cpc;
+  size_t cl_smem;
 };
 
 static void pde_free(smm_pde_batch* pb) {
@@ -1111,10 +1098,11 @@ static int launch_stage(smm_ctx* ctx, smm_pde_batch* pb, const StageArgs& A0) {
   return A0.ctl ? launch_stage_ad<true>(ctx, pb, A0) : launch_stage_ad<false>(ctx, pb, A0);
 }
 
+constexpr int CLUSTER_CTAS = 16;
+
 // one RK step = nstages x (conv, stage).  Buffer roles: u = step start / result, Ua/Ub stage states.
-static int enqueue_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, int scheme) {
-  struct St { const void* U; void* out; double A, B, C, bw; int acc; };
-  St st[4];
+struct RkStage { const void* U; void* out; double A, B, C, bw; int acc; };
+static int rk_stages(smm_ctx* ctx, smm_pde_batch* pb, int scheme, RkStage* st, int* nstages) {
   int ns = 0;
   void *u = pb->u, *a = pb->Ua, *b = pb->Ub;
   switch (scheme) {
@@ -1139,6 +1127,14 @@ static int enqueue_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, int scheme) 
     default:
       return smm_fail(ctx, SMM_ERR_INVALID, "unknown RK scheme %d", scheme);
   }
+  *nstages = ns;
+  return SMM_OK;
+}
+
+static int enqueue_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, int scheme) {
+  RkStage st[4];
+  int ns = 0;
+  SMM_TRY(rk_stages(ctx, pb, scheme, st, &ns));
   for (int s = 0; s < ns; s++) {
     SMM_TRY(launch_conv(ctx, pb));
     StageArgs A = base_args(pb);
@@ -1239,6 +1235,7 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
   pb->steps_taken = 0;
   pb->time = 0.0; pb->err = nullptr; pb->errpart = nullptr; pb->ctl = nullptr; pb->adapt_graph = nullptr;
   pb->fft = nullptr;
+  pb->cluster_ok = false; pb->cl_rpc = pb->cl_cpc = 0; pb->cl_smem = 0;
   pb->no_graph = false;
   pb->use_tma = false;
   pb->stage2 = false;
@@ -1320,6 +1317,20 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
     if (!(ev && strcmp(ev, "direct") == 0) && need <= 2048)
       PB_TRY(smm_fft_plan_create(ctx, grid->Nx, grid->Ny, pb->Pw, grid->dx, grid->dy, B, precision, &pb->fft));
   }
+  // Small FP32 batches (C3: one instance on the default grid): whole RK steps inside one 16-CTA cluster per instance,
+  // state resident in distributed shared memory (pde_cluster.cu).  Larger batches fill the GPU with the kernel chain.
+  // SMM_PDE_CLUSTER=0 / 1 disables / forces it (where the shape allows).
+  if (pb->fft && precision == SMM_PREC_F32) {
+    const char* ev = getenv("SMM_PDE_CLUSTER");
+    bool want = (size_t)B * CLUSTER_CTAS <= (size_t)ctx->sm_count;
+    if (ev && ev[0] == '0') want = false;
+    if (ev && ev[0] == '1') want = true;
+    if (want) {
+      int dims[4]; const void *tw, *kh;
+      smm_fft_plan_tables(pb->fft, dims, &tw, &kh);
+      pb->cluster_ok = smm_pde_cluster_plan(ctx, grid->Nx, grid->Ny, L, dims[0], &pb->cl_rpc, &pb->cl_cpc, &pb->cl_smem) == SMM_OK;
+    }
+  }
   // initial state: u (converted to `real`), coef.y/z
   const int ninit = shared_init ? 1 : B;
   {
@@ -1362,6 +1373,25 @@ extern "C" int smm_pde_batch_step(smm_ctx* ctx, smm_pde_batch* pb, double dt, in
   SMM_REQUIRE(ctx, scheme >= SMM_RK_EULER && scheme <= SMM_RK_RK4, "smm_pde_batch_step: unknown scheme %d", scheme);
   SMM_CUDA(ctx, cudaSetDevice(ctx->device));
   if (nsteps == 0) return SMM_OK;
+  if (pb->cluster_ok) {  // all nsteps steps in ONE launch: one cluster per instance, state in distributed shared memory
+    RkStage st[4];
+    PdeClusterArgs A;
+    memset(&A, 0, sizeof A);
+    SMM_TRY(rk_stages(ctx, pb, scheme, st, &A.nstages));
+    for (int s = 0; s < A.nstages; s++) A.st[s] = PdeClusterStage{st[s].A, st[s].B, st[s].C, st[s].bw, st[s].acc};
+    int dims[4];
+    smm_fft_plan_tables(pb->fft, dims, &A.tw, &A.khat);
+    A.L = pb->L; A.Nx = pb->Nx; A.Ny = pb->Ny; A.Pw = pb->Pw; A.P = dims[0]; A.m = dims[1]; A.a = dims[2]; A.r3 = dims[3];
+    A.RPC = pb->cl_rpc; A.CPC = pb->cl_cpc; A.nsteps = nsteps;
+    A.gx0 = pb->grid.x0; A.gy0 = pb->grid.y0; A.dx = pb->grid.dx; A.dt = dt;
+    A.u = (float*)pb->u; A.rhosum = (float*)pb->rhosum; A.coef = pb->coef; A.ode = pb->ode; A.inst = pb->inst;
+    smm_tic(ctx, SMM_K_STENCIL);
+    SMM_TRY(smm_launch_pde_cluster(ctx, A, pb->B, pb->cl_smem));
+    smm_toc(ctx, SMM_K_STENCIL);
+    pb->steps_taken += nsteps;
+    pb->time += dt * nsteps;
+    return SMM_OK;
+  }
   // the kernel chain of one step is captured once per (scheme, dt) and replayed
   auto key = std::make_pair((int)scheme, dt);
   auto it = pb->graphs.find(key);

@@ -104,6 +104,24 @@ struct smm_fft_plan;
 int smm_fft_plan_create(smm_ctx* ctx, int Nx, int Ny, int Pw, double hx, double hy, int B, int precision, smm_fft_plan** out);
 int smm_fft_conv(smm_ctx* ctx, smm_fft_plan* p, const void* rhosum, void* Fx, void* Fy);
 void smm_fft_plan_destroy(smm_fft_plan* p);
+void smm_fft_plan_tables(const smm_fft_plan* p, int dims[4] /* P, m, a, r3 */, const void** tw, const void** khat);
+// whole RK steps of small instances inside one thread-block cluster (pde_cluster.cu)
+struct PdeClusterStage { double A, Bc, C, bw; int acc; };
+struct PdeClusterArgs {
+  int L, Nx, Ny, Pw, P, m, a, r3;  // grid, row pitch, FFT length P = r3 * m, m = 2^a
+  int RPC, CPC, nsteps, nstages;   // grid rows / spectrum columns per CTA
+  double gx0, gy0, dx, dt;
+  float* u;                        // [B][2L][Ny][Pw]
+  float* rhosum;                   // [B][Ny][Pw]
+  void* coef;                      // PdeCoef[B]
+  void* ode;                       // PdeOde[B]
+  const void* inst;                // PdeInst[B]
+  const void* tw;                  // float2[P]
+  const void* khat;                // float2[3][P/2+1][P]
+  PdeClusterStage st[4];
+};
+int smm_pde_cluster_plan(smm_ctx* ctx, int Nx, int Ny, int L, int P, int* RPC, int* CPC, size_t* smem);
+int smm_launch_pde_cluster(smm_ctx* ctx, const PdeClusterArgs& A, int B, size_t smem);
 // register-resident FP32 path for P = 96 / 192 / 384 / 768 (fft_fast.cu)
 struct smm_fft_fast;
 bool smm_fft_fast_supported(int P);
