@@ -365,3 +365,66 @@ def test_sharded_pde_sweep_single_rank_equals_direct(coarse):
     us, zs, ys, _ = smm.PDEsolveensemble(0.02, 3, savepoints=3, p=p, qs=[smm.parameters(a=a) for a in (0.5, 1.0, 1.5)],
                                          save=False, precision="f64", adaptive=True)
     assert rel(res["us"], us) < 1e-12
+
+
+# ---- whole RK steps inside one thread-block cluster (csrc/pde_cluster.cu): small FP32 batches ------------------------------
+def _cluster(monkeypatch, on):
+    monkeypatch.setenv("SMM_PDE_CLUSTER", "1" if on else "0")
+
+
+@pytest.mark.parametrize("scheme", ["euler", "heun", "ssprk3", "rk4"])
+@pytest.mark.parametrize("grid", ["coarse", "default"])
+def test_cluster_steps_against_oracle_and_kernel_chain(grid, scheme, monkeypatch):
+    """pde.jl:183-268 + the RK tableau, one instance resident in a 16-CTA cluster: against the Float64 oracle on the coarse
+    grid, against the Float64 kernel chain on the default grid (the oracle takes minutes there), and against the FP32 chain."""
+    p = smm.PDEconstructcoarse() if grid == "coarse" else smm.PDEconstruct()
+    uzy0, q = smm.constructinitial("4inf", (p, smm.parameters()))
+    u0, z0, y0 = perturbed_state(p, q, uzy0, 5) if grid == "coarse" else uzy0.x
+    dt, n = (1e-3, 6)
+    _cluster(monkeypatch, True)
+    a = smm.pde_solve_raw(p, [q], u0, z0, y0, dt=dt, nsteps=n, savesteps=[0, 3, 6], scheme=scheme, precision="f32")
+    launches = smm.Context.default().launches
+    smm.pde_solve_raw(p, [q], u0, z0, y0, dt=dt, nsteps=40, savesteps=[40], scheme=scheme, precision="f32")
+    per_solve = smm.Context.default().launches - launches
+    _cluster(monkeypatch, False)
+    c = smm.pde_solve_raw(p, [q], u0, z0, y0, dt=dt, nsteps=n, savesteps=[0, 3, 6], scheme=scheme, precision="f32")
+    launches = smm.Context.default().launches
+    smm.pde_solve_raw(p, [q], u0, z0, y0, dt=dt, nsteps=40, savesteps=[40], scheme=scheme, precision="f32")
+    assert per_solve < (smm.Context.default().launches - launches) - 40      # the cluster path really ran: 1 launch, not >= 8 per step
+    r = smm.pde_solve_raw(p, [q], u0, z0, y0, dt=dt, nsteps=n, savesteps=[0, 3, 6], scheme=scheme, precision="f64")
+    assert rel(a["us"], r["us"]) < TOL32 and rel(a["us"], c["us"]) < 2e-6
+    assert np.abs(a["ys"] - r["ys"]).max() < 1e-6 and np.abs(a["zs"] - r["zs"]).max() < 1e-6
+    if grid == "coarse":
+        saved = P.rk_solve(u0, z0, y0, n, dt, oracle_p(p), dict(q), scheme=scheme, save_every=3)
+        for m, (k, ur, zr, yr) in enumerate(saved):
+            assert rel(a["us"][..., m, 0], ur) < TOL32, (scheme, k)
+            assert np.abs(a["ys"][..., m, 0] - yr).max() < 1e-6 and np.abs(a["zs"][..., m, 0] - zr).max() < 1e-6
+
+
+def test_cluster_steps_batch_resume_and_controlled_influencer(monkeypatch):
+    """(a) three instances = three clusters, each equal to its solo run bit for bit; (b) 6 steps in one launch = 2 + 4 steps in
+    two launches (the state leaves and re-enters shared memory); (c) L = 5 with a controlled, zero-mass influencer
+    (controlstrategies.jl:16-30) against the oracle."""
+    from oracle import control_oracle as CO
+    _cluster(monkeypatch, True)
+    p = smm.PDEconstructcoarse()
+    qs = [smm.parameters(), smm.parameters(a=1.5, eta=10.0), smm.parameters(c=3.0, sigma=0.4)]
+    inits = [smm.constructinitial("4inf", (p, q)) for q in qs]
+    ql = [qq for _, qq in inits]
+    U = np.stack([uz.x[0] for uz, _ in inits], axis=-1); Z = np.stack([uz.x[1] for uz, _ in inits], axis=-1); Y = np.stack([uz.x[2] for uz, _ in inits], axis=-1)
+    batch = smm.pde_solve_raw(p, ql, U, Z, Y, dt=1e-3, nsteps=6, savesteps=[6], precision="f32")
+    split = smm.pde_solve_raw(p, ql, U, Z, Y, dt=1e-3, nsteps=6, savesteps=[2, 6], precision="f32")
+    np.testing.assert_array_equal(split["us"][..., 1, :], batch["us"][..., 0, :])
+    np.testing.assert_array_equal(split["ys"][..., 1, :], batch["ys"][..., 0, :])
+    for b in range(3):
+        solo = smm.pde_solve_raw(p, [ql[b]], U[..., b:b + 1], Z[..., b:b + 1], Y[..., b:b + 1], dt=1e-3, nsteps=6, savesteps=[6], precision="f32")
+        np.testing.assert_array_equal(solo["us"][..., 0, 0], batch["us"][..., 0, b])
+    # (c)
+    q = smm.parameters(eta=1.0)
+    po, qo = oracle_p(p), A_default_q(eta=1.0)
+    uzy0, sl, q2, ci, cm, slm = CO.prep(0.01, po, qo, start="zero", savedt=0.01, dt=1e-3, countercontrol="no")
+    u, z, y = uzy0
+    qq = q.merge(L=5, controlled_inf=ci, controlled_med=cm)
+    out = smm.pde_solve_raw(p, [qq], u, z, y, dt=1e-3, nsteps=5, savesteps=[5], precision="f32")
+    ur, zr, yr = P.rk_solve(u, z, y, 5, 1e-3, po, dict(q2), ci, cm)
+    assert rel(out["us"][..., 0, 0], ur) < TOL32 and np.abs(out["ys"][..., 0, 0] - yr).max() < 1e-6
