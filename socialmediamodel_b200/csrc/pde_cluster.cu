@@ -82,15 +82,17 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
   static_assert(A_ > 0 && NTC % P == 0 && RPC * Nx <= NTC && (RPC % 2) == 0, "unsupported shape");
   constexpr FftDims d = {P, M_, A_, 3};
   constexpr int cs = P + 1, hp1 = P / 2 + 1, NXP = Nx + 2, nP = NTC / P, nH = NTC / hp1, nR = NTC / Nx;
-  constexpr int UPS = (RPC + 2) * NXP;  // plane stride of the state tiles
+  constexpr int UPS = (RPC + 2) * NXP;  // stride between influencers in the state tiles (float2 units)
   const int rank = (int)cluster.block_rank(), b = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NTC / 32;
   const Lay l = make_lay(L, Nx, Ny, P, RPC, CPC);
   extern __shared__ __align__(16) unsigned char smem[];
-  float* const U0 = reinterpret_cast<float*>(smem + l.U[0]);
-  float* const U1 = reinterpret_cast<float*>(smem + l.U[1]);
-  float* un = reinterpret_cast<float*>(smem + l.un);
-  float* acc = reinterpret_cast<float*>(smem + l.acc);
+  // state tiles: the two media planes of an influencer interleaved, U[j][row][x] = (u_{j,medium 0}, u_{j,medium 1}): the stencil
+  // treats them as one packed FP32x2 value (same formulas, per-medium constants in the two halves)
+  float2* const U0 = reinterpret_cast<float2*>(smem + l.U[0]);
+  float2* const U1 = reinterpret_cast<float2*>(smem + l.U[1]);
+  float2* un = reinterpret_cast<float2*>(smem + l.un);    // [j][row][x] pairs, like the tiles
+  float2* acc = reinterpret_cast<float2*>(smem + l.acc);
   float* sFx = reinterpret_cast<float*>(smem + l.Fx);
   float* sFy = reinterpret_cast<float*>(smem + l.Fy);
   float* rho = reinterpret_cast<float*>(smem + l.rho);
@@ -107,7 +109,8 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
   // ODE unknowns and stage coefficients (Float64), replicated in every CTA
   __shared__ double c_y[LMAX][2], c_z[2][2], c_dy[LMAX][2], c_dz[2][2], c_R[2][LMAX];
   __shared__ double o_yn[LMAX][2], o_zn[2][2], o_ya[LMAX][2], o_za[2][2];
-  __shared__ float s_yx[LMAX], s_yy[LMAX], s_R[2][LMAX], s_zx[2], s_zy[2];
+  __shared__ float s_yx[LMAX], s_yy[LMAX];
+  __shared__ float2 s_R2[LMAX], s_bx2[LMAX], s_by2[LMAX];  // per influencer, the two media in the halves: rates, b y_j + c z_i
 
   const int r0 = min(rank * RPC, Ny), r1 = min(r0 + RPC, Ny), nr = r1 - r0;    // grid rows of this CTA
   const int k0 = min(rank * CPC, hp1), k1 = min(k0 + CPC, hp1), nc = k1 - k0;  // spectrum columns of this CTA
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
   const int fp_src = fp_up ? P - fp_k : fp_k;
 
   // ---- load: tables, this CTA's rows of the state, the ODE unknowns ----------------------------------------------------
-  for (size_t e = tid; e < (l.un - l.U[0]) / 4; e += NTC) U0[e] = 0.f;  // both state buffers incl. halos
+  for (size_t e = tid; e < (l.un - l.U[0]) / 8; e += NTC) U0[e] = make_float2(0.f, 0.f);  // both state buffers incl. halos
   for (int e = tid; e < RPC * NXP; e += NTC) sFx[e] = 0.f;
   for (int e = tid; e < (RPC + 2) * Nx; e += NTC) sFy[e] = 0.f;
   for (int e = tid; e < P; e += NTC) tw[e] = static_cast<const float2*>(A.tw)[e];
@@ -141,7 +144,10 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
     for (int c = cP; c < nc; c += nP) kh[(k3 * CPC + c) * P + tP] = static_cast<const float2*>(A.khat)[((size_t)k3 * hp1 + k0 + c) * P + tP];
   __syncthreads();
   if (pt) {
-    for (int p = 0; p < NP; p++) U0[p * UPS + (tr + 1) * NXP + tx + 1] = ug[(size_t)p * plane + (size_t)(r0 + tr) * A.Pw + tx];
+    for (int j = 0; j < L; j++) {
+      const size_t o = (size_t)(r0 + tr) * A.Pw + tx;
+      U0[j * UPS + (tr + 1) * NXP + tx + 1] = make_float2(ug[(size_t)(2 * j) * plane + o], ug[(size_t)(2 * j + 1) * plane + o]);
+    }
     rho[tr * Nx + tx] = rhog[(size_t)(r0 + tr) * A.Pw + tx];
   }
   if (tid < L) {
@@ -154,17 +160,20 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
     for (int dd = 0; dd < 2; dd++) { c_z[tid][dd] = cfg.z[tid][dd]; c_dz[tid][dd] = cfg.dz[tid][dd]; o_zn[tid][dd] = odg.zn[tid][dd]; o_za[tid][dd] = 0.0; }
   }
   __syncthreads();
+  const float pb = (float)in.b, pc = (float)in.c;
   auto refresh_f32 = [&]() {
     if (tid < L) {
-      s_yx[tid] = (float)c_y[tid][0]; s_yy[tid] = (float)c_y[tid][1];
-      s_R[0][tid] = (float)c_R[0][tid]; s_R[1][tid] = (float)c_R[1][tid];
+      const float yx = (float)c_y[tid][0], yy = (float)c_y[tid][1];
+      s_yx[tid] = yx; s_yy[tid] = yy;
+      s_R2[tid] = make_float2((float)c_R[0][tid], (float)c_R[1][tid]);
+      s_bx2[tid] = make_float2(pb * yx + pc * (float)c_z[0][0], pb * yx + pc * (float)c_z[1][0]);
+      s_by2[tid] = make_float2(pb * yy + pc * (float)c_z[0][1], pb * yy + pc * (float)c_z[1][1]);
     }
-    if (tid < 2) { s_zx[tid] = (float)c_z[tid][0]; s_zy[tid] = (float)c_z[tid][1]; }
   };
   refresh_f32();
   cluster.sync();  // every CTA of the cluster is resident and initialised before the first remote store
 
-  const float pa = (float)in.a, pb = (float)in.b, pc = (float)in.c, D = (float)in.D;
+  const float pa = (float)in.a, D = (float)in.D;
   const float h = (float)A.dx, ih = (float)(1.0 / A.dx), ih2 = (float)(1.0 / (A.dx * A.dx));
   const float Ddx = (float)(in.D / A.dx);  // pde.jl:231-234 (Q12); the reference builds the boundary rows from dx for both axes
   const float bc = pb + pc;
@@ -175,10 +184,10 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
   const bool x_lo = tx == 0, x_hi = tx == Nx - 1, y_lo = gy == 0, y_hi = gy == Ny - 1;
   // remote views of the neighbours' tiles (rows above / below this CTA's)
   const bool has_up = nr > 0 && r0 > 0, has_dn = nr > 0 && r1 < Ny;
-  const float* const upU0 = has_up ? cluster.map_shared_rank(U0, rank - 1) : nullptr;
-  const float* const upU1 = has_up ? cluster.map_shared_rank(U1, rank - 1) : nullptr;
-  const float* const dnU0 = has_dn ? cluster.map_shared_rank(U0, rank + 1) : nullptr;
-  const float* const dnU1 = has_dn ? cluster.map_shared_rank(U1, rank + 1) : nullptr;
+  const float2* const upU0 = has_up ? cluster.map_shared_rank(U0, rank - 1) : nullptr;
+  const float2* const upU1 = has_up ? cluster.map_shared_rank(U1, rank - 1) : nullptr;
+  const float2* const dnU0 = has_dn ? cluster.map_shared_rank(U0, rank + 1) : nullptr;
+  const float2* const dnU1 = has_dn ? cluster.map_shared_rank(U1, rank + 1) : nullptr;
   float2* A_dst = cluster.map_shared_rank(Arecv, tk_owner) + tk_kc * Ny + r0;          // P1: column tk of the owner's inbox
   // ---- P5 (deferred): the ODE unknowns of the stage just finished.  Every CTA adds the 16 partial moment sets with the same
   // shuffle tree and advances the influencer / media ODEs (pde.jl:239-265) redundantly in Float64: identical results
@@ -250,12 +259,12 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
 
   for (int step = 0; step < A.nsteps; step++) {
     if (pt)  // u_n of this step
-      for (int p = 0; p < NP; p++) un[(p * RPC + tr) * Nx + tx] = (cur ? U1 : U0)[p * UPS + (tr + 1) * NXP + tx + 1];
+      for (int j = 0; j < L; j++) un[(j * RPC + tr) * Nx + tx] = (cur ? U1 : U0)[j * UPS + (tr + 1) * NXP + tx + 1];
     for (int s = 0; s < A.nstages; s++) {
       const PdeClusterStage S = A.st[s];
       const bool last = s == A.nstages - 1;
-      float* Uc = cur ? U1 : U0;
-      float* Un = cur ? U0 : U1;
+      float2* Uc = cur ? U1 : U0;
+      float2* Un = cur ? U0 : U1;
       DBG(0);
       // ---- P1: row transforms of the density sum ------------------------------------------------------------------------
       if (pending) ode_sums();  // moments of the previous stage (complete since its last cluster barrier)
@@ -326,11 +335,11 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
           RW[(k3 * npe + pr) * cs + swzP] = make_float2(a.x - bb.y, a.y + bb.x);  // A + i B
         }
       if (tr < nR) {
-        const float* un_ = cur ? upU1 : upU0;
-        const float* dn_ = cur ? dnU1 : dnU0;
-        for (int p = tr; p < NP; p += nR) {
-          if (un_) Uc[p * UPS + tx + 1] = un_[p * UPS + RPC * NXP + tx + 1];
-          if (dn_) Uc[p * UPS + (nr + 1) * NXP + tx + 1] = dn_[p * UPS + NXP + tx + 1];
+        const float2* un_ = cur ? upU1 : upU0;
+        const float2* dn_ = cur ? dnU1 : dnU0;
+        for (int j = tr; j < L; j += nR) {
+          if (un_) Uc[j * UPS + tx + 1] = un_[j * UPS + RPC * NXP + tx + 1];
+          if (dn_) Uc[j * UPS + (nr + 1) * NXP + tx + 1] = dn_[j * UPS + NXP + tx + 1];
         }
       }
       __syncthreads();
@@ -363,53 +372,50 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
         // plane-independent parts of the velocity a F + b (y_j - x) + c (z_i - x)   (pde.jl:214)
         const float vxc0 = pa * fx[0] - bc * X, vxm0 = pa * fx[-1] - bc * (X - h), vxp0 = pa * fx[1] - bc * (X + h);
         const float vyc0 = pa * fy[0] - bc * Y, vym0 = pa * fy[-Nx] - bc * (Y - h), vyp0 = pa * fy[Nx] - bc * (Y + h);
-        const float* tc = Uc + (r + 1) * NXP + x + 1;  // centre of plane 0
-        constexpr int ps = UPS;                        // plane stride
-        float rsum[2] = {0.f, 0.f}, gsum[2] = {0.f, 0.f};
+        const float2* tc = Uc + (r + 1) * NXP + x + 1;  // centre, influencer 0
+        const float2 m1 = make_float2(-1.f, -1.f);
+        auto sub2 = [&](float2 a_, float2 b_) { return fma2(b_, m1, a_); };
+        auto bc2 = [](float v) { return make_float2(v, v); };
+        float2 rsum = make_float2(0.f, 0.f), gsum = rsum;   // per medium: sum of densities and of rates (pde.jl:220-225)
         float E[LT];
 #pragma unroll
         for (int j = 0; j < L; j++) {
           const float ex = X - s_yx[j], ey = Y - s_yy[j];
           E[j] = w_of_r2(fmaf(ex, ex, ey * ey));
-#pragma unroll
-          for (int i = 0; i < 2; i++) {
-            rsum[i] += tc[(j * 2 + i) * ps];
-            gsum[i] += E[j] * s_R[i][j];
-          }
+          rsum = add2(rsum, tc[j * UPS]);
+          gsum = fma2(bc2(E[j]), s_R2[j], gsum);
         }
-        float rs_out = 0.f;
+        float2 rs2 = make_float2(0.f, 0.f);
+        const float2 hih = bc2(0.5f * ih), ih_2 = bc2(ih), ih2_2 = bc2(ih2), Dd2 = bc2(Ddx), D2 = bc2(D);
 #pragma unroll
         for (int j = 0; j < L; j++) {
-#pragma unroll
-          for (int i = 0; i < 2; i++) {
-            const int p = j * 2 + i;
-            const float* tp = tc + p * ps;
-            const float c = tp[0], vxm = tp[-1], vxp = tp[1], vym = tp[-NXP], vyp = tp[NXP];
-            const float bxv = pb * s_yx[j] + pc * s_zx[i], byv = pb * s_yy[j] + pc * s_zy[i];
-            const float fxc = c * (vxc0 + bxv), fxm = vxm * (vxm0 + bxv), fxp = vxp * (vxp0 + bxv);
-            const float fyc = c * (vyc0 + byv), fym = vym * (vym0 + byv), fyp = vyp * (vyp0 + byv);
-            // divergence with C (pde.jl:79-87,216-217), diffusion with MassM (pde.jl:68-77,228)
-            float ddx = (fxp - fxm) * (0.5f * ih), lapx = (vxm - 2.f * c + vxp) * ih2;
-            float ddy = (fyp - fym) * (0.5f * ih), lapy = (vym - 2.f * c + vyp) * ih2, bnd = 0.f;
-            if (x_lo) { ddx = (fxp - fxc) * ih; lapx = (vxp - c) * ih2; bnd -= Ddx * fxc; }
-            if (x_hi) { ddx = (fxc - fxm) * ih; lapx = (vxm - c) * ih2; bnd += Ddx * fxc; }
-            if (y_lo) { ddy = (fyp - fyc) * ih; lapy = (vyp - c) * ih2; bnd -= Ddx * fyc; }
-            if (y_hi) { ddy = (fyc - fym) * ih; lapy = (vym - c) * ih2; bnd += Ddx * fyc; }
-            const float G = E[j] * s_R[i][j];
-            const float reac = -c * (gsum[i] - G) + G * (rsum[i] - c);
-            const float k = D * (lapx + lapy) + bnd - (ddx + ddy) + reac;  // pde.jl:236
-            const int o = (p * RPC + r) * Nx + x;
-            const float unp = un[o];
-            float out = dtC * k;
-            if (dtA != 0.f) out += dtA * unp;
-            if (dtB != 0.f) out += dtB * c;
-            if (S.acc == 1) acc[o] = unp + dtw * k;            // ACC_INIT
-            else if (S.acc == 2) acc[o] = acc[o] + dtw * k;    // ACC_ADD
-            else if (S.acc == 3) out = acc[o] + dtw * k;       // ACC_FINAL
-            Un[p * ps + (r + 1) * NXP + x + 1] = out;
-            rs_out += out;
-          }
+          const float2* tp = tc + j * UPS;
+          const float2 c = tp[0], vxm = tp[-1], vxp = tp[1], vym = tp[-NXP], vyp = tp[NXP];
+          const float2 bxv = s_bx2[j], byv = s_by2[j];  // b y_j + c z_i for the two media
+          const float2 fxc = mul2(c, add2(bc2(vxc0), bxv)), fxm = mul2(vxm, add2(bc2(vxm0), bxv)), fxp = mul2(vxp, add2(bc2(vxp0), bxv));
+          const float2 fyc = mul2(c, add2(bc2(vyc0), byv)), fym = mul2(vym, add2(bc2(vym0), byv)), fyp = mul2(vyp, add2(bc2(vyp0), byv));
+          // divergence with C (pde.jl:79-87,216-217), diffusion with MassM (pde.jl:68-77,228)
+          float2 ddx = mul2(sub2(fxp, fxm), hih), lapx = mul2(fma2(bc2(-2.f), c, add2(vxm, vxp)), ih2_2);
+          float2 ddy = mul2(sub2(fyp, fym), hih), lapy = mul2(fma2(bc2(-2.f), c, add2(vym, vyp)), ih2_2), bnd = make_float2(0.f, 0.f);
+          if (x_lo) { ddx = mul2(sub2(fxp, fxc), ih_2); lapx = mul2(sub2(vxp, c), ih2_2); bnd = sub2(bnd, mul2(Dd2, fxc)); }
+          if (x_hi) { ddx = mul2(sub2(fxc, fxm), ih_2); lapx = mul2(sub2(vxm, c), ih2_2); bnd = fma2(Dd2, fxc, bnd); }
+          if (y_lo) { ddy = mul2(sub2(fyp, fyc), ih_2); lapy = mul2(sub2(vyp, c), ih2_2); bnd = sub2(bnd, mul2(Dd2, fyc)); }
+          if (y_hi) { ddy = mul2(sub2(fyc, fym), ih_2); lapy = mul2(sub2(vym, c), ih2_2); bnd = fma2(Dd2, fyc, bnd); }
+          const float2 G = mul2(bc2(E[j]), s_R2[j]);
+          const float2 reac = sub2(mul2(G, sub2(rsum, c)), mul2(c, sub2(gsum, G)));
+          const float2 k = add2(sub2(fma2(D2, add2(lapx, lapy), bnd), add2(ddx, ddy)), reac);  // pde.jl:236
+          const int o = (j * RPC + r) * Nx + x;
+          const float2 unp = un[o];
+          float2 out = mul2(bc2(dtC), k);
+          if (dtA != 0.f) out = fma2(bc2(dtA), unp, out);
+          if (dtB != 0.f) out = fma2(bc2(dtB), c, out);
+          if (S.acc == 1) acc[o] = fma2(bc2(dtw), k, unp);            // ACC_INIT
+          else if (S.acc == 2) acc[o] = fma2(bc2(dtw), k, acc[o]);    // ACC_ADD
+          else if (S.acc == 3) out = fma2(bc2(dtw), k, acc[o]);       // ACC_FINAL
+          Un[j * UPS + (r + 1) * NXP + x + 1] = out;
+          rs2 = add2(rs2, out);
         }
+        const float rs_out = rs2.x + rs2.y;
         rho[r * Nx + x] = rs_out;
       }
       __syncthreads();
@@ -420,7 +426,8 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
         for (int x = lane; x < Nx; x += 32) {
           float cs0 = 0.f, csy = 0.f;
           for (int r = 0; r < nr; r++) {
-            const float v = Un[p * UPS + (r + 1) * NXP + x + 1];
+            const float2 v2 = Un[(p >> 1) * UPS + (r + 1) * NXP + x + 1];
+            const float v = (p & 1) ? v2.y : v2.x;
             cs0 += v;
             csy += v * (float)(A.gy0 + (r0 + r) * A.dx);
           }
@@ -450,7 +457,11 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
   }
   // ---- store -------------------------------------------------------------------------------------------------------------
   if (pt) {
-    for (int p = 0; p < NP; p++) ug[(size_t)p * plane + (size_t)(r0 + tr) * A.Pw + tx] = (cur ? U1 : U0)[p * UPS + (tr + 1) * NXP + tx + 1];
+    for (int j = 0; j < L; j++) {
+      const float2 v = (cur ? U1 : U0)[j * UPS + (tr + 1) * NXP + tx + 1];
+      const size_t o = (size_t)(r0 + tr) * A.Pw + tx;
+      ug[(size_t)(2 * j) * plane + o] = v.x; ug[(size_t)(2 * j + 1) * plane + o] = v.y;
+    }
     rhog[(size_t)(r0 + tr) * A.Pw + tx] = rho[tr * Nx + tx];
   }
   if (rank == 0) {
