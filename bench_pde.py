@@ -28,17 +28,22 @@ def run_pde_c3(ctx, steps=400, dt=1e-3):
     pb = smm.PDEBatch(p, [q2], *uzy0.x, precision="f32", ctx=ctx)
     pb.step(dt, 20); ctx.sync()
     ms = []
+    l0 = ctx.launches
     for _ in range(3):
         pb.step(dt, steps); ctx.sync()
         ms.append(ctx.kernel_ms(4) / steps)
+    launches_per_step = (ctx.launches - l0) / (3 * steps)
     us_step = float(np.median(ms)) * 1e3
     u, z, y = pb.read()
     pb.close()
     cells = p.N_x * p.N_y * 2 * 4
-    return dict(workload="C3 PDEsolve 89x89x2x4, uniforminit, RK4 dt=1e-3, one instance, CUDA graph per step",
+    cluster = launches_per_step < 1
+    how = ("all steps of a call in ONE launch: the instance lives in the shared memory of a 16-CTA thread-block cluster (pde_cluster.cu)"
+           if cluster else "16 kernels per step in a CUDA graph")
+    return dict(workload=f"C3 PDEsolve 89x89x2x4, uniforminit, RK4 dt=1e-3, one instance, {how}",
                 metric="pde_cell_steps_per_s", value=cells / (us_step * 1e-6), us_per_step=us_step,
-                kernels_per_step=16, mass=float(u.sum() * p.dV), finite=bool(np.isfinite(u).all()),
-                note="63 368 cells: launch/latency-bound, not HBM-bound (SURVEY 8d)")
+                launches_per_step=launches_per_step, mass=float(u.sum() * p.dV), finite=bool(np.isfinite(u).all()),
+                note="63 368 cells: latency-bound, not HBM-bound (SURVEY 8d); SMM_PDE_CLUSTER=0 gives the kernel chain (90 us per step)")
 
 
 def run_pde_sweep(ctx, dx=0.025, B=64, steps=10, dt=None):

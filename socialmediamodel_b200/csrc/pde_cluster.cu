@@ -255,7 +255,27 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
     }
   }
   };
+  // ---- P1: row transforms of the density sum (two real rows per complex transform), half spectra to the column owners.
+  // It needs this CTA's rows only, so it runs right behind the stencil that produced them, in front of the SAME cluster
+  // barrier that publishes the moments: two barriers per stage, not three.
+  auto rows_forward = [&]() {
+    for (int pr = cP; pr < np; pr += nP) {
+      float2 v = make_float2(0.f, 0.f);
+      if (tP < Nx) v = make_float2(rho[(2 * pr) * Nx + tP], 2 * pr + 1 < nr ? rho[(2 * pr + 1) * Nx + tP] : 0.f);
+      RW[pr * cs + swzP] = v;
+    }
+    __syncthreads();
+    fft_dif_fwd<float>(RW, np, cs, d, tw);
+    if (ck < nH)
+      for (int pr = ck; pr < np; pr += nH) {
+        const float2 zk = RW[pr * cs + tk_pk], zm = RW[pr * cs + tk_pm];
+        A_dst[2 * pr] = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+        if (2 * pr + 1 < nr) A_dst[2 * pr + 1] = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
+      }
+  };
   int cur = 0;
+  rows_forward();
+  cluster.sync();
 
   for (int step = 0; step < A.nsteps; step++) {
     if (pt)  // u_n of this step
@@ -266,26 +286,9 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
       float2* Uc = cur ? U1 : U0;
       float2* Un = cur ? U0 : U1;
       DBG(0);
-      // ---- P1: row transforms of the density sum ------------------------------------------------------------------------
-      if (pending) ode_sums();  // moments of the previous stage (complete since its last cluster barrier)
-      for (int pr = cP; pr < np; pr += nP) {
-        float2 v = make_float2(0.f, 0.f);
-        if (tP < Nx) v = make_float2(rho[(2 * pr) * Nx + tP], 2 * pr + 1 < nr ? rho[(2 * pr + 1) * Nx + tP] : 0.f);
-        RW[pr * cs + swzP] = v;
-      }
-      __syncthreads();
-      fft_dif_fwd<float>(RW, np, cs, d, tw);
-      DBG(1);
-      if (ck < nH)
-        for (int pr = ck; pr < np; pr += nH) {
-          const float2 zk = RW[pr * cs + tk_pk], zm = RW[pr * cs + tk_pm];
-          A_dst[2 * pr] = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
-          if (2 * pr + 1 < nr) A_dst[2 * pr + 1] = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
-        }
-      DBG(2);
-      cluster.sync();
       DBG(3);
       // ---- P2: column transforms, three kernel spectra -------------------------------------------------------------------
+      if (pending) ode_sums();  // moments of the previous stage (complete since its cluster barrier)
       for (int c = cP; c < nc; c += nP) R[c * cs + swzP] = tP < Ny ? Arecv[c * Ny + tP] : make_float2(0.f, 0.f);
       __syncthreads();
       fft_dif_fwd<float>(R, nc, cs, d, tw);
@@ -442,6 +445,7 @@ __global__ void __launch_bounds__(NTC, 1) pde_cluster_kernel(const PdeClusterArg
         cluster.map_shared_rank(mom_all, dest)[rank * NV + v] = part[v];
       }
       DBG(13);
+      if (!(last && step == A.nsteps - 1)) rows_forward();  // P1 of the next stage
       cluster.sync();
       DBG(14);
       pending = true; Sp = S; lastp = last;

@@ -13,7 +13,9 @@ lib = _lib.load()
 buf = (ctypes.c_ulonglong * 64)()
 print("rc", lib.smm_debug_cluster_times(buf))
 t = [buf[i] for i in range(16)]
-names = ["P1 fill", "P1 fft", "P1 scatter", "sync1", "P2 fill+fwd", "P2 mul+inv", "P2 scatter", "sync2", "P3 fill+halo", "P3 inv", "P3 F", "sync3", "P4 stage", "P4 moments+scatter", "sync4", "P5"]
-for i in range(1, 16):
-    print(f"{names[i-1]:22s} {t[i] - t[i-1]:6d} ns")
-print("stage total", t[15] - t[0])
+names = {1: "(start) -> P2 entry", 4: "P2 fill+fwd", 5: "P2 mul+inv", 6: "P2 scatter", 7: "cluster barrier", 8: "P3 fill+halo+ODE", 9: "P3 inverse", 10: "P3 force", 11: "syncthreads",
+         12: "P4 stencil", 13: "P4 moments+scatter", 14: "P1' rows fwd + barrier", 15: "end"}
+order = [3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15]
+for a_, b_ in zip(order[:-1], order[1:]):
+    print(f"{names.get(b_, ''):26s} {t[b_] - t[a_]:6d} ns")
+print("stage total", t[15] - t[3])
