@@ -70,6 +70,28 @@ def test_c4_refined_grid_properties(monkeypatch):
     assert np.isfinite(batch["us"]).all()
 
 
+def test_c4_queued_steps_reproducible_and_close_to_float64(monkeypatch):
+    """Eight RK4 steps queued back to back (no host synchronisation in between) on the throughput path: three runs give the
+    same bits and stay within 2e-6 of the Float64 kernels.  This is the configuration in which a missing barrier between the
+    table loads and the first pass of the fast FFT kernels showed up as run-to-run differences of up to 7e-5 (DESIGN.md 6.2);
+    with one step per call it never did."""
+    monkeypatch.setenv("SMM_FFT_FAST", "1")
+    monkeypatch.setenv("SMM_PDE_STAGE2", "1")
+    monkeypatch.setenv("SMM_PDE_PDL", "0")       # programmatic dependent launch hid the race: test without it
+    p = smm.PDEconstruct(dx=0.0125)
+    qs = [smm.parameters(a=0.5, sigma=0.75), smm.parameters(a=2.0, b=6.0, eta=1.0), smm.parameters(c=4.0, sigma=0.25)]
+    inits = [smm.constructinitial("4inf", (p, q)) for q in qs]
+    ql = [qq for _, qq in inits]
+    rng = np.random.default_rng(3)
+    U = np.stack([uz.x[0] * (1 + 0.2 * rng.random(uz.x[0].shape)) for uz, _ in inits], axis=-1)
+    Z = np.stack([uz.x[1] for uz, _ in inits], axis=-1); Y = np.stack([uz.x[2] for uz, _ in inits], axis=-1)
+    runs = [smm.pde_solve_raw(p, ql, U, Z, Y, dt=5e-5, nsteps=8, savesteps=[8], precision="f32")["us"] for _ in range(3)]
+    np.testing.assert_array_equal(runs[1], runs[0])
+    np.testing.assert_array_equal(runs[2], runs[0])
+    ref = smm.pde_solve_raw(p, ql, U, Z, Y, dt=5e-5, nsteps=8, savesteps=[8], precision="f64")["us"]
+    assert np.abs(runs[0] - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
 def test_c5_full_population_properties():
     import torch
     n, L, k = 10_000_000, 64, 16
