@@ -428,3 +428,13 @@ def test_cluster_steps_batch_resume_and_controlled_influencer(monkeypatch):
     out = smm.pde_solve_raw(p, [qq], u, z, y, dt=1e-3, nsteps=5, savesteps=[5], precision="f32")
     ur, zr, yr = P.rk_solve(u, z, y, 5, 1e-3, po, dict(q2), ci, cm)
     assert rel(out["us"][..., 0, 0], ur) < TOL32 and np.abs(out["ys"][..., 0, 0] - yr).max() < 1e-6
+    # (d) the same controlled L = 5 instance on the default 89 x 89 grid (the largest shape the cluster form holds), against
+    # the Float64 kernel chain
+    pd = smm.PDEconstruct()
+    uzy0, sl, q2, ci, cm, slm = CO.prep(0.01, oracle_p(pd), qo, start="zero", savedt=0.01, dt=1e-3, countercontrol="no")
+    u, z, y = uzy0
+    l0 = smm.Context.default().launches
+    out = smm.pde_solve_raw(pd, [qq], u, z, y, dt=1e-3, nsteps=8, savesteps=[8], precision="f32")
+    assert smm.Context.default().launches - l0 < 8 * 8                               # one launch for the 8 steps, not a chain
+    ref = smm.pde_solve_raw(pd, [qq], u, z, y, dt=1e-3, nsteps=8, savesteps=[8], precision="f64")
+    assert rel(out["us"], ref["us"]) < TOL32 and np.abs(out["ys"] - ref["ys"]).max() < 1e-6
