@@ -1322,7 +1322,10 @@ extern "C" int smm_pde_batch_create(smm_ctx* ctx, const smm_grid* grid, const sm
   // SMM_PDE_CLUSTER=0 / 1 disables / forces it (where the shape allows).
   if (pb->fft && precision == SMM_PREC_F32) {
     const char* ev = getenv("SMM_PDE_CLUSTER");
-    bool want = (size_t)B * CLUSTER_CTAS <= (size_t)ctx->sm_count;
+    // measured break-even against the kernel chain (tools/scratch/cluster_batch.py; 8 clusters run at once, one per GPC):
+    // 47 x 47: 34 us per step up to 8 instances, 101 vs 114 us at 16, equal at 27; 89 x 89: 55 us up to 8, 110 vs 121 us at 9,
+    // 164 vs 149 us at 16
+    bool want = B <= (grid->Nx <= 47 ? 24 : 10);
     if (ev && ev[0] == '0') want = false;
     if (ev && ev[0] == '1') want = true;
     if (want) {
