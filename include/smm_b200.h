@@ -119,7 +119,8 @@ double smm_ctx_kernel_ms(const smm_ctx* ctx, int which);
 
 /* Measured denominators for the rooflines MEASURED_PEAKS.json does not carry, and for the floor of the end-to-end
  * ensemble call (bench.py): each runs a few-line kernel / copy, timed with CUDA events after a warm-up.
- *   SMM_MB_MUFU   result = G ex2.approx/s          (bound of the dense ABM pair loop)
+ *   SMM_MB_MUFU   result = G MUFU operations/s; size selects the operation: 0 ex2.approx, 1 sqrt.approx, 2 rsqrt.approx,
+ *                 3 sqrt then ex2 (the dense ABM pair loop's chain), 4 rsqrt then ex2, 5 lg2, 6 rcp, 7 sin
  *   SMM_MB_GATHER result = G random 8-byte gathers/s from an L2-resident table of `size` entries (C5 neighbour reads)
  *   SMM_MB_LDS    result = GB/s of conflict-free 16-byte shared-memory loads (bound of the FFT passes)
  *   SMM_MB_D2H    result = GB/s of a `size`-byte device -> pinned-host copy

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmm_b200.so")
+# SMM_B200_LIB: another build of the same library (A/B timing of kernel variants); default: the in-tree build
+LIB_PATH = os.environ.get("SMM_B200_LIB") or os.path.join(_HERE, "libsmm_b200.so")
 
 PREC = {"f32": 0, "f64": 1, 0: 0, 1: 1}
 SCHEME = {"euler": 0, "heun": 1, "ssprk3": 2, "rk4": 3}

@@ -95,7 +95,15 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
   constexpr int kThreads = THREADS;  // shadows the namespace constant inside this kernel
   const AbmConst& K = A.k;
   const int n = K.n, L = K.L, M = K.M, NT = A.NT;
-  const int r = blockIdx.x;
+  // Step chunks (A.chunk_steps > 0): CTA (chunk, r) = blockIdx.x = chunk * R + r runs steps [k0, k1) of realization r and
+  // hands the state to CTA (chunk + 1, r) through global memory.  Why: the warp schedulers favour the CTAs that were
+  // launched first (measured: of the 7 CTAs of an SM the first finishes 200 steps after 4.1 ms, the last after 5.9 ms), so a
+  // one-CTA-per-realization grid ends in a long tail at falling occupancy.  With chunks, the slot of a CTA that finishes
+  // early is refilled at once by the next chunk of an early realization; the SMs stay full until the last chunk.
+  // Blocks are dispatched in index order, so the predecessor of a waiting CTA is always resident or done.
+  const int r = (int)(blockIdx.x % (unsigned)A.R), chunk = (int)(blockIdx.x / (unsigned)A.R);
+  const int k0 = A.chunk_steps > 0 ? chunk * A.chunk_steps : 0;
+  const int k1 = A.chunk_steps > 0 ? min(NT, k0 + A.chunk_steps) : NT;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kThreads / 32;
   const uint32_t rglob = (uint32_t)(A.first_realization + r);
 
@@ -125,21 +133,49 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
   const int G = (n + 31) >> 5, D = G >> 1, NG = G * 32;
   // xy2[g][i] = log2(e) * (x_a, x_b, y_a, y_b) of the agents a = g*32 + (i & 31), b = g*32 + ((i + 16) & 31), i < 64
   float4* xy2 = reinterpret_cast<float4*>(smem + ((reinterpret_cast<unsigned char*>(st + npad) - smem + 15) & ~(size_t)15));
-  float* part = reinterpret_cast<float*>(xy2 + (SYM ? G * kTab : 0));
+  // SYM: class sums of the current state per warp, in fixed point: wsum[warp][bin] = (sum qx, sum qy, count, sum of states)
+  // with q = round(position * qscale).  Integer sums are exact and associative: the class means do not depend on the
+  // CTA width or on which warp holds which agent.
+  int4* wsum = reinterpret_cast<int4*>(xy2 + (SYM ? G * kTab : 0));
+  float* part = reinterpret_cast<float*>(wsum + (SYM ? nwarps * (L + M) : 0));
 
-  // ---- load the initial condition --------------------------------------------------------
-  const real* x0 = static_cast<const real*>(A.x0) + (size_t)r * 2 * n;
-  for (int j = tid; j < n; j += kThreads) {
-    xbuf0[j] = mk2(x0[j], x0[n + j]);
-    fol[j] = A.follow0[(size_t)r * n + j];
-    st[j] = A.state[(size_t)r * n + j];
+  // ---- load the initial condition, or the state the previous chunk of this realization left -------------------------
+  if (chunk > 0) {
+    const real* hand_x = static_cast<const real*>(A.hand_x) + (size_t)r * 2 * n;  // same layouts as x0 / follow0 / inf0 / media0
+    const int32_t* hand_f = A.hand_f + (size_t)r * n;
+    const double* hand_inf = A.hand_inf + (size_t)r * 2 * L;
+    const double* hand_med = A.hand_med + (size_t)r * 2 * M;
+    if (tid == 0) {
+      unsigned done;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(done) : "l"(A.chunk_done + r) : "memory");
+        if (done < (unsigned)chunk) __nanosleep(200);
+      } while (done < (unsigned)chunk);
+    }
+    __syncthreads();
+    for (int j = tid; j < n; j += kThreads) {  // L2 loads: an earlier chunk of this realization may have run on this SM
+      xbuf0[j] = mk2(__ldcg(hand_x + j), __ldcg(hand_x + n + j));
+      fol[j] = __ldcg(hand_f + j);
+      st[j] = A.state[(size_t)r * n + j];
+    }
+    if (tid < L) { infx[tid] = __ldcg(hand_inf + tid); infy[tid] = __ldcg(hand_inf + L + tid); }
+    if (tid < M) { medx[tid] = __ldcg(hand_med + tid); medy[tid] = __ldcg(hand_med + M + tid); }
+  } else {
+    const real* x0 = static_cast<const real*>(A.x0) + (size_t)r * 2 * n;
+    for (int j = tid; j < n; j += kThreads) {
+      xbuf0[j] = mk2(x0[j], x0[n + j]);
+      fol[j] = A.follow0[(size_t)r * n + j];
+      st[j] = A.state[(size_t)r * n + j];
+    }
+    if (tid < L) { infx[tid] = A.inf0[(size_t)r * 2 * L + tid]; infy[tid] = A.inf0[(size_t)r * 2 * L + L + tid]; }
+    if (tid < M) { medx[tid] = A.media0[(size_t)r * 2 * M + tid]; medy[tid] = A.media0[(size_t)r * 2 * M + M + tid]; }
   }
-  if (tid < L) { infx[tid] = A.inf0[(size_t)r * 2 * L + tid]; infy[tid] = A.inf0[(size_t)r * 2 * L + L + tid]; }
-  if (tid < M) { medx[tid] = A.media0[(size_t)r * 2 * M + tid]; medy[tid] = A.media0[(size_t)r * 2 * M + M + tid]; }
   __syncthreads();
 
   int cur = 0;        // which x buffer / inf slot holds the current state
   int next_save = 0;  // index into savesteps
+  if (chunk > 0)      // history entry k0 was written by the previous chunk
+    while (next_save < A.nsave && A.savesteps[next_save] <= k0) next_save++;
   const double sdt = sqrt(K.dt);
   const double noise_x = sdt * K.sigma;
 
@@ -199,27 +235,88 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
     }
   };
 
-  snapshot(0, xbuf0, 0);
+  // ---- SYM: the pair table and the class sums are kept up to date by the thread that moves an agent ------------------
+  // table entry of agent j (see kTab): the scaled position goes to the four places the rotated reads expect
+  auto table_put = [&](int j, float px, float py) {
+    const float sx = px * kLog2e, sy = py * kLog2e;
+    const int l = j & 31, l2 = (l + 16) & 31;
+    float4* o = xy2 + (j >> 5) * 64;
+    o[l].x = sx; o[l + 32].x = sx; o[l2].y = sx; o[l2 + 32].y = sx;
+    o[l].z = sy; o[l + 32].z = sy; o[l2].w = sy; o[l2 + 32].w = sy;
+  };
+  // positions in fixed point: |q| <= 2^22, at most 128 agents per warp and pass: the warp sums fit 32 bits
+  const float qscale = 4194304.0f / (float)fmax(fmax(fabs(K.lo0), fabs(K.hi0)), fmax(fabs(K.lo1), fabs(K.hi1)));
+  int4 wacc = make_int4(0, 0, 0, 0);  // lane b: running sums of class b (b < L: followers of influencer b; then media)
+  // one agent per lane (valid or not): every class summed over the warp with one REDUX per value; warp-uniform call
+  auto class_add = [&](bool valid, float px, float py, int f, int s) {
+    const int qx = valid ? __float2int_rn(px * qscale) : 0, qy = valid ? __float2int_rn(py * qscale) : 0;
+    const unsigned plus = __ballot_sync(0xffffffffu, valid && s == 1);
+    for (int b = 0; b < L + M; b++) {
+      const bool in = valid && (b < L ? f == b : s == (b == L ? -1 : 1));
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      if (m == 0u) continue;
+      const int rx = __reduce_add_sync(0xffffffffu, in ? qx : 0), ry = __reduce_add_sync(0xffffffffu, in ? qy : 0);
+      if (lane == b) { wacc.x += rx; wacc.y += ry; wacc.z += __popc(m); wacc.w += 2 * __popc(m & plus) - __popc(m); }
+    }
+  };
+  auto class_flush = [&]() {
+    if (lane < L + M) wsum[warp * (L + M) + lane] = wacc;
+    wacc = make_int4(0, 0, 0, 0);
+  };
+  auto class_total = [&](int b) {  // exact totals of class b over the warps
+    long long sx = 0, sy = 0; int c = 0, ss = 0;
+    for (int w = 0; w < nwarps; w++) { const int4 v = wsum[w * (L + M) + b]; sx += v.x; sy += v.y; c += v.z; ss += v.w; }
+    struct { long long sx, sy; int c, ss; } t = {sx, sy, c, ss};
+    return t;
+  };
+  auto add_numbers_sym = [&](int hist_index) {  // plotting.jl:284-307, from the class sums
+    if (A.numbers && tid < L * M) {
+      const int j = tid / M, i = tid % M;
+      const auto t = class_total(j);
+      const int v = i == 1 ? (t.c + t.ss) / 2 : (t.c - t.ss) / 2;
+      atomicAdd(reinterpret_cast<unsigned long long*>(A.numbers) + ((size_t)hist_index * L + j) * M + i, (unsigned long long)v);
+    }
+  };
+  if constexpr (SYM) {
+    static_assert(sizeof(real) == 4, "the symmetric path is FP32");
+    for (int j = tid; j < NG; j += kThreads) {
+      const real2 p = j < n ? xbuf0[j] : mk2((real)kPadPos, (real)kPadPos);  // padding agents: written once
+      table_put(j, (float)p.x, (float)p.y);
+    }
+    for (int jb = 0; jb < n; jb += kThreads) {
+      const int j = jb + tid;
+      const bool valid = j < n;
+      const real2 p = xbuf0[valid ? j : 0];
+      class_add(valid, (float)p.x, (float)p.y, fol[valid ? j : 0], st[valid ? j : 0]);
+    }
+    class_flush();
+    __syncthreads();
+  }
 
-  for (int k = 0; k < NT; k++) {
+  if (chunk == 0) snapshot(0, xbuf0, 0);
+
+#ifdef SMM_DENSE_STAMPS
+  long long st_loop = 0, st_w1 = 0, st_fin = 0, st_w2 = 0;
+  const long long st_c0 = clock64();
+  unsigned long long st_g0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_g0));
+#endif
+  for (int k = k0; k < k1; k++) {
+#ifdef SMM_DENSE_STAMPS
+    const long long t_a = clock64();
+#endif
     const real2* xc = cur ? xbuf1 : xbuf0;
     real2* xn = cur ? xbuf0 : xbuf1;
     const int nxt = cur ^ 1;
 
-    if constexpr (SYM) {
-      for (int j = tid; j < NG; j += kThreads) {
-        const real2 p = j < n ? xc[j] : mk2((real)kPadPos, (real)kPadPos);
-        const float sx = (float)p.x * kLog2e, sy = (float)p.y * kLog2e;
-        const int l = j & 31, l2 = (l + 16) & 31;
-        float4* o = xy2 + (j >> 5) * 64;
-        o[l].x = sx; o[l + 32].x = sx; o[l2].y = sx; o[l2 + 32].y = sx;
-        o[l].z = sy; o[l + 32].z = sy; o[l2].w = sy; o[l2 + 32].w = sy;
-      }
-    }
     // ---- P1: S_i, cnt_i, state sums of the OLD positions / followers (abm.jl:96-100,179-180,188-191)
-    bin_sums(xc);
-    __syncthreads();
-    add_numbers(k);
+    if constexpr (SYM) {
+      add_numbers_sym(k);  // the class sums of the current state were left by the previous step (or the prologue)
+    } else {
+      bin_sums(xc);
+      __syncthreads();
+      add_numbers(k);
+    }
 
     // ---- P2: influencer / media update from OLD x, OLD followers (abm.jl:175-198), reflect (:202-203)
     if (tid < L + M) {
@@ -244,9 +341,17 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
         }
       }
       const double nz = 1.0 / fr * sdt * sg;
-      const int cnt = bcnt[2 * tid] + bcnt[2 * tid + 1];
+      int cnt, ssum;
+      double sumx, sumy;
+      if constexpr (SYM) {
+        const auto t = class_total(tid);
+        cnt = t.c; ssum = t.ss; sumx = (double)t.sx / (double)qscale; sumy = (double)t.sy / (double)qscale;
+      } else {
+        cnt = bcnt[2 * tid] + bcnt[2 * tid + 1]; ssum = bss[2 * tid] + bss[2 * tid + 1];
+        sumx = bsx[2 * tid] + bsx[2 * tid + 1]; sumy = bsy[2 * tid] + bsy[2 * tid + 1];
+      }
       if (cnt > 0) {
-        double mcx = (bsx[2 * tid] + bsx[2 * tid + 1]) / (double)cnt, mcy = (bsy[2 * tid] + bsy[2 * tid + 1]) / (double)cnt;
+        double mcx = sumx / (double)cnt, mcy = sumy / (double)cnt;
         px = px + K.dt / fr * (mcx - px) + nz * z0;
         py = py + K.dt / fr * (mcy - py) + nz * z1;
       } else {
@@ -257,7 +362,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
       py = reflect1(py, K.lo1, K.hi1);
       if (is_inf) {
         infx[nxt * L + e] = px; infy[nxt * L + e] = py;
-        const double fr_e = (double)(bss[2 * e] + bss[2 * e + 1]) / (double)cnt;  // abm.jl:99; 0/0 = NaN (Q5)
+        const double fr_e = (double)ssum / (double)cnt;  // abm.jl:99; 0/0 = NaN (Q5)
         frac[e] = fr_e;
         finx[e] = (float)px; finy[e] = (float)py; ffr[e] = (float)fr_e;
       } else {
@@ -272,6 +377,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
     // Two agents per thread (j0, j0 + kThreads): each broadcast partner load feeds two pair
     // evaluations, and 128-thread CTAs let every realization of a 1 024-member ensemble be
     // resident at once (7 CTAs per SM) instead of two waves of 256-thread CTAs.
+    real2 moved = mk2((real)0, (real)0);  // finish(): the agent's new position (as stored) and follower
+    int fmoved = 0;
     auto finish = [&](int j, real2 xj, real ax, real ay, real ws) {
       const int sj = st[j], fj = fol[j];
       const double x = (double)xj.x, y = (double)xj.y;
@@ -301,8 +408,27 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
         decided = switch_decision_f32_guarded((float)xj.x, (float)xj.y, sj, fj, finx, finy, ffr, L, (float)K.eta, (float)K.dt,
                                               (float)u1, (float)u2, 2e-5f, &fnew);
       if (!decided) fnew = switch_decision_f64(x, y, sj, fj, infx + nxt * L, infy + nxt * L, frac, L, K.eta, K.dt, u1, u2);
-      xn[j] = mk2((real)xn0, (real)xn1);
+      moved = mk2((real)xn0, (real)xn1);
+      fmoved = fnew;
+      xn[j] = moved;
       fol[j] = fnew;  // only this thread reads fol[j] during P3
+    };
+    // SYM: partial sums of agent j, then finish(); the thread that moved the agent also writes its table entry for the next
+    // step (the pair loop is behind a barrier) and adds it to the class sums of the next step.  SLOTS = number of slot
+    // groups of the CTA form (row sums only / row and column sums).
+    auto finish_all = [&](auto total_of) {
+      for (int jb = 0; jb < n; jb += kThreads) {
+        const int j = jb + tid;
+        const bool valid = j < n;
+        if (valid) {
+          real ws, ax, ay;
+          total_of(j, ws, ax, ay);
+          finish(j, xc[j], ax, ay, ws);
+          table_put(j, (float)moved.x, (float)moved.y);
+        }
+        class_add(valid, (float)moved.x, (float)moved.y, fmoved, st[valid ? j : 0]);
+      }
+      class_flush();
     };
     if constexpr (SYM) {
       // Attraction with every unordered pair evaluated once.  Agents are split into G groups of 32; a warp
@@ -341,17 +467,28 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
         float* o = part + g * 32 + lane;
         o[0] = totw; o[NG] = totx; o[2 * NG] = toty;
       }
+#ifdef SMM_DENSE_STAMPS
+      const long long t_b = clock64();
       __syncthreads();
-      for (int j = tid; j < n; j += kThreads) {
-        real ws = part[j], ax = part[NG + j], ay = part[2 * NG + j];
+      const long long t_c = clock64();
+#else
+      __syncthreads();
+#endif
+      finish_all([&](int j, real& ws, real& ax, real& ay) {
+        ws = part[j]; ax = part[NG + j]; ay = part[2 * NG + j];
         const int hg = j >> 5;
         for (int d = 1; d <= D; d++) {
           if (2 * d == G && hg < D) break;  // that slot is only written for the upper half of the groups
           const real* o = part + (size_t)d * 3 * NG + j;
           ws += o[0]; ax += o[NG]; ay += o[2 * NG];
         }
-        finish(j, xc[j], ax, ay, ws);
-      }
+      });
+#ifdef SMM_DENSE_STAMPS
+      const long long t_d = clock64();
+      __syncthreads();
+      const long long t_e = clock64();
+      st_loop += t_b - t_a; st_w1 += t_c - t_b; st_fin += t_d - t_c; st_w2 += t_e - t_d;
+#endif
       } else {
       // Work items = tiles: NO off-diagonal tiles (d = 1..D; for even G the offset G/2 only from the lower half of the
       // groups) and G diagonal ones.  Off-diagonal tiles cost ~1.7x a diagonal one, so they are dealt first and in
@@ -385,8 +522,8 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
         o[0] = fold_w(Rs); o[NG] = fold_x(Rs); o[2 * NG] = fold_y(Rs);
       }
       __syncthreads();
-      for (int j = tid; j < n; j += kThreads) {
-        real ws = part[j], ax = part[NG + j], ay = part[2 * NG + j];
+      finish_all([&](int j, real& ws, real& ax, real& ay) {
+        ws = part[j]; ax = part[NG + j]; ay = part[2 * NG + j];
         const int hg = j >> 5;
         for (int d = 1; d <= D; d++) {  // fixed order: row sums d = 1..D, then column sums d = 1..D
           if (2 * d == G && hg >= D) break;  // tile (hg, hg + G/2) belongs to the lower half of the groups
@@ -398,8 +535,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
           const real* o = part + (size_t)(D + d) * 3 * NG + j;
           ws += o[0]; ax += o[NG]; ay += o[2 * NG];
         }
-        finish(j, xc[j], ax, ay, ws);
-      }
+      });
       }
     } else
     for (int j0 = tid; j0 < n; j0 += 2 * kThreads) {
@@ -438,7 +574,32 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
     cur = nxt;
     snapshot(k + 1, xn, cur);
   }
-  if (A.numbers) {
+#ifdef SMM_DENSE_STAMPS
+  if (THREADS == 128 && SYM && tid == 0) {
+    unsigned long long st_g1;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_g1));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    printf("cta %d chunk %d sm %u start %llu end %llu loop %lld update %lld\n", r, chunk, smid, st_g0, st_g1, st_loop / max(1, k1 - k0), st_fin / max(1, k1 - k0));
+  }
+#endif
+  if (k1 < NT) {  // hand the state to the next chunk of this realization
+    const real2* xc = cur ? xbuf1 : xbuf0;
+    real* hand_x = static_cast<real*>(A.hand_x) + (size_t)r * 2 * n;
+    int32_t* hand_f = A.hand_f + (size_t)r * n;
+    double* hand_inf = A.hand_inf + (size_t)r * 2 * L;
+    double* hand_med = A.hand_med + (size_t)r * 2 * M;
+    for (int j = tid; j < n; j += kThreads) { const real2 p = xc[j]; hand_x[j] = p.x; hand_x[n + j] = p.y; hand_f[j] = fol[j]; }
+    if (tid < L) { hand_inf[tid] = infx[cur * L + tid]; hand_inf[L + tid] = infy[cur * L + tid]; }
+    if (tid < M) { hand_med[tid] = medx[cur * M + tid]; hand_med[M + tid] = medy[cur * M + tid]; }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(A.chunk_done + r), "r"((unsigned)(chunk + 1)) : "memory");
+    return;
+  }
+  if constexpr (SYM) {
+    add_numbers_sym(NT);
+  } else if (A.numbers) {
     bin_sums(cur ? xbuf1 : xbuf0);
     __syncthreads();
     add_numbers(NT);
@@ -510,7 +671,7 @@ size_t dense_smem_bytes(int n, int L, int M, size_t real_size, bool sym, int thr
     const size_t G = (n + 31) / 32, D = G / 2;
     // 128-thread CTAs keep row sums in registers (slots 0..D); wider CTAs deal single tiles (row + column slots).
     // The difference decides whether 7 CTAs (all 1 024 realizations of C2) fit one SM's shared memory.
-    b += 16 + G * kTab * 16 + (1 + (threads == 128 ? 1 : 2) * D) * 3 * G * 32 * 4;
+    b += 16 + G * kTab * 16 + (size_t)(threads / 32) * (L + M) * 16 + (1 + (threads == 128 ? 1 : 2) * D) * 3 * G * 32 * 4;
   }
   return b;
 }
@@ -520,7 +681,8 @@ size_t dense_smem_bytes(int n, int L, int M, size_t real_size, bool sym, int thr
 template <typename real, bool SYM, int THREADS>
 static int launch_dense_t(smm_ctx* ctx, const AbmDenseArgs& A, size_t sm) {
   SMM_CUDA(ctx, cudaFuncSetAttribute(abm_dense_kernel<real, SYM, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  abm_dense_kernel<real, SYM, THREADS><<<A.R, THREADS, sm, ctx->stream>>>(A);
+  const int nchunks = A.chunk_steps > 0 ? (A.NT + A.chunk_steps - 1) / A.chunk_steps : 1;
+  abm_dense_kernel<real, SYM, THREADS><<<(unsigned)A.R * (unsigned)std::max(1, nchunks), THREADS, sm, ctx->stream>>>(A);
   return SMM_OK;
 }
 template <typename real, bool SYM>
@@ -533,7 +695,7 @@ static int launch_dense_w(smm_ctx* ctx, const AbmDenseArgs& A, size_t sm, int th
 int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
   // FP32 all-to-all populations of up to 512 agents take the symmetric-pair path (SMM_ABM_SYM=0: ordered pairs)
   const char* ev = getenv("SMM_ABM_SYM");
-  const bool sym = precision == SMM_PREC_F32 && A.rowptr == nullptr && (A.k.n + 31) / 32 <= kSymMaxGroups && !(ev && ev[0] == '0');
+  const bool sym = precision == SMM_PREC_F32 && A.rowptr == nullptr && (A.k.n + 31) / 32 <= kSymMaxGroups && A.k.L + A.k.M <= 32 && !(ev && ev[0] == '0');
   SMM_REQUIRE(ctx, A.k.L + A.k.M <= kThreads && A.k.L * A.k.M <= kThreads, "dense ABM kernel: L+M and L*M must be <= %d", kThreads);
   // CTA width from the ensemble size: the widest CTA for which all R realizations are still resident at once (one
   // 512-thread CTA or three 256-thread CTAs per SM at their register counts), but never wider than the tile count
@@ -545,12 +707,32 @@ int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
     else if (A.R <= 3 * ctx->sm_count && groups >= 4) threads = 256;
     if (const char* tv = getenv("SMM_ABM_THREADS")) { const int t = atoi(tv); if (t == 128 || t == 256 || t == 512) threads = t; }
   }
+  // Step chunks (see the kernel): only where the grid fills the GPU with 128-thread CTAs.  Measured at 1 024 realizations
+  // x 200 steps: one chunk 5.68 ms, chunks of 50 / 25 / 20 / 10 / 5 steps 5.31 / 5.22 / 5.20 / 5.19 / 5.22 ms (the
+  // prologue -- pair table and class sums -- and the hand-over cost about one step per chunk).
+  // SMM_ABM_CHUNK_STEPS overrides (0 = one chunk).
+  AbmDenseArgs B = A;
+  B.chunk_steps = 0;
+  if (threads == 128 && A.R >= 4 * ctx->sm_count && A.NT >= 40) B.chunk_steps = 20;
+  if (const char* cv = getenv("SMM_ABM_CHUNK_STEPS")) B.chunk_steps = std::max(0, atoi(cv));
+  if (B.chunk_steps >= A.NT) B.chunk_steps = 0;
+  if (B.chunk_steps > 0) {
+    const size_t R = (size_t)A.R, n = (size_t)A.k.n, L = (size_t)A.k.L, M = (size_t)A.k.M, rs = precision == SMM_PREC_F64 ? 8 : 4;
+    void* h = nullptr;
+    SMM_TRY(smm_scratch(ctx, S_HANDOFF, R * (2 * L + 2 * M) * 8 + R * 2 * n * rs + R * n * 4 + R * 4, &h));
+    B.hand_inf = (double*)h;  // widest element type first: every array is aligned for its type
+    B.hand_med = B.hand_inf + R * 2 * L;
+    B.hand_x = (void*)(B.hand_med + R * 2 * M);
+    B.hand_f = (int32_t*)((char*)B.hand_x + R * 2 * n * rs);
+    B.chunk_done = (unsigned*)(B.hand_f + R * n);
+    SMM_CUDA(ctx, cudaMemsetAsync(B.chunk_done, 0, R * 4, ctx->stream));
+  }
   size_t sm = dense_smem_bytes(A.k.n, A.k.L, A.k.M, precision == SMM_PREC_F64 ? 8 : 4, sym, threads);
   SMM_REQUIRE(ctx, sm <= 227 * 1024, "dense ABM kernel: n=%d does not fit shared memory (%zu B); pass a CSR network", A.k.n, sm);
   int rc;
-  if (precision == SMM_PREC_F64) rc = launch_dense_w<double, false>(ctx, A, sm, threads);
-  else if (sym) rc = launch_dense_w<float, true>(ctx, A, sm, threads);
-  else rc = launch_dense_w<float, false>(ctx, A, sm, threads);
+  if (precision == SMM_PREC_F64) rc = launch_dense_w<double, false>(ctx, B, sm, threads);
+  else if (sym) rc = launch_dense_w<float, true>(ctx, B, sm, threads);
+  else rc = launch_dense_w<float, false>(ctx, B, sm, threads);
   SMM_TRY(rc);
   ctx->launches++;
   SMM_CUDA(ctx, cudaGetLastError());

@@ -14,19 +14,36 @@
 
 namespace {
 
+// OP: 0 ex2, 1 sqrt, 2 rsqrt, 3 sqrt then ex2 (the pair loop's chain), 4 rsqrt then ex2, 5 lg2, 6 rcp, 7 sin
+template <int OP>
+__device__ __forceinline__ void mufu_op(float& v) {
+  if (OP == 0) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v));
+  if (OP == 1) asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(v));
+  if (OP == 2) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(v));
+  if (OP == 3) { asm volatile("sqrt.approx.ftz.f32 %0, %0;" : "+f"(v)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v)); }
+  if (OP == 4) { asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(v)); asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v)); }
+  if (OP == 5) asm volatile("lg2.approx.ftz.f32 %0, %0;" : "+f"(v));
+  if (OP == 6) asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(v));
+  if (OP == 7) asm volatile("sin.approx.ftz.f32 %0, %0;" : "+f"(v));
+}
+template <int OP>
 __global__ void __launch_bounds__(256) mufu_kernel(int iters, float* sink) {
   float v[8];
 #pragma unroll
-  for (int k = 0; k < 8; k++) v[k] = -1.0f - 0.01f * (float)(threadIdx.x + k);
+  for (int k = 0; k < 8; k++) v[k] = (OP == 0 ? -1.0f : 1.0f) * (1.0f + 0.01f * (float)(threadIdx.x + k));
   for (int i = 0; i < iters; i++) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[k]));  // 8 independent chains
+    for (int k = 0; k < 8; k++) mufu_op<OP>(v[k]);  // 8 independent chains
   }
   float s = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) s += v[k];
   if (s == 123.456f) sink[0] = s;
 }
+template <int OP>
+void launch_mufu(int grid, int iters, float* sink, cudaStream_t st) { mufu_kernel<OP><<<grid, 256, 0, st>>>(iters, sink); }
+typedef void (*mufu_launcher)(int, int, float*, cudaStream_t);
+const mufu_launcher kMufu[8] = {launch_mufu<0>, launch_mufu<1>, launch_mufu<2>, launch_mufu<3>, launch_mufu<4>, launch_mufu<5>, launch_mufu<6>, launch_mufu<7>};
 
 __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
@@ -90,12 +107,14 @@ extern "C" int smm_microbench(smm_ctx* ctx, int32_t which, uint64_t size, double
   rc = smm_scratch(ctx, S_TMP4, 256, &sink);
   if (rc == SMM_OK && which == SMM_MB_MUFU) {
     const int iters = 4096, grid = ctx->sm_count * 8;
-    mufu_kernel<<<grid, 256, 0, ctx->stream>>>(64, (float*)sink);
+    const int op = size < 8 ? (int)size : 0;  // size selects the operation (0: ex2, the default; see mufu_op)
+    kMufu[op](grid, 64, (float*)sink, ctx->stream);
     cudaEventRecord(e0, ctx->stream);
-    mufu_kernel<<<grid, 256, 0, ctx->stream>>>(iters, (float*)sink);
+    kMufu[op](grid, iters, (float*)sink, ctx->stream);
     cudaEventRecord(e1, ctx->stream);
     ctx->launches += 2;
-    if ((rc = time_ms(ctx, e0, e1, &ms)) == SMM_OK) *result = (double)grid * 256 * 8 * iters / (ms * 1e-3) / 1e9;  // G MUFU/s
+    const int per = (op == 3 || op == 4) ? 2 : 1;
+    if ((rc = time_ms(ctx, e0, e1, &ms)) == SMM_OK) *result = (double)grid * 256 * 8 * iters * per / (ms * 1e-3) / 1e9;  // G MUFU/s
   } else if (rc == SMM_OK && which == SMM_MB_LDS) {
     const int iters = 2048, grid = ctx->sm_count * 2;
     cudaFuncSetAttribute(lds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);

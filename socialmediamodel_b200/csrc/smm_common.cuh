@@ -87,7 +87,7 @@ int smm_collect_times(smm_ctx* ctx);
 enum {
   S_X0 = 0, S_STATE, S_FOLLOW, S_INF0, S_MED0, S_XI, S_U1, S_U2, S_XIINF, S_XIMED, S_SAVESTEPS,
   S_XS, S_FOLS, S_INFS, S_MEDS, S_YS, S_ZS, S_NUMBERS, S_US, S_SUMUS, S_SUMZS, S_SUMYS, S_STAGE,
-  S_ROWPTR, S_COLIDX, S_TMP0, S_TMP1, S_TMP2, S_TMP3, S_TMP4, S_TMP5, S_PDE0, S_STAGE_A, S_STAGE_B, S_YS_ALL, S_ZS_ALL
+  S_ROWPTR, S_COLIDX, S_TMP0, S_TMP1, S_TMP2, S_TMP3, S_TMP4, S_TMP5, S_PDE0, S_STAGE_A, S_STAGE_B, S_YS_ALL, S_ZS_ALL, S_HANDOFF
 };
 
 // ---------------------------------------------------------------------------------------

@@ -31,6 +31,13 @@ struct AbmDenseArgs {
   double* ys;               // f64   [R][nsave][L][2]
   double* zs;               // f64   [R][nsave][M][2]
   int64_t* numbers;         // int64 [NT+1][L][M] (atomically accumulated)
+  // set by smm_launch_abm_dense (step chunks, see abm_dense.cu): state handed from chunk to chunk, chunks done per realization
+  int chunk_steps;          // 0 = the whole run in one CTA
+  void* hand_x;             // real  [R][2][n]
+  int32_t* hand_f;          // int32 [R][n]
+  double* hand_inf;         // f64   [R][2][L]
+  double* hand_med;         // f64   [R][2][M]
+  unsigned* chunk_done;     // [R]
 };
 
 struct AbmInitArgs {

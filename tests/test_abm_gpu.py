@@ -431,6 +431,29 @@ def test_dense_kernel_cta_widths(n, monkeypatch):
     np.testing.assert_array_equal(auto["xs"], ref["xs"])
 
 
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_dense_kernel_step_chunks(precision, monkeypatch):
+    """Large ensembles run a realization as a chain of CTAs, each a chunk of steps, the state handed over through global
+    memory (abm_dense.cu).  Any chunk length gives the bits of the single-CTA run -- histories at every step, follower
+    numbers, injected and Philox noise -- and the chunk boundaries fall on, before and after save steps."""
+    NT, n, R = 31, 90, 3
+    p, q = smm.ABMconstruct(), smm.parameters(n=n)
+    runs = make_run(900, n=n, NT=NT, R=R)
+    init, inj = stack_inputs(runs)
+    monkeypatch.setenv("SMM_ABM_THREADS", "128")
+    outs = {}
+    for cs in ("0", "1", "7", "10", "30"):
+        monkeypatch.setenv("SMM_ABM_CHUNK_STEPS", cs)
+        outs[cs] = (smm.abm_solve_raw(NT, p=p, q=q, R=R, precision=precision, init_state=init, injected=inj),
+                    smm.abm_ensemble_raw(NT, R, p=p, q=q, savesteps=np.array([0, 7, 10, 30], np.int32), first_realization=5,
+                                         precision=precision, want=("zs", "ys", "sums", "numbers")))
+    for cs in ("1", "7", "10", "30"):
+        for k in ("xs", "follows", "infs", "meds", "numbers"):
+            np.testing.assert_array_equal(outs[cs][0][k], outs["0"][0][k], err_msg=f"chunk {cs} {k}")
+        for k in ("sum_us", "ys", "zs", "numbers"):
+            np.testing.assert_array_equal(outs[cs][1][k], outs["0"][1][k], err_msg=f"chunk {cs} ensemble {k}")
+
+
 def test_ensemble_float32_densities_and_means_only():
     """Keyword extensions of ABMsolveensemble for callers that do not need 2 GB of Float64 densities
     (smm_abm_ensemble_f32, us = NULL): the Float32 array holds exactly the values the Float64 array holds, and the

@@ -18,7 +18,7 @@ import socialmediamodel_b200 as smm
 pytestmark = pytest.mark.gpu
 
 
-def test_c2_full_ensemble_properties():
+def test_c2_full_ensemble_properties(monkeypatch):
     NT, R, sp = 200, 1024, 4
     p, q = smm.ABMconstruct(), smm.parameters()
     st = smm.savetimes_abm(NT, sp)
@@ -31,6 +31,13 @@ def test_c2_full_ensemble_properties():
     mass = a["sum_us"].sum(axis=(0, 1, 2, 3)) * p.dV / R
     assert np.all(mass > 0.97) and np.all(mass < 1.0 + 1e-6), mass                 # Gaussians leak a little over the domain edge
     assert np.all(a["sum_us"] >= 0)
+    # the full ensemble runs every realization as a chain of 20-step CTAs (state handed over through global memory, so that
+    # the SMs stay full to the end): same bits as one CTA per realization for the whole run
+    monkeypatch.setenv("SMM_ABM_CHUNK_STEPS", "0")
+    c = smm.abm_ensemble_raw(NT, R, p=p, q=q, savesteps=st, first_realization=1, precision="f32", want=("zs", "ys", "sums", "numbers"))
+    monkeypatch.delenv("SMM_ABM_CHUNK_STEPS")
+    for k in ("sum_us", "sum_ys", "sum_zs", "numbers", "ys", "zs"):
+        np.testing.assert_array_equal(a[k], c[k])
     # realizations 513..640 as their own shard = the same realizations inside the ensemble
     sh = smm.abm_ensemble_raw(NT, 128, p=p, q=q, savesteps=st, first_realization=513, precision="f32", want=("ys", "zs"))
     np.testing.assert_array_equal(sh["ys"], a["ys"][..., 512:640])
