@@ -697,23 +697,28 @@ int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
   const char* ev = getenv("SMM_ABM_SYM");
   const bool sym = precision == SMM_PREC_F32 && A.rowptr == nullptr && (A.k.n + 31) / 32 <= kSymMaxGroups && A.k.L + A.k.M <= 32 && !(ev && ev[0] == '0');
   SMM_REQUIRE(ctx, A.k.L + A.k.M <= kThreads && A.k.L * A.k.M <= kThreads, "dense ABM kernel: L+M and L*M must be <= %d", kThreads);
-  // CTA width from the ensemble size: the widest CTA for which all R realizations are still resident at once (one
-  // 512-thread CTA or three 256-thread CTAs per SM at their register counts), but never wider than the tile count
-  // of the population can feed (n = 250: 8 row groups, 36 tiles)
+  // CTA width from the ensemble size (never wider than the tile count of the population can feed: n = 250 has 8 row
+  // groups, 36 tiles).  With step chunks (below) the realizations need not all be resident at once, they take turns on
+  // the CTA slots chunk by chunk, so the width is chosen for throughput.  Measured per pass (200 steps, n = 250, chunks of
+  // 20 steps; ms): R = 170: 512 threads 1.64, 256 threads 1.98; R = 200: 1.91 / 2.08; R = 256: 256 threads 2.06 (one
+  // chunk); R = 370: 256 threads 2.44, 128 threads 3.14; R = 512: 3.06 / 3.41; R = 600: 3.58 / 3.63; R = 700: 4.18 / 3.99;
+  // R = 1 024: 6.07 / 5.20 (profiles/r2c_dense_chunk_sweep.txt).
   int threads = 128;
   {
-    const int groups = (A.k.n + 31) / 32;
-    if (A.R <= ctx->sm_count && groups >= 8) threads = 512;
-    else if (A.R <= 3 * ctx->sm_count && groups >= 4) threads = 256;
+    const int groups = (A.k.n + 31) / 32, sms = ctx->sm_count;
+    if (2 * A.R <= 3 * sms && groups >= 8) threads = 512;
+    else if (A.R <= 4 * sms && groups >= 4) threads = 256;
     if (const char* tv = getenv("SMM_ABM_THREADS")) { const int t = atoi(tv); if (t == 128 || t == 256 || t == 512) threads = t; }
   }
-  // Step chunks (see the kernel): only where the grid fills the GPU with 128-thread CTAs.  Measured at 1 024 realizations
-  // x 200 steps: one chunk 5.68 ms, chunks of 50 / 25 / 20 / 10 / 5 steps 5.31 / 5.22 / 5.20 / 5.19 / 5.22 ms (the
-  // prologue -- pair table and class sums -- and the hand-over cost about one step per chunk).
-  // SMM_ABM_CHUNK_STEPS overrides (0 = one chunk).
+  // Step chunks (see the kernel) where the ensemble has more realizations than one round of CTA slots can balance: more
+  // than two per SM (one for 512-thread CTAs, which have one slot per SM).  Below that every realization has a slot of its
+  // own for the whole run and a chunk boundary only costs (R = 256: 2.06 -> 2.20 ms).  Measured at 1 024 realizations x 200
+  // steps: one chunk 5.68 ms, chunks of 50 / 25 / 20 / 10 / 5 steps 5.31 / 5.22 / 5.20 / 5.19 / 5.22 ms (the prologue --
+  // pair table and class sums -- and the hand-over cost about one step per chunk); R = 330: 2.77 -> 2.32 ms; R = 600:
+  // 4.28 -> 3.62 ms.  SMM_ABM_CHUNK_STEPS overrides (0 = one chunk).
   AbmDenseArgs B = A;
   B.chunk_steps = 0;
-  if (threads == 128 && A.R >= 4 * ctx->sm_count && A.NT >= 40) B.chunk_steps = 20;
+  if (A.NT >= 40 && A.R > (threads == 512 ? 1 : 2) * ctx->sm_count) B.chunk_steps = 20;
   if (const char* cv = getenv("SMM_ABM_CHUNK_STEPS")) B.chunk_steps = std::max(0, atoi(cv));
   if (B.chunk_steps >= A.NT) B.chunk_steps = 0;
   if (B.chunk_steps > 0) {
