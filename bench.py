@@ -124,7 +124,8 @@ def max_over_ranks(x, world):
 # DRAM traffic per launch of the dominant kernels, from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum;
 # the .csv pages are under profiles/): kernel -> (bytes per launch at the benchmarked size, source)
 NCU_TRAFFIC = {
-    "abm_dense": (3.51e6, "profiles/r2b_abm_dense_full_raw.csv (1 024 realizations x 200 steps; the state lives in shared memory)"),
+    "abm_dense": (3.61e6, "profiles/r2c_abm_dense_full_raw.csv (1 024 realizations x 200 steps in chunks of 20 steps; the state lives in shared memory, "
+                          "4.3 KB per realization and chunk boundary are handed over through L2)"),
     "kde": (9.92e8, "profiles/r2_abm_dense_full_raw.csv (979 MB written + 12.6 MB read; algorithmic output 1.04 GB)"),
     "pop_step": (1.03e9, "profiles/r1_pop_step_full_raw_v2.csv (n = 1e7; positions are L2-resident)"),
     # per launch at 16 instances 353 x 353 (profiles/r2_pde_final_full_raw.csv); scaled by B / 16 in bench_pde.py
