@@ -249,32 +249,43 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
   int4 wacc = make_int4(0, 0, 0, 0);  // lane b: running sums of class b (b < L: followers of influencer b; then media)
   // one agent per lane (valid or not): every class summed over the warp with one REDUX per value; warp-uniform call
   auto class_add = [&](bool valid, float px, float py, int f, int s) {
-    const int qx = valid ? __float2int_rn(px * qscale) : 0, qy = valid ? __float2int_rn(py * qscale) : 0;
+    const int qx = __float2int_rn(px * qscale), qy = __float2int_rn(py * qscale);
+    const int fe = valid ? f : -1;
     const unsigned plus = __ballot_sync(0xffffffffu, valid && s == 1);
-    for (int b = 0; b < L + M; b++) {
-      const bool in = valid && (b < L ? f == b : s == (b == L ? -1 : 1));
+    unsigned mine = 0u;  // lane b: the members of class b among this warp's agents
+    for (int b = 0; b < L; b++) {
+      const bool in = fe == b;
       const unsigned m = __ballot_sync(0xffffffffu, in);
-      if (m == 0u) continue;
       const int rx = __reduce_add_sync(0xffffffffu, in ? qx : 0), ry = __reduce_add_sync(0xffffffffu, in ? qy : 0);
-      if (lane == b) { wacc.x += rx; wacc.y += ry; wacc.z += __popc(m); wacc.w += 2 * __popc(m & plus) - __popc(m); }
+      if (lane == b) { wacc.x += rx; wacc.y += ry; mine = m; }
     }
+    for (int b = L; b < L + M; b++) {  // media classes by state: -1, +1 (abm.jl:188-191)
+      const bool in = valid && s == (b == L ? -1 : 1);
+      const unsigned m = __ballot_sync(0xffffffffu, in);
+      const int rx = __reduce_add_sync(0xffffffffu, in ? qx : 0), ry = __reduce_add_sync(0xffffffffu, in ? qy : 0);
+      if (lane == b) { wacc.x += rx; wacc.y += ry; mine = m; }
+    }
+    wacc.z += __popc(mine);
+    wacc.w += 2 * __popc(mine & plus) - __popc(mine);
   };
   auto class_flush = [&]() {
     if (lane < L + M) wsum[warp * (L + M) + lane] = wacc;
     wacc = make_int4(0, 0, 0, 0);
   };
-  auto class_total = [&](int b) {  // exact totals of class b over the warps
-    long long sx = 0, sy = 0; int c = 0, ss = 0;
-    for (int w = 0; w < nwarps; w++) { const int4 v = wsum[w * (L + M) + b]; sx += v.x; sy += v.y; c += v.z; ss += v.w; }
-    struct { long long sx, sy; int c, ss; } t = {sx, sy, c, ss};
-    return t;
-  };
-  auto add_numbers_sym = [&](int hist_index) {  // plotting.jl:284-307, from the class sums
-    if (A.numbers && tid < L * M) {
-      const int j = tid / M, i = tid % M;
-      const auto t = class_total(j);
-      const int v = i == 1 ? (t.c + t.ss) / 2 : (t.c - t.ss) / 2;
-      atomicAdd(reinterpret_cast<unsigned long long*>(A.numbers) + ((size_t)hist_index * L + j) * M + i, (unsigned long long)v);
+  // exact totals of class `lane` over the warps (warp 0 only; zero in the other lanes), then the follower numbers
+  // (plotting.jl:284-307) from them
+  long long tot_sx = 0, tot_sy = 0;
+  int tot_c = 0, tot_ss = 0;
+  auto class_totals = [&](int hist_index) {
+    tot_sx = tot_sy = 0; tot_c = tot_ss = 0;
+    if (lane < L + M)
+      for (int w = 0; w < nwarps; w++) { const int4 v = wsum[w * (L + M) + lane]; tot_sx += v.x; tot_sy += v.y; tot_c += v.z; tot_ss += v.w; }
+    if (A.numbers) {
+      const int j = lane / M, i = lane % M;
+      const int c = __shfl_sync(0xffffffffu, tot_c, j), ss = __shfl_sync(0xffffffffu, tot_ss, j);
+      if (lane < L * M)
+        atomicAdd(reinterpret_cast<unsigned long long*>(A.numbers) + ((size_t)hist_index * L + j) * M + i,
+                  (unsigned long long)(i == 1 ? (c + ss) / 2 : (c - ss) / 2));
     }
   };
   if constexpr (SYM) {
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
 
     // ---- P1: S_i, cnt_i, state sums of the OLD positions / followers (abm.jl:96-100,179-180,188-191)
     if constexpr (SYM) {
-      add_numbers_sym(k);  // the class sums of the current state were left by the previous step (or the prologue)
+      if (warp == 0) class_totals(k);  // the class sums of the current state were left by the previous step (or the prologue)
     } else {
       bin_sums(xc);
       __syncthreads();
@@ -344,8 +355,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
       int cnt, ssum;
       double sumx, sumy;
       if constexpr (SYM) {
-        const auto t = class_total(tid);
-        cnt = t.c; ssum = t.ss; sumx = (double)t.sx / (double)qscale; sumy = (double)t.sy / (double)qscale;
+        cnt = tot_c; ssum = tot_ss; sumx = (double)tot_sx / (double)qscale; sumy = (double)tot_sy / (double)qscale;
       } else {
         cnt = bcnt[2 * tid] + bcnt[2 * tid + 1]; ssum = bss[2 * tid] + bss[2 * tid + 1];
         sumx = bsx[2 * tid] + bsx[2 * tid + 1]; sumy = bsy[2 * tid] + bsy[2 * tid + 1];
@@ -598,7 +608,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
     return;
   }
   if constexpr (SYM) {
-    add_numbers_sym(NT);
+    if (warp == 0) class_totals(NT);
   } else if (A.numbers) {
     bin_sums(cur ? xbuf1 : xbuf0);
     __syncthreads();
@@ -695,7 +705,7 @@ static int launch_dense_w(smm_ctx* ctx, const AbmDenseArgs& A, size_t sm, int th
 int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
   // FP32 all-to-all populations of up to 512 agents take the symmetric-pair path (SMM_ABM_SYM=0: ordered pairs)
   const char* ev = getenv("SMM_ABM_SYM");
-  const bool sym = precision == SMM_PREC_F32 && A.rowptr == nullptr && (A.k.n + 31) / 32 <= kSymMaxGroups && A.k.L + A.k.M <= 32 && !(ev && ev[0] == '0');
+  const bool sym = precision == SMM_PREC_F32 && A.rowptr == nullptr && (A.k.n + 31) / 32 <= kSymMaxGroups && A.k.L + A.k.M <= 32 && A.k.L * A.k.M <= 32 && !(ev && ev[0] == '0');
   SMM_REQUIRE(ctx, A.k.L + A.k.M <= kThreads && A.k.L * A.k.M <= kThreads, "dense ABM kernel: L+M and L*M must be <= %d", kThreads);
   // CTA width from the ensemble size (never wider than the tile count of the population can feed: n = 250 has 8 row
   // groups, 36 tiles).  With step chunks (below) the realizations need not all be resident at once, they take turns on
