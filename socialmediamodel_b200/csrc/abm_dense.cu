@@ -28,6 +28,12 @@ constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 constexpr int kSymMaxGroups = 16;  // n <= 512: the per-offset partial sums must fit shared memory
 constexpr float kPadPos = 1e15f;   // padding agents of the last 32-group: exp(-|x - pad|) = 0 exactly
 
+// ---- KDE of a snapshot inside the step kernel (same arithmetic, order and results as kde_kernel in kde.cu) ----------
+constexpr int kKdeSpan = 96;   // grid columns / rows of one pass (lane owns columns l, l + 32, l + 64; a warp 12 rows)
+constexpr int kKdeChunk = 16;  // agents staged per chunk: 2 x 16 x 96 floats = 12 KB in the partial-sum area
+constexpr int kKdeRows = 12;
+__device__ __forceinline__ float kde_gauss1d(float d, float inv2s2) { return __expf(-d * d * inv2s2); }
+
 // ---- symmetric pair tiles ---------------------------------------------------------------------------------------
 // Table of a 32-group: T[i] = log2(e) * (x_a, x_b, y_a, y_b) of the agents a = i & 31, b = (i + 16) & 31, i < 64
 // (every entry twice, so that the rotated index lane +- t needs no wrap-around arithmetic).
@@ -179,6 +185,93 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
   const double sdt = sqrt(K.dt);
   const double noise_x = sdt * K.sigma;
 
+  // K4 inside K1 (ensemble.jl:27-41): class densities of the snapshot straight from shared memory.  Agents are counting-
+  // sorted by class c = 2 j + [state = +1] (stable: summation order = agent order, as in kde_kernel), staged 16 at a time as
+  // separable factors ex[k][ix], ey[k][iy]; a thread accumulates a 12 x 3 tile in packed FP32x2 registers.  `other` is the
+  // position buffer that is free between two steps, `part` the partial-sum area of the pair loop.
+  auto kde_snapshot = [&](const real2* xc, real2* other, size_t s) {
+    if constexpr (SYM) {
+      const int ncls = 2 * L, Nx = A.kde_Nx, Ny = A.kde_Ny;
+      int* off = bcnt;  // [ncls + 1] (the class-sum arrays of the ordered path are unused here)
+      float* sax = reinterpret_cast<float*>(other);
+      float* say = sax + n;
+      float* ex = part;
+      float* ey = ex + kKdeChunk * kKdeSpan;
+      for (int c = tid; c <= ncls; c += kThreads) off[c] = 0;
+      __syncthreads();
+      for (int a = tid; a < n; a += kThreads) atomicAdd(&off[fol[a] * 2 + (st[a] == 1 ? 1 : 0) + 1], 1);
+      __syncthreads();
+      if (tid == 0)
+        for (int c = 0; c < ncls; c++) off[c + 1] += off[c];
+      __syncthreads();
+      for (int c = warp; c < ncls; c += nwarps) {
+        int pos = off[c];
+        for (int a0 = 0; a0 < n; a0 += 32) {
+          const int a = a0 + lane;
+          const bool in = a < n && fol[a] * 2 + (st[a] == 1 ? 1 : 0) == c;
+          const unsigned m = __ballot_sync(0xffffffffu, in);
+          if (in) {
+            const int q = pos + __popc(m & ((1u << lane) - 1u));
+            const real2 pa = xc[a];
+            sax[q] = (float)pa.x; say[q] = (float)pa.y;
+          }
+          pos += __popc(m);
+        }
+      }
+      __syncthreads();
+      const float inv2s2 = (float)(1.0 / (2.0 * A.kde_sigma * A.kde_sigma));
+      const float scale = (float)(1.0 / (double)n / (2.0 * 3.14159265358979323846 * A.kde_sigma * A.kde_sigma));
+      float* us = static_cast<float*>(A.kde_us) + s * ncls * Nx * Ny;
+      for (int pass0 = 0; pass0 < kKdeSpan; pass0 += nwarps * kKdeRows) {
+        const int row0 = pass0 + warp * kKdeRows;
+        const bool active = row0 < kKdeSpan;
+        for (int c = 0; c < ncls; c++) {
+          float2 acc2[kKdeRows / 2][3];
+#pragma unroll
+          for (int b = 0; b < kKdeRows / 2; b++)
+#pragma unroll
+            for (int a = 0; a < 3; a++) acc2[b][a] = make_float2(0.f, 0.f);
+          for (int k0 = off[c]; k0 < off[c + 1]; k0 += kKdeChunk) {
+            const int kc = min(kKdeChunk, off[c + 1] - k0);
+            __syncthreads();  // previous chunk fully consumed
+            for (int e = tid; e < kc * kKdeSpan; e += kThreads) {
+              const int k = e / kKdeSpan, i = e - k * kKdeSpan;
+              ex[e] = i < Nx ? kde_gauss1d((float)(A.kde_gx0 + i * A.kde_dx) - sax[k0 + k], inv2s2) : 0.f;
+              ey[e] = i < Ny ? kde_gauss1d((float)(A.kde_gy0 + i * A.kde_dy) - say[k0 + k], inv2s2) : 0.f;
+            }
+            __syncthreads();
+            if (active)
+              for (int k = 0; k < kc; k++) {
+                float vx[3], vy[kKdeRows];
+#pragma unroll
+                for (int a = 0; a < 3; a++) vx[a] = ex[k * kKdeSpan + lane + 32 * a];
+#pragma unroll
+                for (int b = 0; b < kKdeRows; b += 4) {
+                  const float4 v = *reinterpret_cast<const float4*>(ey + k * kKdeSpan + row0 + b);
+                  vy[b] = v.x; vy[b + 1] = v.y; vy[b + 2] = v.z; vy[b + 3] = v.w;
+                }
+#pragma unroll
+                for (int b = 0; b < kKdeRows; b += 2)
+#pragma unroll
+                  for (int a = 0; a < 3; a++) acc2[b / 2][a] = fma2(make_float2(vx[a], vx[a]), make_float2(vy[b], vy[b + 1]), acc2[b / 2][a]);
+              }
+          }
+          if (active) {
+            float* o = us + (size_t)c * Nx * Ny;
+#pragma unroll
+            for (int b = 0; b < kKdeRows; b++)
+#pragma unroll
+              for (int a = 0; a < 3; a++) {
+                const int gx = lane + 32 * a, gy = row0 + b;
+                if (gx < Nx && gy < Ny) o[(size_t)gy * Nx + gx] = ((b & 1) ? acc2[b / 2][a].y : acc2[b / 2][a].x) * scale;
+              }
+          }
+        }
+      }
+      __syncthreads();  // the staging area is the pair loop's partial-sum area again
+    }
+  };
+
   auto snapshot = [&](int hist_index, const real2* xc, int slot) {
     // history entry `hist_index` (0 = initial state): abm.jl:161-164, 209-212
     if (A.infs) {
@@ -205,6 +298,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
         A.zs[(s * M + tid) * 2 + 0] = medx[slot * M + tid];
         A.zs[(s * M + tid) * 2 + 1] = medy[slot * M + tid];
       }
+      if (SYM && A.kde_us) kde_snapshot(xc, xc == xbuf0 ? xbuf1 : xbuf0, s);
       next_save++;
     }
   };
@@ -673,7 +767,7 @@ __global__ void abm_draws_kernel(int n, uint64_t seed, uint32_t realization, int
   u2[t] = d;
 }
 
-size_t dense_smem_bytes(int n, int L, int M, size_t real_size, bool sym, int threads) {
+size_t dense_smem_bytes(int n, int L, int M, size_t real_size, bool sym, int threads, bool kde = false) {
   int npad = (n + 3) & ~3;
   size_t b = 2 * (size_t)npad * 2 * real_size + sizeof(double) * (4 * L + 4 * M + L + 4 * (L + M)) +
              sizeof(int) * (4 * (L + M) + npad) + sizeof(float) * 3 * L + npad + 16;
@@ -681,7 +775,8 @@ size_t dense_smem_bytes(int n, int L, int M, size_t real_size, bool sym, int thr
     const size_t G = (n + 31) / 32, D = G / 2;
     // 128-thread CTAs keep row sums in registers (slots 0..D); wider CTAs deal single tiles (row + column slots).
     // The difference decides whether 7 CTAs (all 1 024 realizations of C2) fit one SM's shared memory.
-    b += 16 + G * kTab * 16 + (size_t)(threads / 32) * (L + M) * 16 + (1 + (threads == 128 ? 1 : 2) * D) * 3 * G * 32 * 4;
+    const size_t part = (1 + (threads == 128 ? 1 : 2) * D) * 3 * G * 32 * 4, stage = kde ? 2 * kKdeChunk * kKdeSpan * 4 : 0;
+    b += 16 + G * kTab * 16 + (size_t)(threads / 32) * (L + M) * 16 + std::max(part, stage);
   }
   return b;
 }
@@ -702,10 +797,25 @@ static int launch_dense_w(smm_ctx* ctx, const AbmDenseArgs& A, size_t sm, int th
   return launch_dense_t<real, SYM, 128>(ctx, A, sm);
 }
 
-int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
+static bool dense_takes_sym_path(const AbmDenseArgs& A, int precision) {
   // FP32 all-to-all populations of up to 512 agents take the symmetric-pair path (SMM_ABM_SYM=0: ordered pairs)
   const char* ev = getenv("SMM_ABM_SYM");
-  const bool sym = precision == SMM_PREC_F32 && A.rowptr == nullptr && (A.k.n + 31) / 32 <= kSymMaxGroups && A.k.L + A.k.M <= 32 && A.k.L * A.k.M <= 32 && !(ev && ev[0] == '0');
+  return precision == SMM_PREC_F32 && A.rowptr == nullptr && (A.k.n + 31) / 32 <= kSymMaxGroups && A.k.L + A.k.M <= 32 && A.k.L * A.k.M <= 32 &&
+         !(ev && ev[0] == '0');
+}
+
+bool smm_abm_dense_fuses_kde(const smm_ctx* ctx, const AbmDenseArgs& A, int precision, int Nx, int Ny) {
+  // Needs the symmetric path, a grid of one 96 x 96 pass and class offsets that fit the small-array area.  Opt-in
+  // (SMM_ABM_FUSED_KDE=1): same bits as kde_kernel, but measured slower at 1 024 realizations -- the step kernel grows by
+  // 0.90 ms (128-thread CTAs need two passes over the grid and stage the separable factors twice) where kde_kernel takes
+  // 0.71 ms: 6.24 against 6.06 ms per pass.  The step kernel does not hide added work.
+  const char* ev = getenv("SMM_ABM_FUSED_KDE");
+  return dense_takes_sym_path(A, precision) && Nx <= kKdeSpan && Ny <= kKdeSpan && A.k.M >= 1 && ev && ev[0] == '1';
+}
+
+int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
+  const bool sym = dense_takes_sym_path(A, precision);
+  SMM_REQUIRE(ctx, A.kde_us == nullptr || (sym && A.kde_Nx <= kKdeSpan && A.kde_Ny <= kKdeSpan), "dense ABM kernel: fused KDE needs the symmetric path");
   SMM_REQUIRE(ctx, A.k.L + A.k.M <= kThreads && A.k.L * A.k.M <= kThreads, "dense ABM kernel: L+M and L*M must be <= %d", kThreads);
   // CTA width from the ensemble size (never wider than the tile count of the population can feed: n = 250 has 8 row
   // groups, 36 tiles).  With step chunks (below) the realizations need not all be resident at once, they take turns on
@@ -742,7 +852,7 @@ int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
     B.chunk_done = (unsigned*)(B.hand_f + R * n);
     SMM_CUDA(ctx, cudaMemsetAsync(B.chunk_done, 0, R * 4, ctx->stream));
   }
-  size_t sm = dense_smem_bytes(A.k.n, A.k.L, A.k.M, precision == SMM_PREC_F64 ? 8 : 4, sym, threads);
+  size_t sm = dense_smem_bytes(A.k.n, A.k.L, A.k.M, precision == SMM_PREC_F64 ? 8 : 4, sym, threads, A.kde_us != nullptr);
   SMM_REQUIRE(ctx, sm <= 227 * 1024, "dense ABM kernel: n=%d does not fit shared memory (%zu B); pass a CSR network", A.k.n, sm);
   int rc;
   if (precision == SMM_PREC_F64) rc = launch_dense_w<double, false>(ctx, B, sm, threads);

@@ -400,9 +400,17 @@ int run_ensemble(smm_ctx* ctx, EnsembleRequest& E, const char* who) {
   void* p;
   A.nsave = E.nsave;
   if (nsave) { SMM_TRY(upload(ctx, S_SAVESTEPS, E.savesteps, nsave * 4, &p)); A.savesteps = (const int32_t*)p; }
-  const bool need_snap = E.want_xs || E.want_kde;
+  // KDE of the save steps inside the step kernel where it can (FP32 symmetric path): no snapshot round trip, no second kernel
+  const bool fused_kde = E.want_kde && nsave && smm_abm_dense_fuses_kde(ctx, A, precision, E.grid.Nx, E.grid.Ny);
+  if (fused_kde) {
+    const size_t per_snap = (size_t)E.grid.Nx * E.grid.Ny * 2 * L;
+    if (!E.d_us) SMM_TRY(smm_scratch(ctx, S_US, R * nsave * per_snap * rs, &E.d_us));
+    A.kde_us = E.d_us; A.kde_Nx = E.grid.Nx; A.kde_Ny = E.grid.Ny;
+    A.kde_gx0 = E.grid.x0; A.kde_gy0 = E.grid.y0; A.kde_dx = E.grid.dx; A.kde_dy = E.grid.dy; A.kde_sigma = E.kde_sigma;
+  }
+  const bool need_snap = E.want_xs || (E.want_kde && !fused_kde);
   if (need_snap && nsave) { SMM_TRY(smm_scratch(ctx, S_XS, R * nsave * 2 * n * rs, &p)); A.xs = p; }
-  if ((E.want_follows || E.want_kde) && nsave) { SMM_TRY(smm_scratch(ctx, S_FOLS, R * nsave * n * 4, &p)); A.follows = (int32_t*)p; }
+  if ((E.want_follows || (E.want_kde && !fused_kde)) && nsave) { SMM_TRY(smm_scratch(ctx, S_FOLS, R * nsave * n * 4, &p)); A.follows = (int32_t*)p; }
   if (E.want_infs) { SMM_TRY(smm_scratch(ctx, S_INFS, R * (NT + 1) * 2 * L * 8, &p)); A.infs = (double*)p; }
   if (E.want_meds) { SMM_TRY(smm_scratch(ctx, S_MEDS, R * (NT + 1) * 2 * M * 8, &p)); A.meds = (double*)p; }
   if (E.want_yz && nsave) {
@@ -424,7 +432,7 @@ int run_ensemble(smm_ctx* ctx, EnsembleRequest& E, const char* who) {
 
   E.d_xs = A.xs; E.d_follows = A.follows; E.d_infs = A.infs; E.d_meds = A.meds; E.d_ys = A.ys; E.d_zs = A.zs;
 
-  if (E.want_kde && nsave) {
+  if (E.want_kde && nsave && !fused_kde) {
     const size_t per_snap = (size_t)E.grid.Nx * E.grid.Ny * 2 * L;
     if (!E.d_us) SMM_TRY(smm_scratch(ctx, S_US, R * nsave * per_snap * rs, &E.d_us));
     KdeArgs Kd;

@@ -31,6 +31,11 @@ struct AbmDenseArgs {
   double* ys;               // f64   [R][nsave][L][2]
   double* zs;               // f64   [R][nsave][M][2]
   int64_t* numbers;         // int64 [NT+1][L][M] (atomically accumulated)
+  // KDE of the save steps inside the kernel (FP32 symmetric path; api_abm.cu asks smm_abm_dense_fuses_kde first):
+  // kde_us = real [R][nsave][L][2][Ny][Nx] or null (then xs / follows feed kde_kernel)
+  void* kde_us;
+  int kde_Nx, kde_Ny;
+  double kde_gx0, kde_gy0, kde_dx, kde_dy, kde_sigma;
   // set by smm_launch_abm_dense (step chunks, see abm_dense.cu): state handed from chunk to chunk, chunks done per realization
   int chunk_steps;          // 0 = the whole run in one CTA
   void* hand_x;             // real  [R][2][n]
@@ -68,6 +73,8 @@ struct KdeArgs {
   void* us;                     // real [S][L][2][Ny][Nx]
 };
 int smm_launch_kde(smm_ctx* ctx, const KdeArgs& A, int precision);
+// true when smm_launch_abm_dense can evaluate the KDE of the save steps itself for this configuration
+bool smm_abm_dense_fuses_kde(const smm_ctx* ctx, const AbmDenseArgs& A, int precision, int Nx, int Ny);
 // K4b ensemble reduction: sum over realizations (plotting.jl:361-363 numerator), f64 output
 int smm_launch_ensemble_sum(smm_ctx* ctx, const void* us, int precision, int R, size_t per_real, double* sum_us, int accumulate = 0);
 int smm_launch_small_sum(smm_ctx* ctx, const double* v, int R, int per_real, double* out);

@@ -454,6 +454,26 @@ def test_dense_kernel_step_chunks(precision, monkeypatch):
             np.testing.assert_array_equal(outs[cs][1][k], outs["0"][1][k], err_msg=f"chunk {cs} ensemble {k}")
 
 
+@pytest.mark.parametrize("n,R,threads", [(60, 5, None), (250, 3, "128"), (250, 3, "256"), (250, 2, "512"), (300, 2, None)])
+def test_kde_inside_the_step_kernel(n, R, threads, monkeypatch):
+    """FP32 ensembles evaluate the KDE of the save steps inside the step kernel, from shared memory (no snapshot round trip,
+    no second kernel): same arithmetic and summation order as kde_kernel, hence the same bits -- for every CTA width, with
+    and without step chunks, on the default 89 x 89 grid and on a coarse non-square one."""
+    NT = 24
+    q = smm.parameters(n=n)
+    st = np.array([0, 7, 20, 24], np.int32)
+    if threads: monkeypatch.setenv("SMM_ABM_THREADS", threads)
+    for p, cs in ((smm.ABMconstruct(), "0"), (smm.ABMconstruct(dx=0.2, dy=0.1), "5")):
+        monkeypatch.setenv("SMM_ABM_CHUNK_STEPS", cs)
+        monkeypatch.setenv("SMM_ABM_FUSED_KDE", "0")
+        ref = smm.abm_ensemble_raw(NT, R, p=p, q=q, savesteps=st, first_realization=3, precision="f32")
+        monkeypatch.setenv("SMM_ABM_FUSED_KDE", "1")
+        fused = smm.abm_ensemble_raw(NT, R, p=p, q=q, savesteps=st, first_realization=3, precision="f32")
+        assert ref["us"].max() > 0
+        for k in ("us", "sum_us", "ys", "zs", "numbers"):
+            np.testing.assert_array_equal(fused[k], ref[k], err_msg=f"{k} n={n} grid={p.X.shape}")
+
+
 def test_ensemble_float32_densities_and_means_only():
     """Keyword extensions of ABMsolveensemble for callers that do not need 2 GB of Float64 densities
     (smm_abm_ensemble_f32, us = NULL): the Float32 array holds exactly the values the Float64 array holds, and the
