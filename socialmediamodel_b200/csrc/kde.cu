@@ -34,7 +34,7 @@ __device__ __forceinline__ double gauss1d(double d, double inv2s2) { return exp(
 // (consecutive lanes -> conflict-free) and 12 ey values (same address in all lanes -> broadcast, as
 // three 128-bit loads) for 36 FMAs, and the stores of a warp are 128-byte contiguous rows.
 template <typename real>
-__global__ void __launch_bounds__(KW * 32) kde_kernel(KdeArgs A) {
+__global__ void __launch_bounds__(KW * 32, sizeof(real) == 4 ? 4 : 1) kde_kernel(KdeArgs A) {
   const int n = A.n, L = A.L, Nx = A.Nx, Ny = A.Ny;
   const int ncls = 2 * L;
   const int s = blockIdx.x;
@@ -85,6 +85,11 @@ __global__ void __launch_bounds__(KW * 32) kde_kernel(KdeArgs A) {
   for (int sy0 = 0; sy0 < Ny; sy0 += SPAN) {
     for (int sx0 = 0; sx0 < Nx; sx0 += SPAN) {
       const int iy0 = sy0 + warp * TYW;
+      // staging role of this thread in this pass (same expression as before: the coordinate in Float64, then rounded)
+      const bool stage_x = tid < SPAN;
+      const int stage_i = stage_x ? sx0 + tid : sy0 + tid - SPAN;
+      const bool stage_in = stage_x ? stage_i < Nx : stage_i < Ny;
+      const real stage_coord = stage_x ? (real)(A.gx0 + stage_i * A.dx) : (real)(A.gy0 + stage_i * A.dy);
       for (int c = 0; c < ncls; c++) {
         real acc[TYW][TXL];
         float2 acc2[TYW / 2][TXL];  // FP32: rows (2b, 2b+1) as packed pairs -> FFMA2, two FMAs per issue slot
@@ -95,11 +100,12 @@ __global__ void __launch_bounds__(KW * 32) kde_kernel(KdeArgs A) {
         for (int k0 = off[c]; k0 < off[c + 1]; k0 += KC) {
           const int kc = min(KC, off[c + 1] - k0);
           __syncthreads();  // previous chunk fully consumed
-          for (int e = tid; e < kc * SPAN; e += nthreads) {
-            const int k = e / SPAN, i = e - k * SPAN;
-            const int gx = sx0 + i, gy = sy0 + i;
-            ex[e] = gx < Nx ? gauss1d((real)(A.gx0 + gx * A.dx) - ax[k0 + k], inv2s2) : (real)0;
-            ey[e] = gy < Ny ? gauss1d((real)(A.gy0 + gy * A.dy) - ay[k0 + k], inv2s2) : (real)0;
+          // separable factors of the chunk: thread t < 96 owns grid column t (ex), thread 96 + t grid row t (ey); its
+          // coordinate sits in a register, the agent coordinate is a broadcast load: 6 instructions per factor
+          if (tid < 2 * SPAN) {
+            real* dst = stage_x ? ex + tid : ey + (tid - SPAN);
+            const real* src = (stage_x ? ax : ay) + k0;
+            for (int k = 0; k < kc; k++) dst[k * SPAN] = stage_in ? gauss1d(stage_coord - src[k], inv2s2) : (real)0;
           }
           __syncthreads();
           for (int k = 0; k < kc; k++) {
@@ -128,14 +134,12 @@ __global__ void __launch_bounds__(KW * 32) kde_kernel(KdeArgs A) {
 #pragma unroll
             for (int a = 0; a < TXL; a++) { acc[b][a] = acc2[b / 2][a].x; acc[b + 1][a] = acc2[b / 2][a].y; }
         }
-        real* o = us + (size_t)c * Nx * Ny;
+        real* o = us + (size_t)c * Nx * Ny + (size_t)iy0 * Nx + sx0 + lane;
 #pragma unroll
         for (int b = 0; b < TYW; b++)
 #pragma unroll
-          for (int a = 0; a < TXL; a++) {
-            const int gx = sx0 + lane + 32 * a, gy = iy0 + b;
-            if (gx < Nx && gy < Ny) o[(size_t)gy * Nx + gx] = acc[b][a] * scale;
-          }
+          for (int a = 0; a < TXL; a++)
+            if (sx0 + lane + 32 * a < Nx && iy0 + b < Ny) o[b * Nx + 32 * a] = acc[b][a] * scale;
       }
     }
   }
