@@ -135,11 +135,19 @@ __global__ void __launch_bounds__(KW * 32, sizeof(real) == 4 ? 4 : 1) kde_kernel
             for (int a = 0; a < TXL; a++) { acc[b][a] = acc2[b / 2][a].x; acc[b + 1][a] = acc2[b / 2][a].y; }
         }
         real* o = us + (size_t)c * Nx * Ny + (size_t)iy0 * Nx + sx0 + lane;
+        const int nrows = min(TYW, Ny - iy0);  // warp-uniform; column predicates once per tile, not per element
+        bool colin[TXL];
 #pragma unroll
-        for (int b = 0; b < TYW; b++)
+        for (int a = 0; a < TXL; a++) colin[a] = sx0 + lane + 32 * a < Nx;
 #pragma unroll
-          for (int a = 0; a < TXL; a++)
-            if (sx0 + lane + 32 * a < Nx && iy0 + b < Ny) o[b * Nx + 32 * a] = acc[b][a] * scale;
+        for (int b = 0; b < TYW; b++) {
+          if (b < nrows) {
+#pragma unroll
+            for (int a = 0; a < TXL; a++)
+              if (colin[a]) o[32 * a] = acc[b][a] * scale;
+          }
+          o += Nx;
+        }
       }
     }
   }
