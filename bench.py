@@ -126,7 +126,7 @@ def max_over_ranks(x, world):
 NCU_TRAFFIC = {
     "abm_dense": (3.61e6, "profiles/r2c_abm_dense_full_raw.csv (1 024 realizations x 200 steps in chunks of 20 steps; the state lives in shared memory, "
                           "4.3 KB per realization and chunk boundary are handed over through L2)"),
-    "kde": (9.92e8, "profiles/r2_abm_dense_full_raw.csv (979 MB written + 12.6 MB read; algorithmic output 1.04 GB)"),
+    "kde": (9.93e8, "profiles/r2c_kde_full_raw.csv (980 MB written + 12.6 MB read; algorithmic output 1.04 GB)"),
     "pop_step": (1.03e9, "profiles/r1_pop_step_full_raw_v2.csv (n = 1e7; positions are L2-resident)"),
     # per launch at 16 instances 353 x 353 (profiles/r2_pde_final_full_raw.csv); scaled by B / 16 in bench_pde.py
     "pde_stage2_per16": (3.28e8, "profiles/r2_pde_final_full_raw.csv: 210 MB read + 117 MB written per launch at 16 x 353^2 (algorithmic 303 MB)"),
