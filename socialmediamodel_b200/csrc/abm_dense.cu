@@ -43,6 +43,7 @@ __device__ __forceinline__ float kde_gauss1d(float d, float inv2s2) { return __e
 // per-warp latency (0.6 instructions per cycle and scheduler with 5.7 resident warps), so what pays is instructions:
 // the column-side fix-up below (21 -> 19 per step) and the symmetric diagonal tile: 5.90 -> 5.60 ms.
 constexpr int kTab = 64;   // table entries per 32-group
+constexpr int kSchedMax = 32;  // wide CTAs: bytes of a warp's tile list (count + up to 31 tiles; 136 tiles over >= 8 warps)
 struct Sums2 { float2 ws, ax, ay; };
 __device__ __forceinline__ void zero(Sums2& s) { s.ws = s.ax = s.ay = make_float2(0.f, 0.f); }
 // (sum of the two halves; forces scaled back by ln 2) -- explicit _rn operations: no contraction into an FMA
@@ -138,7 +139,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
   // slot D + d, d = 1..D: column sums of tile (h-d, h); each [G*32] x (ws, ax, ay)
   const int G = (n + 31) >> 5, D = G >> 1, NG = G * 32;
   // xy2[g][i] = log2(e) * (x_a, x_b, y_a, y_b) of the agents a = g*32 + (i & 31), b = g*32 + ((i + 16) & 31), i < 64
-  float4* xy2 = reinterpret_cast<float4*>(smem + ((reinterpret_cast<unsigned char*>(st + npad) - smem + 15) & ~(size_t)15));
+  // wide CTAs: the tiles each warp evaluates (sched[warp][0] = count, then the tile indices), fixed at kernel start
+  unsigned char* sched = reinterpret_cast<unsigned char*>(st + npad);
+  float4* xy2 = reinterpret_cast<float4*>(smem + ((sched + (SYM && THREADS != 128 ? nwarps * kSchedMax : 0) - smem + 15) & ~(size_t)15));
   // SYM: class sums of the current state per warp, in fixed point: wsum[warp][bin] = (sum qx, sum qy, count, sum of states)
   // with q = round(position * qscale).  Integer sums are exact and associative: the class means do not depend on the
   // CTA width or on which warp holds which agent.
@@ -177,6 +180,29 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
     if (tid < M) { medx[tid] = A.media0[(size_t)r * 2 * M + tid]; medy[tid] = A.media0[(size_t)r * 2 * M + M + tid]; }
   }
   __syncthreads();
+
+  if constexpr (SYM && THREADS != 128) {
+    // Tiles dealt to the warps once, by the longest-processing-time rule (off-diagonal tiles, 16 steps each, first; then
+    // the diagonal ones, 9 steps), with warp 0 starting from the cost of the influencer / media update it also carries
+    // (A.p2_cost steps): that update sits in front of warp 0's tiles, and every other warp waits for it at the barrier
+    // behind the pair loop.  Every tile owns its partial-sum slots, so any assignment gives bit-identical results.
+    if (tid == 0) {
+      const int Gs = (n + 31) >> 5, Ds = Gs >> 1;
+      const int NOs = (Gs & 1) ? Ds * Gs : (Ds > 0 ? (Ds - 1) * Gs + Ds : 0), NIs = NOs + Gs;
+      int load[THREADS / 32];
+      for (int w = 0; w < nwarps; w++) { load[w] = 0; sched[w * kSchedMax] = 0; }
+      load[0] = A.p2_cost;
+      for (int it = 0; it < NIs; it++) {
+        int best = nwarps - 1;
+        for (int w = nwarps - 2; w >= 0; w--)
+          if (load[w] < load[best]) best = w;
+        unsigned char* my = sched + best * kSchedMax;
+        if (my[0] < kSchedMax - 1) { my[++my[0]] = (unsigned char)it; load[best] += it < NOs ? 16 : 9; }
+        else { for (int w = 0; w < nwarps; w++) if (sched[w * kSchedMax] < kSchedMax - 1) { unsigned char* o = sched + w * kSchedMax; o[++o[0]] = (unsigned char)it; load[w] += 16; break; } }
+      }
+    }
+    __syncthreads();
+  }
 
   int cur = 0;        // which x buffer / inf slot holds the current state
   int next_save = 0;  // index into savesteps
@@ -598,11 +624,11 @@ __global__ void __launch_bounds__(THREADS, THREADS == 128 ? (SYM ? 7 : 8) : (THR
       // groups) and G diagonal ones.  Off-diagonal tiles cost ~1.7x a diagonal one, so they are dealt first and in
       // snake order over the warps (longest-processing-time rule): 36 tiles at n = 250 balance to within 6 % over 16
       // warps.  Every tile owns its partial-sum slots, so any assignment gives bit-identical results.
-      const int NO = (G & 1) ? D * G : (D > 0 ? (D - 1) * G + D : 0), NI = NO + G;
-      for (int round = 0;; round++) {
-        const int it = (round & 1) ? (round + 1) * nwarps - 1 - warp : round * nwarps + warp;
-        if (round * nwarps >= NI) break;
-        if (it >= NI) continue;
+      const int NO = (G & 1) ? D * G : (D > 0 ? (D - 1) * G + D : 0);
+      const unsigned char* mine = sched + warp * kSchedMax;
+      const int nmine = mine[0];
+      for (int si = 1; si <= nmine; si++) {
+        const int it = mine[si];
         const int d = it < NO ? it / G + 1 : 0;
         const int g = it < NO ? it - (d - 1) * G : it - NO;
         const float4* rowp = xy2 + g * kTab + lane;
@@ -776,6 +802,7 @@ size_t dense_smem_bytes(int n, int L, int M, size_t real_size, bool sym, int thr
     // 128-thread CTAs keep row sums in registers (slots 0..D); wider CTAs deal single tiles (row + column slots).
     // The difference decides whether 7 CTAs (all 1 024 realizations of C2) fit one SM's shared memory.
     const size_t part = (1 + (threads == 128 ? 1 : 2) * D) * 3 * G * 32 * 4, stage = kde ? 2 * kKdeChunk * kKdeSpan * 4 : 0;
+    if (threads != 128) b += (size_t)(threads / 32) * kSchedMax;
     b += 16 + G * kTab * 16 + (size_t)(threads / 32) * (L + M) * 16 + std::max(part, stage);
   }
   return b;
@@ -839,6 +866,10 @@ int smm_launch_abm_dense(smm_ctx* ctx, const AbmDenseArgs& A, int precision) {
   AbmDenseArgs B = A;
   B.chunk_steps = 0;
   if (A.NT >= 40 && A.R > (threads == 512 ? 1 : 2) * ctx->sm_count) B.chunk_steps = 20;
+  // measured (ms per pass, R = 128 / 296 realizations): snake order without head start 1.345 / 2.069; LPT with head start
+  // 0 / 10 / 20 / 30 steps: 1.281 / 1.240 / 1.248 / 1.251 and 2.063 / 2.025 / 2.029 / 2.037
+  B.p2_cost = 10;
+  if (const char* pv = getenv("SMM_ABM_P2_COST")) B.p2_cost = std::max(0, atoi(pv));
   if (const char* cv = getenv("SMM_ABM_CHUNK_STEPS")) B.chunk_steps = std::max(0, atoi(cv));
   if (B.chunk_steps >= A.NT) B.chunk_steps = 0;
   if (B.chunk_steps > 0) {

@@ -38,6 +38,7 @@ struct AbmDenseArgs {
   double kde_gx0, kde_gy0, kde_dx, kde_dy, kde_sigma;
   // set by smm_launch_abm_dense (step chunks, see abm_dense.cu): state handed from chunk to chunk, chunks done per realization
   int chunk_steps;          // 0 = the whole run in one CTA
+  int p2_cost;              // wide CTAs: head start of warp 0 in the tile dealing, in tile steps (it also updates the influencers)
   void* hand_x;             // real  [R][2][n]
   int32_t* hand_f;          // int32 [R][n]
   double* hand_inf;         // f64   [R][2][L]
