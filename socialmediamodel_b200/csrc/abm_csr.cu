@@ -21,6 +21,7 @@
 namespace {
 
 constexpr int kPopThreads = 256;
+constexpr int kPopChunk = 8;  // 32-agent slices a warp claims at a time (one atomic per 256 agents)
 
 struct PopArgs {
   AbmConst k;
@@ -44,6 +45,7 @@ struct PopArgs {
   const double* u2;
   unsigned long long* fallback_count;  // diagnostics: agents that took the FP64 re-evaluation
   int prefix_decision;                 // 1: prefix-sum/binary-search decision, 0: cooperative CDF walk
+  unsigned int* tile_counter;          // next unclaimed chunk of kPopChunk 32-agent slices (zeroed before every launch)
 };
 
 // class index c = follow*2 + (state==+1)
@@ -166,16 +168,30 @@ __global__ void __launch_bounds__(kPopThreads) pop_step_kernel(PopArgs A) {
   real2* xw = static_cast<real2*>(A.x_new);
   const double noise_x = sdt * K.sigma;
   unsigned int nfallback = 0;
-  for (size_t base = (size_t)blockIdx.x * kPopThreads; base < (size_t)n; base += (size_t)gridDim.x * kPopThreads) {
-    const bool valid = base + tid < (size_t)n;          // warp-uniform loop; tail lanes idle but shuffle
-    const size_t j = valid ? base + tid : (size_t)n - 1;
+  // Work is claimed, not assigned: a warp takes the next chunk of kPopChunk slices (32 consecutive agents each) from a global
+  // counter.  With a fixed share per CTA (grid-stride loop) the CTAs of an SM finish far apart -- the warp schedulers favour
+  // the older ones, see the dense kernel -- and the launch ends in a tail at falling occupancy; claimed work keeps every
+  // warp busy until the population is used up.  Results do not depend on who processes a slice (per-agent arithmetic,
+  // fixed-point class sums).
+  const int lane = tid & 31;
+  for (;;) {
+  unsigned int chunk = 0;
+  if (lane == 0) chunk = atomicAdd(A.tile_counter, 1u);
+  chunk = __shfl_sync(0xffffffffu, chunk, 0);
+  const size_t cbase = (size_t)chunk * (32 * kPopChunk);
+  if (cbase >= (size_t)n) break;
+  for (int sl = 0; sl < kPopChunk; sl++) {
+    const size_t base = cbase + (size_t)sl * 32;        // this warp's slice
+    if (base >= (size_t)n) break;
+    const bool valid = base + lane < (size_t)n;         // warp-uniform loop; tail lanes idle but shuffle
+    const size_t j = valid ? base + lane : (size_t)n - 1;
     const real2 xj = xo[j];
     real ax = 0, ay = 0, ws = 0;
     if (A.rowptr) {
       // sliced-ELL neighbour lists: lane l of a warp reads colidx[sp + t*32 + l] -> one coalesced
       // wavefront per neighbour slot instead of 32 (per-thread CSR rows made this kernel L1-bound)
       const int e0 = A.rowptr[j], e1 = valid ? A.rowptr[j + 1] : e0;
-      const int32_t* nb = A.colidx + (valid ? A.slice_ptr[(base + tid) >> 5] : 0) + (tid & 31);
+      const int32_t* nb = A.colidx + A.slice_ptr[base >> 5] + lane;
 #pragma unroll 4
       for (int e = e0; e < e1; e++, nb += 32) {  // abm.jl:51,57-62
         real2 p = ld_gather(xo + *nb);
@@ -232,6 +248,7 @@ __global__ void __launch_bounds__(kPopThreads) pop_step_kernel(PopArgs A) {
       atomicAdd(reinterpret_cast<unsigned long long*>(&bins[c * 3 + 1]), (unsigned long long)__double2ll_rn((double)pn.y * A.fx_scale));
       atomicAdd(reinterpret_cast<unsigned long long*>(&bins[c * 3 + 2]), 1ull);
     }
+  }
   }
   __syncthreads();
   for (int t = tid; t < 2 * L * 3; t += kPopThreads)
@@ -317,6 +334,8 @@ int smm_launch_pop_step(smm_ctx* ctx, smm_abm_pop* p, const void* xi, const doub
   A.xi = xi; A.u1 = u1; A.u2 = u2;
   A.fallback_count = p->fallback_count;
   A.prefix_decision = p->prefix_decision && p->precision != SMM_PREC_F64;
+  A.tile_counter = reinterpret_cast<unsigned int*>(p->fallback_count + 1);
+  SMM_CUDA(ctx, cudaMemsetAsync(A.tile_counter, 0, 4, ctx->stream));
   size_t sm = pop_smem_bytes(p->k.L, p->k.M, A.prefix_decision != 0);
   if (sm > 48 * 1024) {
     if (p->precision == SMM_PREC_F64) SMM_CUDA(ctx, cudaFuncSetAttribute(pop_step_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));

@@ -892,8 +892,8 @@ extern "C" int smm_abm_pop_create(smm_ctx* ctx, const smm_params* q, int32_t pre
   for (int i = 0; i < 3; i++) { POP_CUDA(cudaMalloc((void**)&p->acc[i], 2 * L * 3 * 8)); POP_CUDA(cudaMemsetAsync(p->acc[i], 0, 2 * L * 3 * 8, ctx->stream)); }
   POP_CUDA(cudaMalloc((void**)&p->follow, n));
   POP_CUDA(cudaMalloc((void**)&p->state, n));
-  POP_CUDA(cudaMalloc((void**)&p->fallback_count, 8));
-  POP_CUDA(cudaMemsetAsync(p->fallback_count, 0, 8, ctx->stream));
+  POP_CUDA(cudaMalloc((void**)&p->fallback_count, 16));  // + the work counter of pop_step_kernel
+  POP_CUDA(cudaMemsetAsync(p->fallback_count, 0, 16, ctx->stream));
   if (rowptr) {
     // neighbour lists are kept in sliced-ELL form (slices of 32 agents, width = max degree of the slice)
     const size_t nslices = (n + 31) / 32;
