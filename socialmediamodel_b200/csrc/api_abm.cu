@@ -504,7 +504,12 @@ static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precisio
   // realizations are processed in chunks and the device->host copy of chunk c overlaps the
   // simulation of chunk c+1 (copy stream, double-buffered Float64 staging).
   int nchunks = 1;
-  if (us_any && nsave && R >= 512) nchunks = std::min(4, R / 256);
+  // Measured (1 024 realizations, Float64 `us`, 16 host threads; ms per call, tools/scratch/e2e_chunks.sh): 4 chunks x 2 copy
+  // units (128 realizations per unit) 27.5-29.8; 4 x 4: 26.2; 8 x 2: 25.7; 8 x 3: 24.1; 8 x 4 (32 per unit): 23.4-24.7; 10 x 3:
+  // 23.5; 12 x 2: 24.8 -- shorter lead-in before the first copy and finer interleaving of DMA and widening.  64 or more
+  // units per call (8 x 8, 4 x 16, 16 x 4) fall off a cliff (68-113 ms): the unit count stays at 32.
+  if (us_any && nsave && R >= 512) nchunks = std::min(8, R / 128);
+  if (const char* ce = getenv("SMM_ENSEMBLE_CHUNKS")) { const int c = atoi(ce); if (c >= 1 && us_any && nsave && R >= 2 * c) nchunks = c; }
   const int Rc0 = (R + nchunks - 1) / nchunks;
   if (nchunks > 1 && !ctx->copy_stream) {
     SMM_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
@@ -534,7 +539,7 @@ static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precisio
     if (!ctx->hostpool) ctx->hostpool = smm_hostpool_create(ctx->host_threads);
     if (smm_hostpool_threads(ctx->hostpool) < 12 && !(hw_env && hw_env[0] == '1')) host_widen = false;
   }
-  int kSub = 2;
+  int kSub = 4;
   if (const char* e = getenv("SMM_HOST_WIDEN_SUB")) kSub = std::max(1, atoi(e));
   const size_t unit_real = ((size_t)Rc0 + kSub - 1) / kSub;  // realizations per copy unit
   if (host_widen) {
