@@ -38,6 +38,20 @@ __attribute__((target("avx2"))) void widen_avx2(const float* src, double* dst, s
   _mm_sfence();
 }
 
+// one 64-byte streaming store per destination cache line (AVX2 needs two 32-byte halves, which the write-combining buffers
+// have to merge)
+__attribute__((target("avx512f"))) void widen_avx512(const float* src, double* dst, size_t count) {
+  size_t i = 0;
+  while (i < count && ((uintptr_t)(dst + i) & 63)) { dst[i] = (double)src[i]; i++; }
+  for (; i + 16 <= count; i += 16) {
+    const __m256 lo = _mm256_loadu_ps(src + i), hi = _mm256_loadu_ps(src + i + 8);
+    _mm512_stream_pd(dst + i, _mm512_cvtps_pd(lo));
+    _mm512_stream_pd(dst + i + 8, _mm512_cvtps_pd(hi));
+  }
+  for (; i < count; i++) dst[i] = (double)src[i];
+  _mm_sfence();
+}
+
 }  // namespace
 
 struct smm_hostpool {
@@ -47,7 +61,7 @@ struct smm_hostpool {
   uint64_t generation = 0;
   int remaining = 0;
   bool quit = false;
-  bool avx2 = false;
+  bool avx2 = false, avx512 = false;
   const float* src = nullptr;
   double* dst = nullptr;
   size_t count = 0;
@@ -59,7 +73,8 @@ struct smm_hostpool {
     const size_t per = ((count + parts - 1) / parts + 15) & ~(size_t)15;
     const size_t b = std::min(count, per * (size_t)part), e = std::min(count, b + per);
     if (e <= b) return;
-    if (avx2) widen_avx2(src + b, dst + b, e - b);
+    if (avx512) widen_avx512(src + b, dst + b, e - b);
+    else if (avx2) widen_avx2(src + b, dst + b, e - b);
     else widen_scalar(src + b, dst + b, e - b);
   }
 
@@ -95,6 +110,10 @@ smm_hostpool* smm_hostpool_create(int nthreads) {
   smm_hostpool* p = new smm_hostpool;
   p->parts = nthreads;
   p->avx2 = __builtin_cpu_supports("avx2");
+  {  // SMM_HOST_WIDEN_ISA=avx2 keeps the 32-byte stores (A/B timing)
+    const char* isa = getenv("SMM_HOST_WIDEN_ISA");
+    p->avx512 = __builtin_cpu_supports("avx512f") && !(isa && isa[0] == 'a' && isa[3] == '2');
+  }
   for (int t = 1; t < nthreads; t++) p->workers.emplace_back([p, t] { p->worker(t); });
   return p;
 }
