@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include <vector>
 #include "smm_internal.h"
@@ -559,6 +560,7 @@ static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precisio
   struct Unit { int chunk; size_t r0, rc; bool last_of_chunk; };
   std::vector<Unit> units;
   size_t issued = 0, widened = 0;
+  double dbg_sync = 0, dbg_widen = 0;
   auto issue_unit = [&](size_t g) -> int {
     const Unit& u = units[g];
     const int sl = u.chunk & 1, hs = (int)(g & 1);
@@ -575,10 +577,15 @@ static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precisio
     while (widened < drain_end) {
       while (issued < std::min(issuable_end, widened + 2)) SMM_TRY(issue_unit(issued++));
       const int hs = (int)(widened & 1);
+      const auto t0 = std::chrono::steady_clock::now();
       SMM_CUDA(ctx, cudaEventSynchronize(ctx->ev_h[hs]));
+      const auto t1 = std::chrono::steady_clock::now();
       const Unit& u = units[widened];
       smm_hostpool_widen(ctx->hostpool, (const float*)ctx->h_ring + (size_t)hs * unit_real * per_real,
                          us + u.r0 * per_real, u.rc * per_real);
+      const auto t2 = std::chrono::steady_clock::now();
+      dbg_sync += std::chrono::duration<double, std::milli>(t1 - t0).count();
+      dbg_widen += std::chrono::duration<double, std::milli>(t2 - t1).count();
       widened++;
     }
     return SMM_OK;
@@ -650,6 +657,7 @@ static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precisio
   }
   if (pending.chunk >= 0) SMM_TRY(issue_copy(pending));
   if (host_widen) SMM_TRY(pump(units.size(), units.size()));
+  if (host_widen && getenv("SMM_E2E_DEBUG")) fprintf(stderr, "[smm] widen pipeline: %zu units, waiting for copies %.2f ms, widening %.2f ms\n", units.size(), dbg_sync, dbg_widen);
   void* p;
   // shard mode (member of a multi-GPU context): the sums stay in device scratch (S_SUMUS / S_SUMZS / S_SUMYS /
   // S_NUMBERS) for the NCCL all-reduce in multi.cu, which also delivers them to the caller
