@@ -3,6 +3,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <unistd.h>
+
 #include <algorithm>
 #include <chrono>
 
@@ -79,7 +81,7 @@ extern "C" int smm_ctx_destroy(smm_ctx* ctx) {
     if (ctx->ev1[i]) cudaEventDestroy(ctx->ev1[i]);
   }
   for (int i = 0; i < 2; i++) { if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]); if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]); }
-  for (int i = 0; i < 2; i++) if (ctx->ev_h[i]) cudaEventDestroy(ctx->ev_h[i]);
+  for (int i = 0; i < 32; i++) if (ctx->ev_h[i]) cudaEventDestroy(ctx->ev_h[i]);
   if (ctx->h_ring) cudaFreeHost(ctx->h_ring);
   smm_hostpool_destroy(ctx->hostpool);
   smm_multi_destroy(ctx->multi);
@@ -480,6 +482,23 @@ extern "C" int smm_abm_solve(smm_ctx* ctx, const smm_params* q, int32_t precisio
   return smm_collect_times(ctx);
 }
 
+// last-level cache of the host in bytes (0 = unknown): SMM_HOST_L3_MB, sysconf, then sysfs
+static size_t host_l3_bytes() {
+  if (const char* e = getenv("SMM_HOST_L3_MB")) return (size_t)std::max(0, atoi(e)) << 20;
+#ifdef _SC_LEVEL3_CACHE_SIZE
+  const long v = sysconf(_SC_LEVEL3_CACHE_SIZE);
+  if (v > 0) return (size_t)v;
+#endif
+  if (FILE* f = fopen("/sys/devices/system/cpu/cpu0/cache/index3/size", "r")) {
+    unsigned long kb = 0;
+    char unit = 0;
+    const int got = fscanf(f, "%lu%c", &kb, &unit);
+    fclose(f);
+    if (got >= 1 && kb > 0) return (size_t)kb * (unit == 'M' ? (size_t)1 << 20 : (size_t)1 << 10);
+  }
+  return 0;
+}
+
 // `us_any` is the caller's Float64 array, or (us_f32) a Float32 array of the same shape that receives the FP32
 // device densities without widening (half the PCIe bytes, half the host bytes written).
 static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precision, int32_t NT, int32_t R,
@@ -540,13 +559,32 @@ static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precisio
     if (!ctx->hostpool) ctx->hostpool = smm_hostpool_create(ctx->host_threads);
     if (smm_hostpool_threads(ctx->hostpool) < 12 && !(hw_env && hw_env[0] == '1')) host_widen = false;
   }
+  // Copy units and the pinned ring they land in, sized against the host's last-level cache (measured on a 16-core Xeon
+  // with 60 MB of L3, 1 024 realizations, ms per call; profiles/r2c_e2e_chunk_sweep.txt):
+  //  * ring smaller than the L3 (two slots of <= 22 realizations): the lines a DMA write targets are still cached from the
+  //    widening threads' reads, every write has to snoop them out, and the copies crawl: 60-110 ms;
+  //  * ring 1.1-1.4 x L3 (two slots of 32-43 realizations): 23.5-25 -- old lines are gone before they are rewritten, and the
+  //    widening threads still find part of a freshly copied unit in the cache;
+  //  * ring 2-4 x L3 (or 256 MB in 8-32 slots of any size): 26-30 -- everything the widening reads comes from DRAM.
+  // Hence units of 0.7 x L3 in a ring of at least 1.3 x L3; with an unknown L3 a 256 MB ring (never in the first regime).
+  // SMM_HOST_L3_MB, SMM_HOST_WIDEN_SUB (units per chunk) and SMM_HOST_RING_MB override.
+  static const size_t l3_bytes = host_l3_bytes();
   int kSub = 4;
+  if (l3_bytes) {
+    const size_t want = std::max<size_t>(1, (size_t)(0.7 * (double)l3_bytes) / (per_real * 4));
+    kSub = (int)(((size_t)Rc0 + std::min<size_t>(want, (size_t)Rc0) - 1) / std::min<size_t>(want, (size_t)Rc0));
+  }
   if (const char* e = getenv("SMM_HOST_WIDEN_SUB")) kSub = std::max(1, atoi(e));
   const size_t unit_real = ((size_t)Rc0 + kSub - 1) / kSub;  // realizations per copy unit
+  int ring_slots = 2;
   if (host_widen) {
-    for (int i = 0; i < 2; i++)
+    const size_t unit_bytes = unit_real * per_real * 4;
+    size_t ring_min = l3_bytes ? (size_t)(1.3 * (double)l3_bytes) : (size_t)256 << 20;
+    if (const char* e = getenv("SMM_HOST_RING_MB")) ring_min = (size_t)std::max(0, atoi(e)) << 20;
+    ring_slots = (int)std::min<size_t>(32, std::max<size_t>(2, (ring_min + unit_bytes - 1) / unit_bytes));
+    for (int i = 0; i < ring_slots; i++)
       if (!ctx->ev_h[i]) SMM_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_h[i], cudaEventDisableTiming));
-    const size_t need = 2 * unit_real * per_real * 4;
+    const size_t need = (size_t)ring_slots * unit_bytes;
     if (ctx->h_ring_bytes < need) {
       if (ctx->h_ring) { SMM_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream)); SMM_CUDA(ctx, cudaFreeHost(ctx->h_ring)); ctx->h_ring = nullptr; ctx->h_ring_bytes = 0; }
       SMM_CUDA(ctx, cudaHostAlloc(&ctx->h_ring, need, cudaHostAllocDefault));
@@ -563,7 +601,7 @@ static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precisio
   double dbg_sync = 0, dbg_widen = 0;
   auto issue_unit = [&](size_t g) -> int {
     const Unit& u = units[g];
-    const int sl = u.chunk & 1, hs = (int)(g & 1);
+    const int sl = u.chunk & 1, hs = (int)(g % (size_t)ring_slots);
     float* h = (float*)ctx->h_ring + (size_t)hs * unit_real * per_real;
     const float* d = (const float*)stage[sl] + (u.r0 - (size_t)u.chunk * Rc0) * per_real;
     SMM_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_ready[sl], 0));
@@ -576,7 +614,7 @@ static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precisio
   auto pump = [&](size_t drain_end, size_t issuable_end) -> int {
     while (widened < drain_end) {
       while (issued < std::min(issuable_end, widened + 2)) SMM_TRY(issue_unit(issued++));
-      const int hs = (int)(widened & 1);
+      const int hs = (int)(widened % (size_t)ring_slots);
       const auto t0 = std::chrono::steady_clock::now();
       SMM_CUDA(ctx, cudaEventSynchronize(ctx->ev_h[hs]));
       const auto t1 = std::chrono::steady_clock::now();

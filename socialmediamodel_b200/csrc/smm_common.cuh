@@ -36,7 +36,7 @@ struct smm_ctx {
   struct smm_hostpool* hostpool = nullptr;
   void* h_ring = nullptr;
   size_t h_ring_bytes = 0;
-  cudaEvent_t ev_h[2] = {nullptr, nullptr};
+  cudaEvent_t ev_h[32] = {};  // one per slot of h_ring
   int host_threads = 0;            // host widening threads (0 = default: cores / local ranks, <= 16)
   // multi-GPU (multi.cu): a leader context owns one member context per GPU; members run in shard mode
   struct smm_multi* multi = nullptr;
