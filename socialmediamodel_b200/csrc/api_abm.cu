@@ -568,7 +568,10 @@ static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precisio
   //  * ring 2-4 x L3 (or 256 MB in 8-32 slots of any size): 26-30 -- everything the widening reads comes from DRAM.
   // Hence units of 0.7 x L3 in a ring of at least 1.3 x L3; with an unknown L3 a 256 MB ring (never in the first regime).
   // SMM_HOST_L3_MB, SMM_HOST_WIDEN_SUB (units per chunk) and SMM_HOST_RING_MB override.
-  static const size_t l3_bytes = host_l3_bytes();
+  // The regimes were measured on a part with one large shared L3.  A small reported L3 usually means a cache per core
+  // complex (several of them behind the widening threads, i.e. an aggregate the sizing cannot see): keep the 256 MB ring there.
+  static const size_t l3_detected = host_l3_bytes();
+  const size_t l3_bytes = l3_detected >= ((size_t)48 << 20) || getenv("SMM_HOST_L3_MB") ? l3_detected : 0;
   int kSub = 4;
   if (l3_bytes) {
     const size_t want = std::max<size_t>(1, (size_t)(0.7 * (double)l3_bytes) / (per_real * 4));
