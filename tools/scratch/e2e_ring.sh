@@ -1,8 +1,8 @@
 #!/bin/bash
-run() { echo -n "$* : "; env "$@" SMM_E2E_DEBUG=1 python bench.py --no-extra --steps 4 --warmup 2 2> gpurun_out/ring.err | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('e2e ms', round(d['e2e']['ms_per_step'],2), end='  ')"; grep "widen pipeline" gpurun_out/ring.err | tail -1; }
+run() { echo -n "$* : "; env "$@" SMM_E2E_DEBUG=1 python bench.py --no-extra --steps 5 --warmup 3 2> gpurun_out/ring.err | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('e2e ms', round(d['e2e']['ms_per_step'],2), end='  ')"; grep "widen pipeline" gpurun_out/ring.err | tail -1; }
 run DEFAULT=1
+run SMM_HOST_WIDEN_SUB=3
+run SMM_HOST_WIDEN_SUB=5
+run DEFAULT=1
+run SMM_HOST_WIDEN_SUB=3
 run SMM_HOST_L3_MB=0
-run SMM_HOST_L3_MB=105
-run DEFAULT=1
-run SMM_HOST_L3_MB=30
-python -m pytest tests/test_abm_gpu.py -x -q -m gpu -k "chunked or ensemble or multi_gpu" 2>&1 | tail -1
