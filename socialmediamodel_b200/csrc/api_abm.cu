@@ -566,8 +566,9 @@ static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precisio
   //  * ring 1.1-1.4 x L3 (two slots of 32-43 realizations): 23.5-25 -- old lines are gone before they are rewritten, and the
   //    widening threads still find part of a freshly copied unit in the cache;
   //  * ring 2-4 x L3 (or 256 MB in 8-32 slots of any size): 26-30 -- everything the widening reads comes from DRAM.
-  // Hence units of 0.55 x L3 in a ring of at least the L3 size (two slots of 32 realizations here: on the slower boxes of the
-  // pool 29.8 against 31-33 for two slots of 43); with an unknown L3 a 256 MB ring (never in the first regime).
+  // Hence units of 0.55 x L3 in a ring of at least 1.3 x L3 (three slots of 32 realizations here: 24.2-24.5, the same as two
+  // slots, with more distance to the first regime; on the slower boxes of the pool units of 32 gave 29.8 against 31-33 for
+  // units of 43); with an unknown L3 a 256 MB ring (never in the first regime).
   // SMM_HOST_L3_MB, SMM_HOST_WIDEN_SUB (units per chunk) and SMM_HOST_RING_MB override.
   // The regimes were measured on a part with one large shared L3.  A small reported L3 usually means a cache per core
   // complex (several of them behind the widening threads, i.e. an aggregate the sizing cannot see): keep the 256 MB ring there.
@@ -583,7 +584,7 @@ static int abm_ensemble_impl(smm_ctx* ctx, const smm_params* q, int32_t precisio
   int ring_slots = 2;
   if (host_widen) {
     const size_t unit_bytes = unit_real * per_real * 4;
-    size_t ring_min = l3_bytes ? l3_bytes : (size_t)256 << 20;
+    size_t ring_min = l3_bytes ? (size_t)(1.3 * (double)l3_bytes) : (size_t)256 << 20;
     if (const char* e = getenv("SMM_HOST_RING_MB")) ring_min = (size_t)std::max(0, atoi(e)) << 20;
     ring_slots = (int)std::min<size_t>(32, std::max<size_t>(2, (ring_min + unit_bytes - 1) / unit_bytes));
     for (int i = 0; i < ring_slots; i++)
