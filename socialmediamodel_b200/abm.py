@@ -119,9 +119,13 @@ def ABMsolve(NT=100, *, p=None, q=None, init="4inf", chosenseed=0, precision="f3
         init_state = dict(x0=x0, state=state, follow0=follow0, inf0=inf0, media0=media0)
     out = abm_solve_raw(NT, p=p, q=q, R=1, seed=chosenseed, precision=precision, init_state=init_state,
                         injected=injected, network=network, ctx=ctx)
-    xs = [np.ascontiguousarray(out["xs"][:, :, k, 0]) for k in range(NT + 1)]
-    stateinfs = [out["follows"][:, k, 0].astype(np.float64) + 1.0 for k in range(NT + 1)]
-    infs = [np.ascontiguousarray(out["infs"][:, :, k, 0]) for k in range(NT + 1)]
-    meds = [np.ascontiguousarray(out["meds"][:, :, k, 0]) for k in range(NT + 1)]
+    # lists of per-step matrices as the reference returns them; the entries are column-major views of the history arrays
+    # (Julia's layout), the follower ids are widened once for all steps
+    X, I, Md = out["xs"][:, :, :, 0], out["infs"][:, :, :, 0], out["meds"][:, :, :, 0]
+    F = np.asfortranarray(out["follows"][:, :, 0].astype(np.float64) + 1.0)
+    xs = [X[:, :, k] for k in range(NT + 1)]
+    stateinfs = [F[:, k] for k in range(NT + 1)]
+    infs = [I[:, :, k] for k in range(NT + 1)]
+    meds = [Md[:, :, k] for k in range(NT + 1)]
     state = np.asarray(init_state["state"]).reshape(-1).astype(np.int64)
     return xs, stateinfs, infs, meds, state, (p, q)
